@@ -1,0 +1,459 @@
+"""CPU oracle for the KeystoneML block least-squares hot path (numpy, IEEE fp64).
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product path (``keystone_b200/``) may import
+this module; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs use it, and only as the checker / the timed CPU stand-in.
+
+Every function restates one reference function and cites it (paths are relative to
+``/root/reference/src/main/scala/keystoneml`` = ``K/`` and ``src/test/scala/keystoneml`` =
+``T/``).  The reference itself (Scala 2.10 + Spark 2.1 + Breeze 0.12 + mlmatrix 0.2) cannot
+be compiled or imported in this image (no JVM), so there is no ``oracle/_ref``.
+
+Pinning status
+--------------
+* ``bwls_fit`` / ``per_class_wls_fit`` / ``compute_gradient``: PINNED by the reference's own
+  fixtures ``src/test/resources/{aMat,bMat,aMat-1class,bMat-1class}.csv`` and the
+  assertions of ``T/nodes/learning/BlockWeightedLeastSquaresSuite.scala`` (see
+  ``tests/test_oracle_golden.py``).
+* ``standard_scaler_*``: PINNED by the golden rows of ``T/nodes/stats/StandardScalerSuite.scala``.
+* ``cosine_random_features``, ``vector_splitter``, ``block_linear_apply``,
+  ``linear_map_fit``: PINNED by the formula / known-answer tests of the matching suites.
+* ``block_ls_fit``: **parity unpinned** at the mlmatrix boundary.  Its arithmetic lives in
+  the un-vendored dependency ``edu.berkeley.cs.amplab:mlmatrix:0.2`` (``build.sbt:44``) and
+  no reference test pins its numerical output.  It restates the published algorithm of
+  ``BlockCoordinateDescent.solveOnePassL2`` / ``solveLeastSquaresWithL2`` with
+  ``NormalEquations`` (per block: tree-summed ``(A_j^T A_j, A_j^T r)``, then
+  ``(A_j^T A_j + lambda I) \\ A_j^T r``, lambda un-scaled, sequential block order) and is
+  anchored on the call site ``K/nodes/learning/BlockLinearMapper.scala:212-243`` plus the
+  invariants checked in ``tests/test_oracle_golden.py`` (nb=1 == closed-form centred ridge
+  == ``LinearMapEstimator``; many sweeps converge to the same; LinearMapperSuite known answer).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+F64 = np.float64
+
+
+# --------------------------------------------------------------------------------------
+# a1  VectorSplitter            K/nodes/util/VectorSplitter.scala:15-35
+# --------------------------------------------------------------------------------------
+def block_bounds(num_features: int, block_size: int) -> List[Tuple[int, int]]:
+    """[start, end) of each feature block; nb = ceil(D / blockSize), last block ragged
+    (VectorSplitter.scala:16-22)."""
+    nb = int(math.ceil(num_features / float(block_size)))
+    return [(j * block_size, min(num_features, (j + 1) * block_size)) for j in range(nb)]
+
+
+def vector_splitter(x: np.ndarray, block_size: int, num_features: Optional[int] = None) -> List[np.ndarray]:
+    """Split rows (N x D) or one vector (D) into column blocks (VectorSplitter.scala:15-35).
+    ``num_features`` mirrors ``numFeaturesOpt`` (overrides D)."""
+    x = np.asarray(x, dtype=F64)
+    d = x.shape[-1] if num_features is None else int(num_features)
+    return [np.array(x[..., s:e], dtype=F64, copy=True) for s, e in block_bounds(d, block_size)]
+
+
+# --------------------------------------------------------------------------------------
+# a2  StandardScaler            K/nodes/stats/StandardScaler.scala:25-59
+# --------------------------------------------------------------------------------------
+def standard_scaler_fit(data: np.ndarray, normalize_std_dev: bool = True, eps: float = 1e-12):
+    """Column mean and (optionally) sample (n-1) std with the ``<eps -> 1.0`` guard
+    (StandardScaler.scala:45-59; MLlib MultivariateOnlineSummarizer.variance is unbiased)."""
+    data = np.asarray(data, dtype=F64)
+    mean = data.mean(axis=0)
+    if not normalize_std_dev:
+        return mean, None
+    n = data.shape[0]
+    var = ((data - mean) ** 2).sum(axis=0) / (n - 1) if n > 1 else np.zeros_like(mean)
+    std = np.sqrt(var)
+    bad = np.isnan(std) | np.isinf(std) | (np.abs(std) < eps)
+    std = np.where(bad, 1.0, std)
+    return mean, std
+
+
+def standard_scaler_apply(x: np.ndarray, mean: np.ndarray, std: Optional[np.ndarray] = None) -> np.ndarray:
+    """``(in - mean) [/ std]`` (StandardScaler.scala:25-31)."""
+    out = np.asarray(x, dtype=F64) - mean
+    if std is not None:
+        out = out / std
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# a4  CosineRandomFeatures      K/nodes/stats/CosineRandomFeatures.scala:25-60
+# --------------------------------------------------------------------------------------
+def cosine_random_features(x: np.ndarray, W: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """``cos(X W^T + b)``; W is (n_out x n_in), b is (n_out) (CosineRandomFeatures.scala:30-32, 38-43)."""
+    x = np.asarray(x, dtype=F64)
+    return np.cos(x @ np.asarray(W, dtype=F64).T + np.asarray(b, dtype=F64))
+
+
+def cosine_random_features_params(n_in: int, n_out: int, gamma: float, rng: np.random.Generator,
+                                  w_dist: str = "gaussian") -> Tuple[np.ndarray, np.ndarray]:
+    """Factory (CosineRandomFeatures.scala:51-60): ``W = gamma * rand(n_out x n_in, wDist)``,
+    ``b = 2*pi * uniform(n_out)``.  Breeze's RNG stream cannot be reproduced without a JVM, so
+    parity runs always share the *arrays*, never a seed."""
+    if w_dist == "gaussian":
+        W = rng.standard_normal((n_out, n_in))
+    elif w_dist == "cauchy":
+        W = rng.standard_cauchy((n_out, n_in))
+    else:
+        raise ValueError(w_dist)
+    return W * gamma, rng.random(n_out) * (2.0 * math.pi)
+
+
+# --------------------------------------------------------------------------------------
+# label helpers (K/nodes/util/ClassLabelIndicators.scala:15-29, MaxClassifier.scala:9-11)
+# --------------------------------------------------------------------------------------
+def class_label_indicators(labels: np.ndarray, num_classes: int) -> np.ndarray:
+    """+1 at the class index, -1 elsewhere."""
+    y = -np.ones((len(labels), num_classes), dtype=F64)
+    y[np.arange(len(labels)), np.asarray(labels, dtype=np.int64)] = 1.0
+    return y
+
+
+def max_classifier(scores: np.ndarray) -> np.ndarray:
+    return np.argmax(np.asarray(scores), axis=-1)
+
+
+# --------------------------------------------------------------------------------------
+# a5/a6  BlockLeastSquaresEstimator.fit   K/nodes/learning/BlockLinearMapper.scala:212-243
+#        (+ mlmatrix 0.2 BlockCoordinateDescent / NormalEquations, restated; parity unpinned)
+# --------------------------------------------------------------------------------------
+def _solve_spd(G: np.ndarray, C: np.ndarray) -> np.ndarray:
+    """Breeze ``\\`` on a square system is LAPACK dgesv (LU); numpy.linalg.solve is the same routine."""
+    return np.linalg.solve(G, C)
+
+
+def block_ls_fit(features: np.ndarray, labels: np.ndarray, block_size: int, num_iter: int,
+                 lam: float = 0.0, num_features: Optional[int] = None,
+                 feature_blocks: Optional[Sequence[np.ndarray]] = None):
+    """Ridge regression by block coordinate descent on mean-centred features and labels.
+
+    BlockLinearMapper.scala:215-219  labels centred by their column mean (the intercept)
+    BlockLinearMapper.scala:224-232  every feature block centred by its own column mean
+    BlockLinearMapper.scala:234-240  numIter == 1 -> one Gauss-Seidel sweep from x = 0
+                                     (solveOnePassL2); numIter > 1 -> cyclic sweeps
+                                     (solveLeastSquaresWithL2); lambda passed un-scaled
+    BlockLinearMapper.scala:242      returns (xs, blockSize, Some(labelMean), Some(featureScalers))
+
+    Returns ``(xs, intercept, feature_means)`` with xs[j] of shape (b_j, k).
+    """
+    labels = np.asarray(labels, dtype=F64)
+    if feature_blocks is None:
+        feature_blocks = vector_splitter(features, block_size, num_features)
+    y_mean = labels.mean(axis=0)
+    resid = labels - y_mean                          # b  (RowPartitionedMatrix of centred labels)
+    means = [blk.mean(axis=0) for blk in feature_blocks]
+    k = labels.shape[1]
+    xs = [np.zeros((blk.shape[1], k), dtype=F64) for blk in feature_blocks]
+    grams: List[Optional[np.ndarray]] = [None] * len(feature_blocks)
+    for it in range(max(1, num_iter)):
+        for j, blk in enumerate(feature_blocks):     # sequential block order (see module docstring)
+            A = blk - means[j]
+            if grams[j] is None:
+                grams[j] = A.T @ A                   # cached across sweeps
+            G = grams[j]
+            # A_j^T (b - sum_{i != j} A_i x_i) = A_j^T resid + G x_j
+            rhs = A.T @ resid + G @ xs[j]
+            x_new = _solve_spd(G + lam * np.eye(G.shape[0]), rhs)
+            resid -= A @ (x_new - xs[j])
+            xs[j] = x_new
+    return xs, y_mean, means
+
+
+# --------------------------------------------------------------------------------------
+# a8  BlockLinearMapper.apply   K/nodes/learning/BlockLinearMapper.scala:40-87
+# a9  LinearMapper.apply        K/nodes/learning/LinearMapper.scala:30-62
+# --------------------------------------------------------------------------------------
+def block_linear_apply(features: np.ndarray, xs: Sequence[np.ndarray], block_size: int,
+                       intercept: Optional[np.ndarray] = None,
+                       feature_means: Optional[Sequence[np.ndarray]] = None,
+                       return_partials: bool = False):
+    """``sum_j (x_j - mu_j) W_j + b``.  With ``return_partials`` also returns the cumulative
+    sum (+ intercept) after every block, i.e. what ``applyAndEvaluate`` hands its callback
+    (BlockLinearMapper.scala:117-135)."""
+    features = np.asarray(features, dtype=F64)
+    d = sum(x.shape[0] for x in xs)
+    blocks = vector_splitter(features, block_size, d)
+    out = None
+    partials = []
+    for j, (blk, x) in enumerate(zip(blocks, xs)):
+        if feature_means is not None:
+            blk = blk - feature_means[j]
+        part = blk @ x
+        out = part if out is None else out + part
+        if return_partials:
+            partials.append(out + intercept if intercept is not None else out.copy())
+    if intercept is not None:
+        out = out + intercept
+    return (out, partials) if return_partials else out
+
+
+def linear_mapper_apply(x_in: np.ndarray, x: np.ndarray, b: Optional[np.ndarray] = None,
+                        mean: Optional[np.ndarray] = None) -> np.ndarray:
+    """``x^T (in - mean) + b`` (LinearMapper.scala:30-37, 44-62)."""
+    x_in = np.asarray(x_in, dtype=F64)
+    if mean is not None:
+        x_in = x_in - mean
+    out = x_in @ x
+    return out + b if b is not None else out
+
+
+def linear_map_fit(features: np.ndarray, labels: np.ndarray, lam: Optional[float] = None):
+    """LinearMapEstimator.fit (LinearMapper.scala:80-98): exact normal equations on centred data,
+    intercept = label mean, returns the feature scaler mean too."""
+    features = np.asarray(features, dtype=F64)
+    labels = np.asarray(labels, dtype=F64)
+    mu = features.mean(axis=0)
+    ymu = labels.mean(axis=0)
+    A = features - mu
+    G = A.T @ A
+    if lam is not None:
+        G = G + lam * np.eye(G.shape[0])
+    x = _solve_spd(G, A.T @ (labels - ymu))
+    return x, ymu, mu
+
+
+# --------------------------------------------------------------------------------------
+# a10  computeCost              K/nodes/learning/BlockLinearMapper.scala:142-187
+# --------------------------------------------------------------------------------------
+def compute_cost(features: np.ndarray, labels: np.ndarray, lam: float, xs: Sequence[np.ndarray],
+                 block_size: int, intercept: Optional[np.ndarray] = None) -> float:
+    """``||A W + b - Y||_F^2 / (2N) + lambda/2 ||W||_F^2`` -- note: no feature centring and
+    lambda un-scaled (BlockLinearMapper.scala:149-185)."""
+    labels = np.asarray(labels, dtype=F64)
+    axb = block_linear_apply(features, xs, block_size, intercept, None)
+    cost = float(((axb - labels) ** 2).sum())
+    n = labels.shape[0]
+    if lam == 0:
+        return cost / (2.0 * n)
+    wnorm = float(sum((x ** 2).sum() for x in xs))
+    return cost / (2.0 * n) + lam / 2.0 * wnorm
+
+
+# --------------------------------------------------------------------------------------
+# a7  BlockWeightedLeastSquaresEstimator.trainWithL2
+#     K/nodes/learning/BlockWeightedLeastSquares.scala:102-321  (all arithmetic in-repo)
+# --------------------------------------------------------------------------------------
+def group_by_classes(labels: np.ndarray) -> List[np.ndarray]:
+    """Row-index partitions, one class per partition, class c in partition c
+    (groupByClasses, BlockWeightedLeastSquares.scala:333-370: HashPartitioner(nClasses) on the
+    argmax class index, original order kept inside a partition).  Classes with no rows yield
+    empty partitions."""
+    labels = np.asarray(labels, dtype=F64)
+    cls = np.argmax(labels, axis=1)
+    return [np.nonzero(cls == c)[0] for c in range(labels.shape[1])]
+
+
+def _needs_reshuffle(labels: np.ndarray, partitions: Sequence[np.ndarray]) -> bool:
+    """BlockWeightedLeastSquares.scala:111-124."""
+    class_of = []
+    for idx in partitions:
+        if len(idx) == 0:
+            # mapPartitions on an empty iterator: distinct.length == 0 != 1 -> "not same class"
+            return True
+        cls = np.unique(np.argmax(labels[idx], axis=1))
+        if len(cls) != 1:
+            return True
+        class_of.append(int(cls[0]))
+    return len(set(class_of)) != len(class_of)
+
+
+def bwls_fit(features: np.ndarray, labels: np.ndarray, block_size: int, num_iter: int, lam: float,
+             mixture_weight: float, num_features: Optional[int] = None,
+             partitions: Optional[Sequence[np.ndarray]] = None):
+    """Line-by-line restatement of ``trainWithL2``.  ``partitions`` (list of row-index arrays)
+    plays the role of the RDD partitioning; by default -- and whenever the one-class-per-
+    partition precondition fails (:111-131) -- rows are regrouped by class.
+
+    Returns ``(xs, final_b)``; the mapper has no feature scalers (:316-320).
+    """
+    features = np.asarray(features, dtype=F64)
+    labels = np.asarray(labels, dtype=F64)
+    w = float(mixture_weight)
+    if partitions is None or _needs_reshuffle(labels, partitions):
+        partitions = group_by_classes(labels)
+    parts = [np.asarray(p) for p in partitions if len(p) > 0]   # rowsToMatrixIter skips empties
+    class_idxs = [int(np.argmax(labels[p[0]])) for p in parts]  # :133-139
+    n_train = int(sum(len(p) for p in parts))                   # labels.count  :141
+    n_classes = labels.shape[1]                                  # :142
+    d = features.shape[1] if num_features is None else int(num_features)
+    bounds = block_bounds(d, block_size)
+    nb = len(bounds)
+
+    joint_label_mean = np.zeros(n_classes, dtype=F64)            # :148-156
+    for p, c in zip(parts, class_idxs):
+        joint_label_mean[c] = 2 * w + (2 * (1.0 - w) * len(p) / float(n_train)) - 1
+
+    models = [np.zeros((e - s, n_classes), dtype=F64) for s, e in bounds]
+    residual = [labels[p] - joint_label_mean for p in parts]    # :167-169
+    residual_mean = np.concatenate(residual, axis=0).mean(axis=0)  # :171
+    stats: List[Optional[dict]] = [None] * nb
+
+    for it in range(num_iter):
+        for blk in range(nb):                                    # sequential order :180
+            s, e = bounds[blk]
+            feats = [features[p, s:e] for p in parts]            # blockFeaturesMat per partition
+            if it == 0:
+                pop_mean = np.concatenate(feats, axis=0).mean(axis=0)            # :197
+                joint_means_parts = [f.mean(axis=0) * w + pop_mean * (1.0 - w) for f in feats]  # :201-204
+                joint_means = np.zeros((n_classes, e - s), dtype=F64)           # :206-210
+                for jm, c in zip(joint_means_parts, class_idxs):
+                    joint_means[c, :] = jm
+                ata = sum(f.T @ f for f in feats)                                # :212-214
+                atr = sum(f.T @ r for f, r in zip(feats, residual))
+                pop_cov = ata / float(n_train) - np.outer(pop_mean, pop_mean)    # :216
+                pop_xtr = atr / float(n_train)                                   # :221
+                stats[blk] = dict(pop_cov=pop_cov, pop_mean=pop_mean, joint_mean=joint_means,
+                                  joint_means_parts=joint_means_parts)
+            else:
+                atr = sum(f.T @ r for f, r in zip(feats, residual))              # :223-225
+                st = stats[blk]
+                pop_cov, pop_mean = st["pop_cov"], st["pop_mean"]
+                joint_means_parts = st["joint_means_parts"]
+                pop_xtr = atr / float(n_train)
+
+            delta = np.zeros_like(models[blk])
+            for f, r, jm, c in zip(feats, residual, joint_means_parts, class_idxs):   # :241-276
+                res_local = r[:, c]
+                n_pos = f.shape[0]
+                class_mean = f.mean(axis=0)
+                zm = f - class_mean
+                class_cov = (zm.T @ zm) / float(n_pos)
+                class_xtr = (f.T @ res_local) / float(n_pos)
+                mean_diff = class_mean - pop_mean
+                joint_xtx = (pop_cov * (1.0 - w) + class_cov * w
+                             + np.outer(mean_diff, mean_diff) * (1.0 - w) * w)
+                mean_mixture_wt = residual_mean[c] * (1.0 - w) + w * res_local.mean()
+                joint_xtr = pop_xtr[:, c] * (1.0 - w) + class_xtr * w - jm * mean_mixture_wt
+                nd = joint_xtx.shape[1]
+                W = _solve_spd(joint_xtx + np.eye(nd) * lam, joint_xtr - models[blk][:, c] * lam)
+                delta[:, c] = W
+            models[blk] = models[blk] + delta                                    # :278-284
+            residual = [r - f @ delta for f, r in zip(feats, residual)]          # :287-294
+            residual_mean = np.concatenate(residual, axis=0).mean(axis=0)        # :296
+
+    full = np.concatenate(models, axis=0)                                        # :314
+    jm_comb = np.concatenate([st["joint_mean"] for st in stats], axis=1)         # :315
+    final_b = joint_label_mean - (jm_comb.T * full).sum(axis=0)                  # :316
+    return models, final_b
+
+
+# --------------------------------------------------------------------------------------
+# Cross-check solver: PerClassWeightedLeastSquaresEstimator
+#   K/nodes/learning/PerClassWeightedLeastSquares.scala:65-222
+#   K/nodes/learning/internal/ReWeightedLeastSquares.scala:36-141
+# --------------------------------------------------------------------------------------
+def _reweighted_ls(blocks: Sequence[np.ndarray], labels_zm: np.ndarray, weights: np.ndarray,
+                   feature_mean: np.ndarray, bounds, num_iter: int, lam: float) -> List[np.ndarray]:
+    """ReWeightedLeastSquaresSolver.trainWithL2 for one class (numClasses = 1)."""
+    n = labels_zm.shape[0]
+    residual = np.zeros((n, 1), dtype=F64)
+    model = [np.zeros((e - s, 1), dtype=F64) for s, e in bounds]
+    ata_cache: List[Optional[np.ndarray]] = [None] * len(bounds)
+    wcol = weights.reshape(-1, 1)
+    for it in range(num_iter):
+        for blk, (s, e) in enumerate(bounds):
+            a_zm = blocks[blk] - feature_mean[s:e]
+            if it == 0:
+                ata_cache[blk] = a_zm.T @ (a_zm * wcol)                          # :92-99
+            xw_old = a_zm @ model[blk]
+            res_updated = residual - xw_old * wcol                                # :114-116
+            atb = a_zm.T @ (labels_zm * wcol - res_updated)                       # :118-119
+            new_model = _solve_spd(ata_cache[blk] + np.eye(e - s) * lam, atb)    # :123
+            residual = residual + (a_zm @ (new_model - model[blk])) * wcol       # :129-134
+            model[blk] = new_model
+    return model
+
+
+def per_class_wls_fit(features: np.ndarray, labels: np.ndarray, block_size: int, num_iter: int,
+                      lam: float, mixture_weight: float, num_features: Optional[int] = None):
+    """PerClassWeightedLeastSquaresEstimator.trainWithL2 (:65-124)."""
+    features = np.asarray(features, dtype=F64)
+    labels = np.asarray(labels, dtype=F64)
+    w = float(mixture_weight)
+    n_classes = labels.shape[1]
+    d = features.shape[1] if num_features is None else int(num_features)
+    n = labels.shape[0]
+    cls = np.argmax(labels, axis=1)
+    pop_mean = features[:, :d].sum(axis=0) / float(n)                              # :78-81
+    counts = np.array([(cls == c).sum() for c in range(n_classes)], dtype=np.int64)   # :136-142
+    jfm = np.zeros((n_classes, d), dtype=F64)
+    present = [c for c in range(n_classes) if counts[c] > 0]
+    for c in present:                                                             # :150-165
+        cm = features[cls == c, :d].sum(axis=0) / float(counts[c])
+        jfm[c] = cm * w + pop_mean * (1.0 - w)
+    neg_wt = (1.0 - w) / float(n)                                                 # :176-183
+    weights = np.full((n, n_classes), neg_wt, dtype=F64)
+    weights[np.arange(n), cls] += w / counts[cls].astype(F64)
+    joint_label_mean = (counts / float(n)) * (2.0 * (1.0 - w)) - 1.0 + 2.0 * w   # :188-194
+    labels_zm = labels - joint_label_mean
+    bounds = block_bounds(d, block_size)
+    blocks = [features[:, s:e] for s, e in bounds]
+    # jfmMat = rows of jointFeatureMean sorted by key: only classes that occur (:85)
+    xs = [np.zeros((e - s, n_classes), dtype=F64) for s, e in bounds]
+    for c in present:   # classes without rows keep a zero model column
+        cm = jfm[c]
+        model = _reweighted_ls(blocks, labels_zm[:, [c]], weights[:, c], cm, bounds, num_iter, lam)
+        for blk in range(len(bounds)):
+            xs[blk][:, c] = model[blk][:, 0]
+    full = np.concatenate(xs, axis=0)
+    final_b = joint_label_mean - (jfm.T * full).sum(axis=0)                       # :119
+    return xs, final_b
+
+
+# --------------------------------------------------------------------------------------
+# Gradient oracle of the weighted objective
+#   T/nodes/learning/BlockWeightedLeastSquaresSuite.scala:19-61
+# --------------------------------------------------------------------------------------
+def compute_gradient(features: np.ndarray, labels: np.ndarray, lam: float, mixture_weight: float,
+                     x: np.ndarray, b: np.ndarray, partitions: Optional[Sequence[np.ndarray]] = None) -> np.ndarray:
+    """Per partition (= class): weights negWt everywhere, posWt in the class column, where the
+    class is read from the partition's first label row (:32-41); grad = sum A^T((A x + b - Y) .* wts)
+    + lambda x (:47-60)."""
+    features = np.asarray(features, dtype=F64)
+    labels = np.asarray(labels, dtype=F64)
+    if partitions is None:
+        partitions = group_by_classes(labels)
+    parts = [np.asarray(p) for p in partitions if len(p) > 0]
+    n_train = int(sum(len(p) for p in parts))
+    grad = np.zeros_like(x)
+    for p in parts:
+        lab = labels[p]
+        feats = features[p]
+        c = int(np.argmax(lab[0]))
+        neg = (1.0 - mixture_weight) / float(n_train)
+        pos = neg + mixture_weight / float(len(p))
+        wts = np.full(lab.shape, neg, dtype=F64)
+        wts[:, c] = pos
+        out = feats @ x + b - lab
+        grad += feats.T @ (out * wts)
+    return grad + x * lam
+
+
+# --------------------------------------------------------------------------------------
+# Multi-partition restatement used by the sharding tests: the same BlockLS fit computed from
+# per-shard partial sums only (what the GPU path all-reduces).  Algebra of DESIGN.md section 4.
+# --------------------------------------------------------------------------------------
+def block_ls_partial_sums(A_shift: np.ndarray, R: np.ndarray):
+    """Per-shard contribution for one block: ``A^T A``, ``A^T R``, column sums of A and of R,
+    where ``A_shift = A - shift`` for a shift vector shared by all shards."""
+    return A_shift.T @ A_shift, A_shift.T @ R, A_shift.sum(axis=0), R.sum(axis=0)
+
+
+def block_ls_solve_from_sums(G, C, sa, sr, n_total: int, lam: float, w_old: Optional[np.ndarray] = None):
+    """Exact centring correction from reduced sums: with delta = sa / N (mean of the shifted
+    block) and rbar = sr / N,  G_c = G - N delta delta^T,  C_c = C - N delta rbar^T, then the
+    BCD step  dW = (G_c + lam I)^-1 (C_c - lam W_old)."""
+    delta = sa / float(n_total)
+    rbar = sr / float(n_total)
+    Gc = G - n_total * np.outer(delta, delta)
+    Cc = C - n_total * np.outer(delta, rbar)
+    if w_old is not None:
+        Cc = Cc - lam * w_old
+    dW = _solve_spd(Gc + lam * np.eye(G.shape[0]), Cc)
+    return dW, delta
