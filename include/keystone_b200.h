@@ -1,0 +1,162 @@
+/* keystone_b200 -- C ABI of the B200-native block least-squares engine.
+ *
+ * Drop-in boundary for the KeystoneML (amplab/keystone) node bodies on the block-LS hot path.
+ * Every entry point names the reference interface it replaces (paths relative to
+ * /root/reference; K/ = src/main/scala/keystoneml/).  The reference reaches native code
+ * through JNI with primitives and primitive arrays only (K/utils/external/VLFeat.scala:18-26,
+ * src/main/cpp/VLFeat.cxx:203); this ABI keeps that shape: plain pointers, sizes and opaque
+ * 64-bit handles (1:1 with a JVM Long).  INTEGRATION.md shows the JNI / ctypes bindings.
+ *
+ * Process model: ONE process (context) per GPU.  A row-sharded dataset is represented by every
+ * rank holding a matrix handle for ITS rows (the analogue of an RDD partition set); reductions
+ * that Spark does with treeReduce (K/nodes/learning/BlockWeightedLeastSquares.scala:212-225,
+ * K/utils/MatrixUtils.scala:137-146) are NCCL all-reduces inside the fit calls, so every rank
+ * must call the same collective entry points in the same order.
+ *
+ * Conventions
+ *   - every function returns 0 on success, < 0 on error; ks_last_error() gives the message.
+ *     Nothing calls exit() or throws across the boundary (the reference's JNI code does
+ *     exit(-1), src/main/cpp/EncEval.cxx:43-47).
+ *   - host buffers are caller-owned and only borrowed for the duration of the call;
+ *     device objects are library-owned and released by the matching *_destroy.
+ *   - a context is not thread-safe (same contract as Pipeline / GraphExecutor,
+ *     K/workflow/Pipeline.scala:14).
+ *   - dense host matrices are row-major with an explicit leading dimension, except where a
+ *     parameter says "colmajor": those are Breeze DenseMatrix[Double] layouts (column-major),
+ *     so a JVM caller can pass DenseMatrix.data unchanged.
+ *   - there is NO CPU fallback: without a CUDA device ks_ctx_create fails.
+ */
+#ifndef KEYSTONE_B200_H
+#define KEYSTONE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define KS_API __attribute__((visibility("default")))
+#else
+#define KS_API
+#endif
+
+#define KS_OK 0
+#define KS_ERR_INVALID (-1)
+#define KS_ERR_CUDA (-2)
+#define KS_ERR_NCCL (-3)
+#define KS_ERR_SOLVER (-4)
+#define KS_ERR_NO_DEVICE (-5)
+#define KS_ERR_HANDLE (-6)
+#define KS_ERR_NOT_SPD (-7)
+
+/* precision_mode of the fit/apply entry points */
+#define KS_PRECISION_TF32 0  /* operands rounded to tf32 (round-to-nearest), fp32 accumulate, fp64 solve */
+
+#define KS_NCCL_ID_BYTES 128
+
+KS_API int32_t ks_version(void);
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+/* Rank 0 creates the NCCL unique id; the host runtime (Spark driver / torch.distributed / MPI)
+ * ships the 128 bytes to the other ranks. */
+KS_API int32_t ks_nccl_unique_id(uint8_t* out_id /* KS_NCCL_ID_BYTES */);
+/* world_size == 1: nccl_id may be NULL and no communicator is created. */
+KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size, const uint8_t* nccl_id, int64_t* out_ctx);
+KS_API int32_t ks_ctx_destroy(int64_t ctx);
+KS_API const char* ks_last_error(int64_t ctx);
+KS_API int32_t ks_ctx_synchronize(int64_t ctx);
+/* tunables: "gram_chunk_rows", "sample_rows" */
+KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value);
+
+/* ---- row-sharded matrices (this rank's rows) ---------------------------------------------
+ * Replace RDD[DenseVector[Double]] + MatrixUtils.rowsToMatrix packing
+ * (K/utils/MatrixUtils.scala:48-93).  Stored on device as fp32 row-major, 128 B aligned rows. */
+KS_API int32_t ks_matrix_from_host_f64(int64_t ctx, const double* rowmajor, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                int64_t* out_m);
+KS_API int32_t ks_matrix_from_host_f32(int64_t ctx, const float* rowmajor, int64_t n_rows, int64_t n_cols, int64_t ld,
+                                int64_t* out_m);
+/* iid N(mean, stddev) generated on the device (benchmarks; counter-based, reproducible per (seed,row,col)). */
+KS_API int32_t ks_matrix_synthetic_normal(int64_t ctx, int64_t n_rows, int64_t n_cols, uint64_t seed, int64_t global_row_offset,
+                                   double mean, double stddev, int64_t* out_m);
+/* ClassLabelIndicatorsFromIntLabels (K/nodes/util/ClassLabelIndicators.scala:15-29): +1 / -1 indicators. */
+KS_API int32_t ks_labels_from_classes(int64_t ctx, const int32_t* classes, int64_t n_rows, int32_t num_classes, int64_t* out_m);
+KS_API int32_t ks_matrix_shape(int64_t ctx, int64_t m, int64_t* n_rows, int64_t* n_cols);
+KS_API int32_t ks_matrix_to_host_f64(int64_t ctx, int64_t m, double* rowmajor_out, int64_t ld);
+KS_API int32_t ks_matrix_to_host_f32(int64_t ctx, int64_t m, float* rowmajor_out, int64_t ld);
+KS_API int32_t ks_matrix_destroy(int64_t ctx, int64_t m);
+
+/* ---- CosineRandomFeatures (K/nodes/stats/CosineRandomFeatures.scala:19-44) ----------------
+ * W is (n_out x n_in) COLUMN-major fp64 exactly as Breeze stores it, b has n_out entries. */
+KS_API int32_t ks_cosine_rf_create(int64_t ctx, const double* W_colmajor, const double* b, int64_t n_out, int64_t n_in,
+                            int64_t* out_rf);
+/* apply(RDD) :25-36 -- materialises cos(X W^T + b) as a new (N x n_out) matrix. */
+KS_API int32_t ks_cosine_rf_apply(int64_t ctx, int64_t rf, int64_t x_in, int64_t* out_features);
+KS_API int32_t ks_cosine_rf_destroy(int64_t ctx, int64_t rf);
+
+/* ---- feature source shared by fit / apply -------------------------------------------------
+ * Either `features` (a materialised N x D matrix; VectorSplitter blocks are column ranges of it,
+ * K/nodes/util/VectorSplitter.scala:15-25) or `x_in` + `rfs[n_rfs]` (the gather of
+ * CosineRandomFeatures nodes followed by VectorCombiner, K/pipelines/speech/TimitPipeline.scala:76-93),
+ * whose feature blocks are regenerated on the fly and never stored.  Pass 0 for the unused one. */
+
+/* BlockLeastSquaresEstimator(blockSize, numIter, lambda, numFeaturesOpt).fit(features, labels)
+ * (K/nodes/learning/BlockLinearMapper.scala:199-257).  Collective across ranks. */
+KS_API int32_t ks_blockls_fit(int64_t ctx, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, int64_t labels,
+                       int32_t block_size, int32_t num_iter, double lambda, int64_t num_features_or_0,
+                       int32_t precision_mode, int64_t* out_model);
+/* BlockWeightedLeastSquaresEstimator(blockSize, numIter, lambda, mixtureWeight, numFeaturesOpt).fit
+ * (K/nodes/learning/BlockWeightedLeastSquares.scala:36-84, trainWithL2 :102-321).  Rows need not be
+ * class-sorted (groupByClasses :333-370 is applied on the device).  Single-rank in this version. */
+KS_API int32_t ks_blockwls_fit(int64_t ctx, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, int64_t labels,
+                        int32_t block_size, int32_t num_iter, double lambda, double mixture_weight,
+                        int64_t num_features_or_0, int32_t precision_mode, int64_t* out_model);
+/* LinearMapEstimator(lambda).fit (K/nodes/learning/LinearMapper.scala:69-98): exact centred normal
+ * equations == one block covering all features.  has_lambda = 0 mirrors lambda = None. */
+KS_API int32_t ks_linear_map_fit(int64_t ctx, int64_t features, int64_t labels, int32_t has_lambda, double lambda,
+                          int64_t* out_model);
+
+/* ---- BlockLinearMapper / LinearMapper state (K/nodes/learning/BlockLinearMapper.scala:22-33,
+ * K/nodes/learning/LinearMapper.scala:18-22) ------------------------------------------------ */
+KS_API int32_t ks_model_from_host(int64_t ctx, const double* const* xs_colmajor, const int64_t* block_rows, int32_t n_blocks,
+                           int64_t k, const double* b_or_null, const double* const* feature_means_or_null,
+                           int32_t block_size, int64_t* out_model);
+KS_API int32_t ks_model_num_blocks(int64_t ctx, int64_t model, int32_t* n_blocks, int64_t* k, int32_t* block_size);
+KS_API int32_t ks_model_block_rows(int64_t ctx, int64_t model, int32_t j, int64_t* rows);
+/* W_j as a column-major (rows_j x k) fp64 matrix; mean_out (rows_j) may be NULL; *has_mean tells whether the
+ * model carries feature scalers (BlockLS: yes, BWLS: no -- BlockWeightedLeastSquares.scala:316-320). */
+KS_API int32_t ks_model_get_block(int64_t ctx, int64_t model, int32_t j, double* W_colmajor_out, double* mean_out,
+                           int32_t* has_mean);
+KS_API int32_t ks_model_get_intercept(int64_t ctx, int64_t model, double* b_out, int32_t* has_intercept);
+/* BlockLinearMapper.apply(RDD) :40-73 -> new (N x k) matrix of predictions. */
+KS_API int32_t ks_model_apply(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
+                       int64_t* out_predictions);
+/* apply followed by MaxClassifier (K/nodes/util/MaxClassifier.scala:9-11); host_out has N int32. */
+KS_API int32_t ks_model_apply_argmax(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs,
+                              int32_t n_rfs, int32_t* host_out);
+/* applyAndEvaluate (BlockLinearMapper.scala:95-137): the cumulative prediction after block j (intercept included). */
+KS_API int32_t ks_model_apply_partial(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs,
+                               int32_t n_rfs, int32_t last_block, int64_t* out_predictions);
+/* BlockLeastSquaresEstimator.computeCost (K/nodes/learning/BlockLinearMapper.scala:142-187); collective. */
+KS_API int32_t ks_model_cost(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
+                      int64_t labels, double lambda, double* out_cost);
+KS_API int32_t ks_model_destroy(int64_t ctx, int64_t model);
+
+/* ---- instrumentation ----------------------------------------------------------------------
+ * JSON with per-phase device milliseconds of the last fit (featurize, gram, allreduce, solve, update),
+ * kernel launch count and the algorithmic flop count. */
+KS_API int32_t ks_last_fit_stats_json(int64_t ctx, char* buf, int64_t buflen);
+/* number of kernels this library has launched on the context since creation */
+KS_API int32_t ks_ctx_launch_count(int64_t ctx, int64_t* out_count);
+
+/* ---- low-level kernel entry points (unit tests and micro-benchmarks) ----------------------- */
+/* out_g (M x M, row-major fp64, ld_g) = A^T A upper triangle mirrored; out_c (M x Nb) = A^T B; A, B device matrices
+ * with equal row counts.  Exercises the Gram kernel alone (no centring, no collective). */
+KS_API int32_t ks_debug_gram(int64_t ctx, int64_t a, int64_t b, double* out_g, int64_t ld_g, double* out_c, int64_t ld_c);
+/* Times `iters` launches of the Gram kernel alone (CUDA events on the launching stream); returns ms per launch. */
+KS_API int32_t ks_debug_time_gram(int64_t ctx, int64_t a, int64_t b, int32_t iters, double* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KEYSTONE_B200_H */

@@ -1,0 +1,382 @@
+// HBM-bound helper kernels of the block least-squares path: conversions, column sums
+// (StandardScaler, K/nodes/stats/StandardScaler.scala:45-59; MatrixUtils.computeMean,
+// K/utils/MatrixUtils.scala:137-146), residual initialisation, the fp64 assembly of the reduced
+// normal equations and operand packing.  All matrices are row-major fp32 with ld % 32 == 0
+// unless stated; fp64 matrices are column-major exactly as Breeze stores DenseMatrix[Double].
+#include "kernels.h"
+
+namespace ks {
+
+__device__ __forceinline__ float round_tf32_aux(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+static inline unsigned grid_for(int64_t n, int threads, int64_t cap = 148 * 16) {
+  int64_t g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return static_cast<unsigned>(g);
+}
+
+// ------------------------------------------------------------------ conversions
+__global__ void f64_to_f32_rows_kernel(const double* __restrict__ src, int64_t src_ld, float* __restrict__ dst,
+                                       int64_t dst_ld, int64_t rows, int64_t cols) {
+  const int64_t total = rows * dst_ld;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / dst_ld, c = i - r * dst_ld;
+    dst[i] = c < cols ? static_cast<float>(src[r * src_ld + c]) : 0.f;
+  }
+}
+void launch_f64_to_f32_rows(const double* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int64_t cols,
+                            cudaStream_t st) {
+  if (rows * dst_ld == 0) return;
+  f64_to_f32_rows_kernel<<<grid_for(rows * dst_ld, 256), 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols);
+}
+
+__global__ void f32_to_f64_rows_kernel(const float* __restrict__ src, int64_t src_ld, double* __restrict__ dst,
+                                       int64_t dst_ld, int64_t rows, int64_t cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    dst[r * dst_ld + c] = static_cast<double>(src[r * src_ld + c]);
+  }
+}
+void launch_f32_to_f64_rows(const float* src, int64_t src_ld, double* dst, int64_t dst_ld, int64_t rows, int64_t cols,
+                            cudaStream_t st) {
+  if (rows * cols == 0) return;
+  f32_to_f64_rows_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols);
+}
+
+__global__ void f64_to_f32_vec_kernel(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dst[i] = static_cast<float>(src[i]);
+}
+void launch_f64_to_f32_vec(const double* src, float* dst, int64_t n, cudaStream_t st) {
+  if (n == 0) return;
+  f64_to_f32_vec_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, dst, n);
+}
+
+// ClassLabelIndicatorsFromIntLabels (K/nodes/util/ClassLabelIndicators.scala:15-29): +1 at the class, -1 elsewhere
+__global__ void labels_from_classes_kernel(const int32_t* __restrict__ cls, float* __restrict__ dst, int64_t ld,
+                                           int64_t rows, int k) {
+  const int64_t total = rows * ld;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / ld;
+    const int c = static_cast<int>(i - r * ld);
+    dst[i] = c < k ? (c == cls[r] ? 1.f : -1.f) : 0.f;
+  }
+}
+void launch_labels_from_classes(const int32_t* cls, float* dst, int64_t ld, int64_t rows, int k, cudaStream_t st) {
+  if (rows == 0) return;
+  labels_from_classes_kernel<<<grid_for(rows * ld, 256), 256, 0, st>>>(cls, dst, ld, rows, k);
+}
+
+__global__ void fill_kernel(float* p, int64_t n, float v) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    p[i] = v;
+}
+void launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st) {
+  if (n == 0) return;
+  fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, n, v);
+}
+
+// ------------------------------------------------------------------ synthetic N(mean, std) (benchmarks)
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void normal_kernel(float* __restrict__ dst, int64_t ld, int64_t rows, int cols, uint64_t seed,
+                              int64_t row_offset, float mean, float stddev) {
+  const int64_t total = rows * ld;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / ld;
+    const int c = static_cast<int>(i - r * ld);
+    float v = 0.f;
+    if (c < cols) {
+      const uint64_t h = splitmix64(seed ^ splitmix64(static_cast<uint64_t>((row_offset + r) * cols + c)));
+      const float u1 = (static_cast<float>(h >> 40) + 0.5f) * (1.0f / 16777216.0f);
+      const float u2 = (static_cast<float>((h >> 16) & 0xFFFFFF) + 0.5f) * (1.0f / 16777216.0f);
+      v = mean + stddev * sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+    }
+    dst[i] = v;
+  }
+}
+void launch_normal_f32(float* dst, int64_t ld, int64_t rows, int cols, uint64_t seed, int64_t row_offset, float mean,
+                       float stddev, cudaStream_t st) {
+  if (rows == 0) return;
+  normal_kernel<<<grid_for(rows * ld, 256), 256, 0, st>>>(dst, ld, rows, cols, seed, row_offset, mean, stddev);
+}
+
+// ------------------------------------------------------------------ column sums
+// block (32, 8): each thread owns 4 consecutive columns (float4), rows strided by 8; one fp64 atomic per column
+// per block.  Coalesced 512 B per warp-row.
+__global__ void colsum_kernel(const float* __restrict__ hi, const float* __restrict__ lo, int64_t ld, int64_t rows,
+                              int cols, double* __restrict__ sums, int64_t rows_per_block) {
+  __shared__ double red[8][128];
+  const int c4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int64_t r_begin = blockIdx.y * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if (c4 < ld) {
+    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
+      float4 v = *reinterpret_cast<const float4*>(hi + r * ld + c4);
+      if (lo) {
+        const float4 w = *reinterpret_cast<const float4*>(lo + r * ld + c4);
+        a0 += static_cast<double>(v.x) + w.x; a1 += static_cast<double>(v.y) + w.y;
+        a2 += static_cast<double>(v.z) + w.z; a3 += static_cast<double>(v.w) + w.w;
+      } else {
+        a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+      }
+    }
+  }
+  red[threadIdx.y][threadIdx.x * 4 + 0] = a0;
+  red[threadIdx.y][threadIdx.x * 4 + 1] = a1;
+  red[threadIdx.y][threadIdx.x * 4 + 2] = a2;
+  red[threadIdx.y][threadIdx.x * 4 + 3] = a3;
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 128) {
+    double s = 0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += red[y][t];
+    const int c = blockIdx.x * 128 + t;
+    if (c < cols) atomicAdd(sums + c, s);
+  }
+}
+void launch_colsum(const float* hi, const float* lo, int64_t ld, int64_t rows, int cols, double* sums, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return;
+  const int64_t rpb = 1024;
+  dim3 grid(static_cast<unsigned>((cols + 127) / 128), static_cast<unsigned>((rows + rpb - 1) / rpb));
+  colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(hi, lo, ld, rows, cols, sums, rpb);
+}
+
+// ------------------------------------------------------------------ residual init / slab from materialised features
+__global__ void init_residual_kernel(const float* __restrict__ Y, int64_t ldy, const double* __restrict__ ymean,
+                                     float* __restrict__ r_hi, float* __restrict__ r_lo, int64_t ldr, int64_t rows, int k) {
+  const int64_t total = rows * ldr;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / ldr;
+    const int c = static_cast<int>(i - r * ldr);
+    float h = 0.f, l = 0.f;
+    if (c < k) {
+      const float v = static_cast<float>(static_cast<double>(Y[r * ldy + c]) - ymean[c]);
+      h = round_tf32_aux(v);
+      l = v - h;
+    } else if (c == k) {
+      h = 1.f;  // ones column: A^T [R | 1] yields the column sums of the slab in the same pass
+    }
+    r_hi[i] = h;
+    r_lo[i] = l;
+  }
+}
+void launch_init_residual(const float* Y, int64_t ldy, const double* ymean, float* r_hi, float* r_lo, int64_t ldr,
+                          int64_t rows, int k, cudaStream_t st) {
+  if (rows == 0) return;
+  init_residual_kernel<<<grid_for(rows * ldr, 256), 256, 0, st>>>(Y, ldy, ymean, r_hi, r_lo, ldr, rows, k);
+}
+
+__global__ void center_round_kernel(const float* __restrict__ F, int64_t ldf, int c0, const float* __restrict__ shift,
+                                    float* __restrict__ s_hi, float* __restrict__ s_lo, int64_t lds, int64_t rows, int cols) {
+  const int64_t total = rows * lds;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / lds;
+    const int c = static_cast<int>(i - r * lds);
+    float h = 0.f, l = 0.f;
+    if (c < cols) {
+      const float v = F[r * ldf + c0 + c] - shift[c];
+      h = round_tf32_aux(v);
+      l = v - h;
+    }
+    s_hi[i] = h;
+    if (s_lo) s_lo[i] = l;
+  }
+}
+void launch_center_round(const float* F, int64_t ldf, int c0, const float* shift, float* s_hi, float* s_lo, int64_t lds,
+                         int64_t rows, int cols, cudaStream_t st) {
+  if (rows == 0) return;
+  center_round_kernel<<<grid_for(rows * lds, 256), 256, 0, st>>>(F, ldf, c0, shift, s_hi, s_lo, lds, rows, cols);
+}
+
+// ------------------------------------------------------------------ reduced system assembly (fp64)
+__global__ void build_system_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ C, int ldc,
+                                    int k_ones, double n_total, double lam, double* __restrict__ H,
+                                    double* __restrict__ delta, int b) {
+  const int64_t total = static_cast<int64_t>(b) * b;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i / b), r = static_cast<int>(i - static_cast<int64_t>(c) * b);
+    const int lo = min(r, c), hi = max(r, c);
+    const double g = static_cast<double>(G[static_cast<int64_t>(lo) * ldg + hi]);  // upper triangle is the computed one
+    const double dr = static_cast<double>(C[static_cast<int64_t>(r) * ldc + k_ones]) / n_total;
+    const double dc = static_cast<double>(C[static_cast<int64_t>(c) * ldc + k_ones]) / n_total;
+    H[i] = g - n_total * dr * dc + (r == c ? lam : 0.0);
+    if (c == 0) delta[r] = dr;
+  }
+}
+void launch_build_system(const float* G, int ldg, const float* C, int ldc, int k_ones, double n_total, double lam,
+                         double* H, double* delta, int b, cudaStream_t st) {
+  if (b == 0) return;
+  build_system_kernel<<<grid_for(static_cast<int64_t>(b) * b, 256), 256, 0, st>>>(G, ldg, C, ldc, k_ones, n_total, lam, H,
+                                                                              delta, b);
+}
+
+__global__ void build_rhs_kernel(const float* __restrict__ C, int ldc, const double* __restrict__ delta,
+                                 const double* __restrict__ rsum, double n_total, double lam,
+                                 const double* __restrict__ Wold, double* __restrict__ rhs, int b, int k) {
+  const int64_t total = static_cast<int64_t>(b) * k;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i / b), f = static_cast<int>(i - static_cast<int64_t>(c) * b);
+    double v = static_cast<double>(C[static_cast<int64_t>(f) * ldc + c]) - delta[f] * rsum[c];  // n * delta * (rsum / n)
+    if (Wold) v -= lam * Wold[i];
+    rhs[i] = v;
+  }
+}
+void launch_build_rhs(const float* C, int ldc, const double* delta, const double* rsum, double n_total, double lam,
+                      const double* Wold, double* rhs, int b, int k, cudaStream_t st) {
+  if (b == 0 || k == 0) return;
+  build_rhs_kernel<<<grid_for(static_cast<int64_t>(b) * k, 256), 256, 0, st>>>(C, ldc, delta, rsum, n_total, lam, Wold, rhs, b, k);
+}
+
+// one block per class column c: packs dW[:, c] into the K-major GEMM operand row c and reduces delta . dW[:, c]
+__global__ void pack_update_kernel(const double* __restrict__ dW, double* __restrict__ Wmodel,
+                                   const double* __restrict__ delta, float* __restrict__ bop_hi,
+                                   float* __restrict__ bop_lo, int ldb, float* __restrict__ cbias, int b, int k) {
+  const int c = blockIdx.x;
+  __shared__ double red[256];
+  double acc = 0;
+  for (int f = threadIdx.x; f < ldb; f += blockDim.x) {
+    float h = 0.f, l = 0.f;
+    if (c < k && f < b) {
+      const double w = dW[static_cast<int64_t>(c) * b + f];
+      if (Wmodel) Wmodel[static_cast<int64_t>(c) * b + f] += w;
+      if (delta) acc += delta[f] * w;
+      const float wf = static_cast<float>(w);
+      h = round_tf32_aux(wf);
+      l = static_cast<float>(w - static_cast<double>(h));
+    }
+    bop_hi[static_cast<int64_t>(c) * ldb + f] = h;
+    if (bop_lo) bop_lo[static_cast<int64_t>(c) * ldb + f] = l;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && cbias) cbias[c] = static_cast<float>(red[0]);
+}
+void launch_pack_update(const double* dW, double* Wmodel, const double* delta, float* bop_hi, float* bop_lo, int ldb,
+                        float* cbias, int b, int k, int kpad, cudaStream_t st) {
+  if (kpad == 0) return;
+  pack_update_kernel<<<kpad, 256, 0, st>>>(dW, Wmodel, delta, bop_hi, bop_lo, ldb, cbias, b, k);
+}
+
+__global__ void pack_apply_kernel(const double* __restrict__ W, const double* __restrict__ mean,
+                                  const double* __restrict__ intercept, float* __restrict__ bop_hi, int ldb,
+                                  float* __restrict__ cbias, int b, int k) {
+  const int c = blockIdx.x;
+  __shared__ double red[256];
+  double acc = 0;
+  for (int f = threadIdx.x; f < ldb; f += blockDim.x) {
+    float h = 0.f;
+    if (c < k && f < b) {
+      const double w = W[static_cast<int64_t>(c) * b + f];
+      if (mean) acc -= mean[f] * w;
+      h = round_tf32_aux(static_cast<float>(w));
+    }
+    bop_hi[static_cast<int64_t>(c) * ldb + f] = h;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cbias[c] = static_cast<float>(red[0] + ((intercept && c < k) ? intercept[c] : 0.0));
+}
+void launch_pack_apply(const double* W, const double* mean_or_null, const double* intercept_or_null, float* bop_hi,
+                       int ldb, float* cbias, int b, int k, int kpad, cudaStream_t st) {
+  if (kpad == 0) return;
+  pack_apply_kernel<<<kpad, 256, 0, st>>>(W, mean_or_null, intercept_or_null, bop_hi, ldb, cbias, b, k);
+}
+
+// CosineRandomFeatures W is (n_out x n_in) column-major fp64 (Breeze); the GEMM wants row-major [n_out][ld] tf32
+__global__ void w_to_operand_kernel(const double* __restrict__ W, int64_t n_out, int64_t n_in, float* __restrict__ dst, int64_t ld) {
+  const int64_t total = n_out * ld;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t o = i / ld, c = i - o * ld;
+    dst[i] = c < n_in ? round_tf32_aux(static_cast<float>(W[c * n_out + o])) : 0.f;
+  }
+}
+void launch_w_to_operand(const double* W_colmajor, int64_t n_out, int64_t n_in, float* dst, int64_t ld, cudaStream_t st) {
+  if (n_out == 0) return;
+  w_to_operand_kernel<<<grid_for(n_out * ld, 256), 256, 0, st>>>(W_colmajor, n_out, n_in, dst, ld);
+}
+
+// ------------------------------------------------------------------ MaxClassifier (K/nodes/util/MaxClassifier.scala:9-11)
+__global__ void argmax_rows_kernel(const float* __restrict__ Y, int64_t ld, int64_t rows, int k, int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = lane; c < k; c += 32) {
+      const float v = Y[r * ld + c];
+      if (v > best) { best = v; bi = c; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) out[r] = bi;
+  }
+}
+void launch_argmax_rows(const float* Y, int64_t ld, int64_t rows, int k, int32_t* out, cudaStream_t st) {
+  if (rows == 0) return;
+  argmax_rows_kernel<<<grid_for(rows * 32, 256), 256, 0, st>>>(Y, ld, rows, k, out);
+}
+
+__global__ void sq_err_kernel(const float* __restrict__ Y, int64_t ldy, const float* __restrict__ L, int64_t ldl,
+                              int64_t rows, int k, double* __restrict__ out) {
+  double acc = 0;
+  const int64_t total = rows * k;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / k;
+    const int c = static_cast<int>(i - r * k);
+    const double d = static_cast<double>(Y[r * ldy + c]) - static_cast<double>(L[r * ldl + c]);
+    acc += d * d;
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out, red[0]);
+}
+void launch_sq_err(const float* Y, int64_t ldy, const float* L, int64_t ldl, int64_t rows, int k, double* out,
+                   cudaStream_t st) {
+  if (rows == 0) return;
+  sq_err_kernel<<<grid_for(rows * k, 256), 256, 0, st>>>(Y, ldy, L, ldl, rows, k, out);
+}
+
+}  // namespace ks

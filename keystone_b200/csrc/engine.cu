@@ -1,0 +1,1168 @@
+// Host engine + C ABI of libkeystone_b200: contexts, row-sharded device matrices, the
+// BlockLeastSquaresEstimator solver loop (K/nodes/learning/BlockLinearMapper.scala:212-243 and the
+// mlmatrix BlockCoordinateDescent it delegates to), BlockLinearMapper apply (:40-87) and computeCost
+// (:142-187).  All arithmetic of the hot path runs in the CUDA kernels of tc_kernels.cu /
+// aux_kernels.cu and in cuSOLVER (dense Cholesky of the reduced b x b system); there is no CPU path.
+#include "engine.h"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <string.h>
+
+#include <mutex>
+#include <sstream>
+
+namespace ks {
+
+// ------------------------------------------------------------------------------------ dynamic libraries
+template <class F>
+static void load_sym(void* lib, const char* name, F& out, const char* libname) {
+  void* s = dlsym(lib, name);
+  if (!s) throw KsError{KS_ERR_SOLVER, std::string("symbol ") + name + " missing from " + libname};
+  out = reinterpret_cast<F>(s);
+}
+static void* open_first(const std::vector<const char*>& names) {
+  for (const char* n : names) {
+    void* h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) return h;
+  }
+  return nullptr;
+}
+SolverApi& solver_api() {
+  static SolverApi api;
+  static std::once_flag once;
+  static std::string fail;
+  std::call_once(once, [] {
+    try {
+      api.lib = open_first({"libcusolver.so.11", "libcusolver.so", "/usr/local/cuda/lib64/libcusolver.so.11"});
+      if (!api.lib) throw KsError{KS_ERR_SOLVER, std::string("cannot load libcusolver: ") + dlerror()};
+      load_sym(api.lib, "cusolverDnCreate", api.Create, "libcusolver");
+      load_sym(api.lib, "cusolverDnDestroy", api.Destroy, "libcusolver");
+      load_sym(api.lib, "cusolverDnSetStream", api.SetStream, "libcusolver");
+      load_sym(api.lib, "cusolverDnDpotrf_bufferSize", api.DpotrfBufferSize, "libcusolver");
+      load_sym(api.lib, "cusolverDnDpotrf", api.Dpotrf, "libcusolver");
+      load_sym(api.lib, "cusolverDnDpotrs", api.Dpotrs, "libcusolver");
+    } catch (const KsError& e) {
+      fail = e.msg;
+    }
+  });
+  if (!fail.empty()) throw KsError{KS_ERR_SOLVER, fail};
+  return api;
+}
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  static std::string fail;
+  std::call_once(once, [] {
+    try {
+      api.lib = open_first({"libnccl.so.2", "libnccl.so"});
+      if (!api.lib) throw KsError{KS_ERR_NCCL, std::string("cannot load libnccl: ") + dlerror()};
+      load_sym(api.lib, "ncclGetUniqueId", api.GetUniqueId, "libnccl");
+      load_sym(api.lib, "ncclCommInitRank", api.CommInitRank, "libnccl");
+      load_sym(api.lib, "ncclCommDestroy", api.CommDestroy, "libnccl");
+      load_sym(api.lib, "ncclAllReduce", api.AllReduce, "libnccl");
+      load_sym(api.lib, "ncclGetErrorString", api.GetErrorString, "libnccl");
+    } catch (const KsError& e) {
+      fail = e.msg;
+    }
+  });
+  if (!fail.empty()) throw KsError{KS_ERR_NCCL, fail};
+  return api;
+}
+#define KS_NCCL(call)                                                                                      \
+  do {                                                                                                     \
+    ncclResult_t r__ = (call);                                                                             \
+    if (r__ != ncclSuccess)                                                                                \
+      throw KsError{KS_ERR_NCCL, std::string(#call) + " failed: " + nccl_api().GetErrorString(r__)};      \
+  } while (0)
+
+// ------------------------------------------------------------------------------------ Ctx
+static constexpr int kMaxInfo = 4096;
+
+Matrix& Ctx::matrix(int64_t h) {
+  auto it = matrices.find(h);
+  if (it == matrices.end()) throw KsError{KS_ERR_HANDLE, "unknown matrix handle " + std::to_string(h)};
+  return *it->second;
+}
+CosRF& Ctx::rf(int64_t h) {
+  auto it = rfs.find(h);
+  if (it == rfs.end()) throw KsError{KS_ERR_HANDLE, "unknown CosineRandomFeatures handle " + std::to_string(h)};
+  return *it->second;
+}
+Model& Ctx::model(int64_t h) {
+  auto it = models.find(h);
+  if (it == models.end()) throw KsError{KS_ERR_HANDLE, "unknown model handle " + std::to_string(h)};
+  return *it->second;
+}
+int64_t Ctx::add(std::unique_ptr<Matrix> m) {
+  const int64_t id = next_id++;
+  matrices[id] = std::move(m);
+  return id;
+}
+int64_t Ctx::add(std::unique_ptr<Model> m) {
+  const int64_t id = next_id++;
+  models[id] = std::move(m);
+  return id;
+}
+cudaEvent_t Ctx::get_event() {
+  cudaEvent_t e;
+  if (!event_pool.empty()) {
+    e = event_pool.back();
+    event_pool.pop_back();
+    return e;
+  }
+  KS_CUDA(cudaEventCreate(&e));
+  return e;
+}
+void Ctx::span_begin(int phase) {
+  if (!timing) return;
+  Span s{phase, get_event(), get_event()};
+  KS_CUDA(cudaEventRecord(s.a, st));
+  spans.push_back(s);
+}
+void Ctx::span_end() {
+  if (!timing) return;
+  KS_CUDA(cudaEventRecord(spans.back().b, st));
+}
+void Ctx::collect_spans(double out_ms[PH_COUNT]) {
+  for (int i = 0; i < PH_COUNT; ++i) out_ms[i] = 0;
+  for (auto& s : spans) {
+    float ms = 0;
+    cudaEventSynchronize(s.b);
+    cudaEventElapsedTime(&ms, s.a, s.b);
+    out_ms[s.phase] += ms;
+    event_pool.push_back(s.a);
+    event_pool.push_back(s.b);
+  }
+  spans.clear();
+}
+void Ctx::allreduce_f32(float* p, size_t n) {
+  if (world <= 1 || n == 0) return;
+  KS_NCCL(nccl_api().AllReduce(p, p, n, ncclFloat32, ncclSum, comm, st));
+}
+void Ctx::allreduce_f64(double* p, size_t n) {
+  if (world <= 1 || n == 0) return;
+  KS_NCCL(nccl_api().AllReduce(p, p, n, ncclFloat64, ncclSum, comm, st));
+}
+void Ctx::ensure_solver() {
+  if (solver) return;
+  SolverApi& api = solver_api();
+  if (api.Create(&solver) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnCreate failed"};
+  if (api.SetStream(solver, st) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
+  dev_info.alloc(sizeof(int) * kMaxInfo);
+  KS_CUDA(cudaMemsetAsync(dev_info.p, 0, sizeof(int) * kMaxInfo, st));
+}
+void Ctx::potrf(double* H, int n, int info_slot) {
+  ensure_solver();
+  SolverApi& api = solver_api();
+  int lwork = 0;
+  if (api.DpotrfBufferSize(solver, CUBLAS_FILL_MODE_LOWER, n, H, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
+    throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrf_bufferSize failed"};
+  if (lwork > solver_lwork) {
+    KS_CUDA(cudaStreamSynchronize(st));
+    solver_work.alloc(sizeof(double) * static_cast<size_t>(lwork));
+    solver_lwork = lwork;
+  }
+  if (api.Dpotrf(solver, CUBLAS_FILL_MODE_LOWER, n, H, n, solver_work.as<double>(), solver_lwork,
+                 dev_info.as<int>() + (info_slot % kMaxInfo)) != CUSOLVER_STATUS_SUCCESS)
+    throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrf failed"};
+  launches += 1;
+}
+void Ctx::potrs(const double* H, int n, double* B, int nrhs, int info_slot) {
+  ensure_solver();
+  if (nrhs == 0 || n == 0) return;
+  if (solver_api().Dpotrs(solver, CUBLAS_FILL_MODE_LOWER, n, nrhs, H, n, B, n, dev_info.as<int>() + (info_slot % kMaxInfo)) !=
+      CUSOLVER_STATUS_SUCCESS)
+    throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrs failed"};
+  launches += 1;
+}
+void Ctx::check_infos(int used_slots) {
+  if (!solver || used_slots <= 0) return;
+  if (used_slots > kMaxInfo) used_slots = kMaxInfo;
+  std::vector<int> h(used_slots);
+  KS_CUDA(cudaMemcpyAsync(h.data(), dev_info.p, sizeof(int) * used_slots, cudaMemcpyDeviceToHost, st));
+  KS_CUDA(cudaStreamSynchronize(st));
+  KS_CUDA(cudaMemsetAsync(dev_info.p, 0, sizeof(int) * used_slots, st));
+  for (int i = 0; i < used_slots; ++i)
+    if (h[i] != 0)
+      throw KsError{KS_ERR_NOT_SPD, "Cholesky failed (slot " + std::to_string(i) + ", info " + std::to_string(h[i]) +
+                                        "): the regularised Gram matrix is not positive definite (lambda too small?)"};
+}
+void Ctx::check_async(const char* what) {
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) {
+    std::string extra;
+    if (e == cudaErrorLaunchFailure || e == cudaErrorIllegalInstruction) extra = " (kernel trapped: barrier wait budget exceeded or illegal instruction)";
+    throw KsError{KS_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e) + extra};
+  }
+}
+
+// ------------------------------------------------------------------------------------ feature source
+void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out) {
+  if (features != 0) {
+    if (x_in != 0 || n_rfs != 0) throw KsError{KS_ERR_INVALID, "pass either features or (x_in, rfs), not both"};
+    out.F = &c.matrix(features);
+    out.D = out.F->cols;
+    out.n_rows = out.F->rows;
+    out.zeros.alloc(sizeof(float) * static_cast<size_t>(round_up(out.D, 32) + 32));
+    KS_CUDA(cudaMemsetAsync(out.zeros.p, 0, out.zeros.bytes, c.st));
+    return;
+  }
+  if (x_in == 0 || n_rfs <= 0 || rfs == nullptr) throw KsError{KS_ERR_INVALID, "no feature source given"};
+  out.X = &c.matrix(x_in);
+  out.n_rows = out.X->rows;
+  out.d_in = out.X->cols;
+  int64_t total = 0;
+  for (int i = 0; i < n_rfs; ++i) {
+    CosRF& r = c.rf(rfs[i]);
+    if (r.n_in != out.d_in) throw KsError{KS_ERR_INVALID, "CosineRandomFeatures input dimension does not match x_in"};
+    total += r.n_out;
+  }
+  out.D = total;
+  CosRF& r0 = c.rf(rfs[0]);
+  out.ldw = r0.ld;
+  if (n_rfs == 1) {
+    out.Wall = r0.W;
+    out.ball = r0.bias;
+  } else {  // VectorCombiner: concatenate the gathered feature maps
+    out.wcat.alloc(sizeof(float) * static_cast<size_t>(total * out.ldw));
+    out.bcat.alloc(sizeof(float) * static_cast<size_t>(total));
+    int64_t off = 0;
+    for (int i = 0; i < n_rfs; ++i) {
+      CosRF& r = c.rf(rfs[i]);
+      KS_CUDA(cudaMemcpyAsync(out.wcat.as<float>() + off * out.ldw, r.W, sizeof(float) * r.n_out * r.ld,
+                              cudaMemcpyDeviceToDevice, c.st));
+      KS_CUDA(cudaMemcpyAsync(out.bcat.as<float>() + off, r.bias, sizeof(float) * r.n_out, cudaMemcpyDeviceToDevice, c.st));
+      off += r.n_out;
+    }
+    out.Wall = out.wcat.as<float>();
+    out.ball = out.bcat.as<float>();
+  }
+  out.zeros.alloc(sizeof(float) * static_cast<size_t>(round_up(std::max(out.D, out.d_in), 32) + 32));
+  KS_CUDA(cudaMemsetAsync(out.zeros.p, 0, out.zeros.bytes, c.st));
+  // GEMM operand copy of X rounded to tf32 (round-to-nearest instead of the MMA's truncation)
+  out.xop.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(out.n_rows, 1) * out.X->ld));
+  launch_center_round(out.X->d, out.X->ld, 0, out.zeros.as<float>(), out.xop.as<float>(), nullptr, out.X->ld, out.n_rows,
+                      static_cast<int>(out.X->cols), c.st);
+  c.launches += 1;
+}
+
+static void tmap_or_throw(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  const int r = make_tmap_2d(m, base, rows, cols, ld, box_rows);
+  if (r != 0)
+    throw KsError{KS_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(r) + ") rows=" + std::to_string(rows) +
+                                   " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld)};
+}
+
+void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, float* slab, int64_t lds,
+                  int64_t row_begin, int64_t rows, bool round_out) {
+  if (rows <= 0 || cols <= 0) return;
+  if (src.F) {
+    if (!round_out) throw KsError{KS_ERR_INVALID, "unrounded slab only for generated features"};
+    launch_center_round(src.F->d + row_begin * src.F->ld, src.F->ld, static_cast<int>(c0), shift, slab, nullptr, lds, rows,
+                        static_cast<int>(cols), c.st);
+    c.launches += 1;
+    return;
+  }
+  KmLaunch k;
+  tmap_or_throw(&k.tmA, src.xop.as<float>() + row_begin * src.X->ld, rows, src.d_in, src.X->ld, 128);
+  tmap_or_throw(&k.tmB, src.Wall + c0 * src.ldw, cols, src.d_in, src.ldw, 256);
+  k.p.out_hi = slab;
+  k.p.out_lo = nullptr;
+  k.p.vec0 = src.ball + c0;
+  k.p.vec1 = shift;
+  k.p.ld_out = static_cast<int>(lds);
+  k.p.M = static_cast<int>(rows);
+  k.p.N = static_cast<int>(cols);
+  k.p.K = static_cast<int>(src.d_in);
+  k.p.n_keep = static_cast<int>(cols);
+  k.p.accumulate = round_out ? 0 : 1;  // EPI_COS: non-zero => keep full fp32 output
+  k.epi = EPI_COS;
+  k.num_sms = c.num_sms;
+  KS_CUDA(launch_kmajor(k, c.st));
+  c.launches += 1;
+}
+
+const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, int* num_tiles) {
+  std::vector<int> key = {b, kcols, with_g ? 1 : 0, with_c ? 1 : 0};
+  auto it = c.tile_cache.find(key);
+  std::vector<GramTile> t;
+  const int mb = (b + 127) / 128;
+  if (with_g) {
+    const int nbk = (b + 255) / 256;
+    for (int i = 0; i < mb; ++i)
+      for (int j = 0; j < nbk; ++j)
+        if ((j + 1) * 256 - 1 >= i * 128) t.push_back(GramTile{i, j, 0, 0});  // tile touches the upper triangle
+  }
+  if (with_c) {
+    const int nck = (kcols + 255) / 256;
+    for (int i = 0; i < mb; ++i)
+      for (int j = 0; j < nck; ++j) t.push_back(GramTile{i, j, 1, 0});
+  }
+  *num_tiles = static_cast<int>(t.size());
+  if (it != c.tile_cache.end()) return it->second->as<GramTile>();
+  auto buf = std::make_unique<DevBuf>();
+  buf->alloc(sizeof(GramTile) * std::max<size_t>(t.size(), 1));
+  KS_CUDA(cudaMemcpyAsync(buf->p, t.data(), sizeof(GramTile) * t.size(), cudaMemcpyHostToDevice, c.st));
+  KS_CUDA(cudaStreamSynchronize(c.st));  // t is a stack temporary
+  const GramTile* p = buf->as<GramTile>();
+  c.tile_cache[key] = std::move(buf);
+  return p;
+}
+
+void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* R, int64_t ldr, int kcols,
+                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c) {
+  if (rows <= 0 || b <= 0 || (!with_g && !with_c)) return;
+  GramLaunch g;
+  int nt = 0;
+  g.tiles = gram_tiles(c, b, kcols, with_g, with_c, &nt);
+  g.num_tiles = nt;
+  tmap_or_throw(&g.tmA, slab, rows, b, lds, kGramStageRows);
+  g.tmB0 = g.tmA;
+  if (with_c) tmap_or_throw(&g.tmB1, R, rows, kcols, ldr, kGramStageRows);
+  else g.tmB1 = g.tmA;
+  g.rows = static_cast<int>(rows);
+  int64_t chunk = c.gram_chunk_rows;
+  chunk = std::max<int64_t>(kGramStageRows, chunk / kGramStageRows * kGramStageRows);
+  g.chunk_rows = static_cast<int>(chunk);
+  g.bn = 256;
+  g.out0 = GramOut{G, ldg, b, b};
+  g.out1 = GramOut{C, ldc, b, kcols};
+  KS_CUDA(launch_gram(g, c.st));
+  c.launches += 1;
+}
+
+void launch_update(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* bop, int64_t ldb, int k,
+                   float* r_hi, float* r_lo, int64_t ldr, const float* cbias, int epi, int accumulate) {
+  if (rows <= 0 || k <= 0 || b <= 0) return;
+  KmLaunch u;
+  tmap_or_throw(&u.tmA, slab, rows, b, lds, 128);
+  tmap_or_throw(&u.tmB, bop, k, b, ldb, 256);
+  u.p.out_hi = r_hi;
+  u.p.out_lo = r_lo;
+  u.p.vec0 = cbias;
+  u.p.vec1 = nullptr;
+  u.p.ld_out = static_cast<int>(ldr);
+  u.p.M = static_cast<int>(rows);
+  u.p.N = k;
+  u.p.K = b;
+  u.p.n_keep = k;
+  u.p.accumulate = accumulate;
+  u.epi = epi;
+  u.num_sms = c.num_sms;
+  KS_CUDA(launch_kmajor(u, c.st));
+  c.launches += 1;
+}
+
+// ------------------------------------------------------------------------------------ small device helpers
+__global__ void mean_from_shift_kernel(const float* shift, const double* delta, double* mean, int b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < b) mean[i] = static_cast<double>(shift[i]) + delta[i];
+}
+__global__ void scale_f64_to_f32_kernel(const double* src, double scale, float* dst, double* dst64, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double v = src[i] * scale;
+    if (dst) dst[i] = static_cast<float>(v);
+    if (dst64) dst64[i] = v;
+  }
+}
+__global__ void sumsq_f64_kernel(const double* p, int64_t n, double* out) {
+  double acc = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    acc += p[i] * p[i];
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out, red[0]);
+}
+
+// ------------------------------------------------------------------------------------ BlockLS fit
+static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, int64_t nf_opt) {
+  if (bs <= 0 || num_iter < 1) throw KsError{KS_ERR_INVALID, "blockSize must be > 0 and numIter >= 1"};
+  if (Y.rows != src.n_rows) throw KsError{KS_ERR_INVALID, "features and labels have different row counts"};
+  const int64_t n_loc = Y.rows;
+  const int k = static_cast<int>(Y.cols);
+  const int64_t D = nf_opt > 0 ? nf_opt : src.D;
+  if (D > src.D) throw KsError{KS_ERR_INVALID, "numFeaturesOpt exceeds the feature dimension"};
+  if (D <= 0 || k <= 0) throw KsError{KS_ERR_INVALID, "empty problem"};
+  const int nb = static_cast<int>((D + bs - 1) / bs);
+  const int bmax = static_cast<int>(std::min<int64_t>(bs, D));
+  const int64_t lds = round_up(bmax, 32);
+  const int kcols = k + 1;  // residual + ones column
+  const int64_t kpad = round_up(kcols, 32);
+  c.spans.clear();
+  const int64_t launches0 = c.launches;
+  cudaEvent_t ev0 = c.get_event(), ev1 = c.get_event();
+  KS_CUDA(cudaEventRecord(ev0, c.st));
+
+  // ---- label mean (StandardScaler on labels, BlockLinearMapper.scala:215) + global row count
+  DevBuf ysum;  // [k] sums, [k] = local row count
+  ysum.alloc(sizeof(double) * (k + 1));
+  KS_CUDA(cudaMemsetAsync(ysum.p, 0, ysum.bytes, c.st));
+  c.span_begin(PH_OTHER);
+  launch_colsum(Y.d, nullptr, Y.ld, n_loc, k, ysum.as<double>(), c.st);
+  c.launches += 1;
+  {
+    const double nl = static_cast<double>(n_loc);
+    KS_CUDA(cudaMemcpyAsync(ysum.as<double>() + k, &nl, sizeof(double), cudaMemcpyHostToDevice, c.st));
+    KS_CUDA(cudaStreamSynchronize(c.st));
+  }
+  c.allreduce_f64(ysum.as<double>(), k + 1);
+  double n_total_d = 0;
+  KS_CUDA(cudaMemcpyAsync(&n_total_d, ysum.as<double>() + k, sizeof(double), cudaMemcpyDeviceToHost, c.st));
+  KS_CUDA(cudaStreamSynchronize(c.st));
+  if (n_total_d < 1) throw KsError{KS_ERR_INVALID, "no training rows"};
+  auto model = std::make_unique<Model>();
+  model->block_size = bs;
+  model->k = k;
+  model->has_mean = true;
+  model->has_intercept = true;
+  model->intercept.alloc(sizeof(double) * k);
+  scale_f64_to_f32_kernel<<<(k + 255) / 256, 256, 0, c.st>>>(ysum.as<double>(), 1.0 / n_total_d, nullptr,
+                                                             model->intercept.as<double>(), k);
+  c.launches += 1;
+
+  // ---- residual R = Y - mean (hi/lo planes) with the ones column
+  DevBuf r_hi, r_lo, slab, gc, H, rhs, rsum, bop, cbias;
+  r_hi.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * kpad));
+  r_lo.alloc(r_hi.bytes);
+  launch_init_residual(Y.d, Y.ld, model->intercept.as<double>(), r_hi.as<float>(), r_lo.as<float>(), kpad, n_loc, k, c.st);
+  c.launches += 1;
+  c.span_end();
+
+  slab.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));
+  const int ldg = static_cast<int>(lds), ldc = static_cast<int>(kpad);
+  const size_t g_elems = static_cast<size_t>(bmax) * ldg, c_elems = static_cast<size_t>(bmax) * ldc;
+  gc.alloc(sizeof(float) * (g_elems + c_elems));
+  float* G = gc.as<float>();
+  float* Cm = G + g_elems;
+  rhs.alloc(sizeof(double) * static_cast<size_t>(bmax) * k);
+  rsum.alloc(sizeof(double) * kpad);
+  bop.alloc(sizeof(float) * static_cast<size_t>(kpad) * lds);
+  cbias.alloc(sizeof(float) * kpad);
+  const bool cache_factors = num_iter > 1;
+  std::vector<std::unique_ptr<DevBuf>> factors(nb), deltas(nb), shifts(nb);
+  if (!cache_factors) H.alloc(sizeof(double) * static_cast<size_t>(bmax) * bmax);
+
+  // ---- exact column means for materialised features (one pass over F for all blocks)
+  DevBuf fsum;
+  if (src.F) {
+    c.span_begin(PH_FEATURIZE);
+    fsum.alloc(sizeof(double) * static_cast<size_t>(src.F->ld));
+    KS_CUDA(cudaMemsetAsync(fsum.p, 0, fsum.bytes, c.st));
+    launch_colsum(src.F->d, nullptr, src.F->ld, n_loc, static_cast<int>(src.F->cols), fsum.as<double>(), c.st);
+    c.launches += 1;
+    c.allreduce_f64(fsum.as<double>(), static_cast<size_t>(src.F->cols));
+    c.span_end();
+  }
+  DevBuf ssum;  // sample column sums for generated features: [bmax] sums + [1] count
+  if (!src.F) ssum.alloc(sizeof(double) * (bmax + 1));
+
+  int info_slot = 0;
+  double flops = 0;
+  for (int it = 0; it < num_iter; ++it) {
+    for (int j = 0; j < nb; ++j) {
+      const int64_t c0 = static_cast<int64_t>(j) * bs;
+      const int b = static_cast<int>(std::min<int64_t>(D, c0 + bs) - c0);
+      // ---------------- featurize: shift estimate (pass 0) + centred, tf32-rounded slab
+      c.span_begin(PH_FEATURIZE);
+      if (it == 0) {
+        shifts[j] = std::make_unique<DevBuf>();
+        shifts[j]->alloc(sizeof(float) * lds);
+        KS_CUDA(cudaMemsetAsync(shifts[j]->p, 0, shifts[j]->bytes, c.st));
+        if (src.F) {
+          scale_f64_to_f32_kernel<<<(b + 255) / 256, 256, 0, c.st>>>(fsum.as<double>() + c0, 1.0 / n_total_d,
+                                                                     shifts[j]->as<float>(), nullptr, b);
+          c.launches += 1;
+        } else {
+          // mean estimate from the first sample_rows rows of every rank (exactness is restored by the rank-1
+          // correction with delta below; the estimate only has to be close enough to avoid cancellation)
+          const int64_t ns = std::min<int64_t>(n_loc, c.sample_rows);
+          KS_CUDA(cudaMemsetAsync(ssum.p, 0, ssum.bytes, c.st));
+          produce_slab(c, src, c0, b, src.zeros.as<float>(), slab.as<float>(), lds, 0, ns, /*round_out=*/false);
+          launch_colsum(slab.as<float>(), nullptr, lds, ns, b, ssum.as<double>(), c.st);
+          c.launches += 1;
+          const double nsd = static_cast<double>(ns);
+          KS_CUDA(cudaMemcpyAsync(ssum.as<double>() + bmax, &nsd, sizeof(double), cudaMemcpyHostToDevice, c.st));
+          KS_CUDA(cudaStreamSynchronize(c.st));
+          c.allreduce_f64(ssum.as<double>(), bmax + 1);
+          double cnt = 0;
+          KS_CUDA(cudaMemcpyAsync(&cnt, ssum.as<double>() + bmax, sizeof(double), cudaMemcpyDeviceToHost, c.st));
+          KS_CUDA(cudaStreamSynchronize(c.st));
+          scale_f64_to_f32_kernel<<<(b + 255) / 256, 256, 0, c.st>>>(ssum.as<double>(), 1.0 / std::max(cnt, 1.0),
+                                                                     shifts[j]->as<float>(), nullptr, b);
+          c.launches += 1;
+          flops += 2.0 * static_cast<double>(ns) * src.d_in * b;
+        }
+      }
+      produce_slab(c, src, c0, b, shifts[j]->as<float>(), slab.as<float>(), lds, 0, n_loc);
+      if (!src.F) flops += 2.0 * static_cast<double>(n_loc) * src.d_in * b;
+      c.span_end();
+
+      // ---------------- Gram: [G | C] = S^T [S | R | 1]  (pass > 0: C only, the factor is cached)
+      c.span_begin(PH_GRAM);
+      const bool with_g = (it == 0);
+      if (with_g) KS_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (g_elems + c_elems), c.st));
+      else KS_CUDA(cudaMemsetAsync(Cm, 0, sizeof(float) * c_elems, c.st));
+      launch_gram_block(c, slab.as<float>(), lds, n_loc, b, r_hi.as<float>(), kpad, kcols, G, ldg, Cm, ldc, with_g, true);
+      KS_CUDA(cudaMemsetAsync(rsum.p, 0, rsum.bytes, c.st));
+      launch_colsum(r_hi.as<float>(), r_lo.as<float>(), kpad, n_loc, k, rsum.as<double>(), c.st);
+      c.launches += 1;
+      flops += (with_g ? 2.0 * n_loc * static_cast<double>(b) * b : 0.0) + 2.0 * n_loc * static_cast<double>(b) * k;
+      c.span_end();
+
+      // ---------------- all-reduce (replaces treeReduce, BlockWeightedLeastSquares.scala:212-225)
+      c.span_begin(PH_ALLREDUCE);
+      if (with_g) c.allreduce_f32(G, g_elems + c_elems);
+      else c.allreduce_f32(Cm, c_elems);
+      c.allreduce_f64(rsum.as<double>(), k);
+      c.span_end();
+
+      // ---------------- solve (G_c + lambda I) dW = C_c - lambda W_old in fp64
+      c.span_begin(PH_SOLVE);
+      double* Hj;
+      if (it == 0) {
+        deltas[j] = std::make_unique<DevBuf>();
+        deltas[j]->alloc(sizeof(double) * b);
+        if (cache_factors) {
+          factors[j] = std::make_unique<DevBuf>();
+          factors[j]->alloc(sizeof(double) * static_cast<size_t>(b) * b);
+          Hj = factors[j]->as<double>();
+        } else {
+          Hj = H.as<double>();
+        }
+        launch_build_system(G, ldg, Cm, ldc, k, n_total_d, lam, Hj, deltas[j]->as<double>(), b, c.st);
+        c.launches += 1;
+        c.potrf(Hj, b, info_slot++);
+        auto mean = std::make_unique<DevBuf>();
+        mean->alloc(sizeof(double) * b);
+        mean_from_shift_kernel<<<(b + 255) / 256, 256, 0, c.st>>>(shifts[j]->as<float>(), deltas[j]->as<double>(),
+                                                                  mean->as<double>(), b);
+        c.launches += 1;
+        auto W = std::make_unique<DevBuf>();
+        W->alloc(sizeof(double) * static_cast<size_t>(b) * k);
+        KS_CUDA(cudaMemsetAsync(W->p, 0, W->bytes, c.st));
+        model->brows.push_back(b);
+        model->W.push_back(std::move(W));
+        model->mean.push_back(std::move(mean));
+        flops += static_cast<double>(b) * b * b / 3.0;
+      } else {
+        Hj = factors[j]->as<double>();
+      }
+      launch_build_rhs(Cm, ldc, deltas[j]->as<double>(), rsum.as<double>(), n_total_d, lam,
+                       it > 0 ? model->W[j]->as<double>() : nullptr, rhs.as<double>(), b, k, c.st);
+      c.launches += 1;
+      c.potrs(Hj, b, rhs.as<double>(), k, info_slot++);
+      launch_pack_update(rhs.as<double>(), model->W[j]->as<double>(), deltas[j]->as<double>(), bop.as<float>(), nullptr,
+                         static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), c.st);
+      c.launches += 1;
+      flops += 2.0 * static_cast<double>(b) * b * k;
+      c.span_end();
+
+      // ---------------- residual update R -= (S - 1 delta^T) dW
+      c.span_begin(PH_UPDATE);
+      launch_update(c, slab.as<float>(), lds, n_loc, b, bop.as<float>(), lds, k, r_hi.as<float>(), r_lo.as<float>(), kpad,
+                    cbias.as<float>(), EPI_UPDATE, 0);
+      flops += 2.0 * n_loc * static_cast<double>(b) * k;
+      c.span_end();
+    }
+  }
+  KS_CUDA(cudaEventRecord(ev1, c.st));
+  c.check_async("BlockLeastSquaresEstimator.fit");
+  c.check_infos(info_slot);
+  float total_ms = 0;
+  cudaEventElapsedTime(&total_ms, ev0, ev1);
+  c.event_pool.push_back(ev0);
+  c.event_pool.push_back(ev1);
+  double ms[PH_COUNT];
+  c.collect_spans(ms);
+  std::ostringstream js;
+  js << "{\"solver\":\"blockls\",\"n_local\":" << n_loc << ",\"n_total\":" << static_cast<int64_t>(n_total_d) << ",\"d\":" << D
+     << ",\"k\":" << k << ",\"block_size\":" << bs << ",\"num_blocks\":" << nb << ",\"num_iter\":" << num_iter
+     << ",\"world\":" << c.world << ",\"total_ms\":" << total_ms << ",\"featurize_ms\":" << ms[PH_FEATURIZE]
+     << ",\"gram_ms\":" << ms[PH_GRAM] << ",\"allreduce_ms\":" << ms[PH_ALLREDUCE] << ",\"solve_ms\":" << ms[PH_SOLVE]
+     << ",\"update_ms\":" << ms[PH_UPDATE] << ",\"other_ms\":" << ms[PH_OTHER] << ",\"local_flops\":" << flops
+     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"tf32x1\"}";
+  c.stats_json = js.str();
+  return c.add(std::move(model));
+}
+
+// ------------------------------------------------------------------------------------ apply
+static std::unique_ptr<Matrix> new_matrix(int64_t rows, int64_t cols) {
+  auto m = std::make_unique<Matrix>();
+  m->rows = rows;
+  m->cols = cols;
+  m->ld = round_up(std::max<int64_t>(cols, 1), kPadCols);
+  m->buf.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(rows, 1) * m->ld));
+  m->d = m->buf.as<float>();
+  return m;
+}
+
+static std::unique_ptr<Matrix> apply_model(Ctx& c, Model& md, FeatSrc& src, int last_block, bool use_means) {
+  const int nb = static_cast<int>(md.brows.size());
+  if (last_block < 0 || last_block >= nb) last_block = nb - 1;
+  int64_t dsum = 0;
+  for (auto r : md.brows) dsum += r;
+  if (dsum > src.D) throw KsError{KS_ERR_INVALID, "model has more features than the input"};
+  const int k = static_cast<int>(md.k);
+  const int64_t n_loc = src.n_rows;
+  auto out = new_matrix(n_loc, k);
+  KS_CUDA(cudaMemsetAsync(out->d, 0, out->buf.bytes, c.st));
+  int bmax = 0;
+  for (auto r : md.brows) bmax = std::max<int>(bmax, static_cast<int>(r));
+  const int64_t lds = round_up(std::max(bmax, 1), 32);
+  const int64_t kpad = round_up(k, 32);
+  DevBuf slab, bop, cbias, shift;
+  slab.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));
+  bop.alloc(sizeof(float) * static_cast<size_t>(kpad) * lds);
+  cbias.alloc(sizeof(float) * kpad);
+  shift.alloc(sizeof(float) * lds);
+  int64_t c0 = 0;
+  for (int j = 0; j <= last_block; ++j) {
+    const int b = static_cast<int>(md.brows[j]);
+    KS_CUDA(cudaMemsetAsync(shift.p, 0, shift.bytes, c.st));
+    if (use_means && md.has_mean) {
+      launch_f64_to_f32_vec(md.mean[j]->as<double>(), shift.as<float>(), b, c.st);
+      c.launches += 1;
+    }
+    produce_slab(c, src, c0, b, shift.as<float>(), slab.as<float>(), lds, 0, n_loc);
+    // the fp32 rounding of the mean is compensated in the bias: cbias = intercept - (mean - fp32(mean)) . W  ~ intercept
+    launch_pack_apply(md.W[j]->as<double>(), nullptr, (j == 0 && md.has_intercept) ? md.intercept.as<double>() : nullptr,
+                      bop.as<float>(), static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), c.st);
+    c.launches += 1;
+    launch_update(c, slab.as<float>(), lds, n_loc, b, bop.as<float>(), lds, k, out->d, nullptr, out->ld, cbias.as<float>(),
+                  EPI_APPLY, j > 0 ? 1 : 0);
+    c0 += md.block_size;
+  }
+  c.check_async("BlockLinearMapper.apply");
+  return out;
+}
+
+}  // namespace ks
+
+// ======================================================================================= C ABI
+using namespace ks;
+
+static std::mutex g_mu;
+static std::unordered_map<int64_t, std::unique_ptr<Ctx>> g_ctxs;
+static int64_t g_next_ctx = 1;
+static thread_local std::string g_global_err;
+
+static Ctx* find_ctx(int64_t h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_ctxs.find(h);
+  return it == g_ctxs.end() ? nullptr : it->second.get();
+}
+
+template <class Fn>
+static int32_t guard(int64_t ctx, Fn&& fn) {
+  Ctx* c = find_ctx(ctx);
+  if (!c) {
+    g_global_err = "unknown context handle " + std::to_string(ctx);
+    return KS_ERR_HANDLE;
+  }
+  try {
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) throw KsError{KS_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)};
+    fn(*c);
+    return KS_OK;
+  } catch (const KsError& e) {
+    c->err = e.msg;
+    cudaGetLastError();
+    return e.code;
+  } catch (const std::exception& e) {
+    c->err = std::string("exception: ") + e.what();
+    return KS_ERR_INVALID;
+  }
+}
+
+extern "C" {
+
+KS_API int32_t ks_version(void) { return 100; }
+
+KS_API int32_t ks_nccl_unique_id(uint8_t* out_id) {
+  try {
+    if (!out_id) throw KsError{KS_ERR_INVALID, "null out_id"};
+    static_assert(sizeof(ncclUniqueId) == KS_NCCL_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    ncclResult_t r = nccl_api().GetUniqueId(&id);
+    if (r != ncclSuccess) throw KsError{KS_ERR_NCCL, std::string("ncclGetUniqueId: ") + nccl_api().GetErrorString(r)};
+    memcpy(out_id, &id, KS_NCCL_ID_BYTES);
+    return KS_OK;
+  } catch (const KsError& e) {
+    g_global_err = e.msg;
+    return e.code;
+  }
+}
+
+KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size, const uint8_t* nccl_id, int64_t* out_ctx) {
+  try {
+    if (!out_ctx || world_size < 1 || rank < 0 || rank >= world_size) throw KsError{KS_ERR_INVALID, "bad arguments"};
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+      cudaGetLastError();
+      throw KsError{KS_ERR_NO_DEVICE, "no CUDA device: keystone_b200 has no CPU fallback"};
+    }
+    if (device_id < 0 || device_id >= ndev) throw KsError{KS_ERR_INVALID, "device_id out of range"};
+    KS_CUDA(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    KS_CUDA(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major != 10) throw KsError{KS_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) + "; this library contains sm_100a code only"};
+    auto c = std::make_unique<Ctx>();
+    c->device = device_id;
+    c->rank = rank;
+    c->world = world_size;
+    c->num_sms = prop.multiProcessorCount;
+    KS_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    if (world_size > 1) {
+      if (!nccl_id) throw KsError{KS_ERR_INVALID, "nccl_id required for world_size > 1"};
+      ncclUniqueId id;
+      memcpy(&id, nccl_id, KS_NCCL_ID_BYTES);
+      KS_NCCL(nccl_api().CommInitRank(&c->comm, world_size, id, rank));
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    const int64_t h = g_next_ctx++;
+    g_ctxs[h] = std::move(c);
+    *out_ctx = h;
+    return KS_OK;
+  } catch (const KsError& e) {
+    g_global_err = e.msg;
+    return e.code;
+  }
+}
+
+KS_API int32_t ks_ctx_destroy(int64_t ctx) {
+  std::unique_ptr<Ctx> c;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_ctxs.find(ctx);
+    if (it == g_ctxs.end()) return KS_ERR_HANDLE;
+    c = std::move(it->second);
+    g_ctxs.erase(it);
+  }
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->st);
+  c->matrices.clear();
+  c->rfs.clear();
+  c->models.clear();
+  c->tile_cache.clear();
+  for (auto e : c->event_pool) cudaEventDestroy(e);
+  if (c->solver) solver_api().Destroy(c->solver);
+  if (c->comm) nccl_api().CommDestroy(c->comm);
+  cudaStreamDestroy(c->st);
+  return KS_OK;
+}
+
+KS_API const char* ks_last_error(int64_t ctx) {
+  Ctx* c = find_ctx(ctx);
+  return c ? c->err.c_str() : g_global_err.c_str();
+}
+
+KS_API int32_t ks_ctx_synchronize(int64_t ctx) {
+  return guard(ctx, [&](Ctx& c) { c.check_async("synchronize"); });
+}
+
+KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
+  return guard(ctx, [&](Ctx& c) {
+    const std::string n = name ? name : "";
+    if (n == "gram_chunk_rows" && value >= kGramStageRows) c.gram_chunk_rows = value;
+    else if (n == "sample_rows" && value >= 1) c.sample_rows = value;
+    else if (n == "timing") c.timing = value != 0;
+    else throw KsError{KS_ERR_INVALID, "unknown option or bad value: " + n};
+  });
+}
+
+KS_API int32_t ks_ctx_launch_count(int64_t ctx, int64_t* out_count) {
+  return guard(ctx, [&](Ctx& c) { *out_count = c.launches; });
+}
+
+// ---------------------------------------------------------------- matrices
+static void upload_rows(Ctx& c, Matrix& m, const void* host, int64_t ld, bool is_f64) {
+  if (m.rows == 0) return;
+  KS_CUDA(cudaMemsetAsync(m.d, 0, m.buf.bytes, c.st));
+  if (!is_f64) {
+    KS_CUDA(cudaMemcpy2DAsync(m.d, sizeof(float) * m.ld, host, sizeof(float) * ld, sizeof(float) * m.cols, m.rows,
+                              cudaMemcpyHostToDevice, c.st));
+    KS_CUDA(cudaStreamSynchronize(c.st));
+    return;
+  }
+  // fp64 host data: stage in chunks of rows, convert on the device
+  const int64_t chunk_rows = std::max<int64_t>(1, (int64_t(256) << 20) / (8 * std::max<int64_t>(m.cols, 1)));
+  DevBuf stage;
+  stage.alloc(sizeof(double) * static_cast<size_t>(std::min(chunk_rows, m.rows) * m.cols));
+  const double* h = static_cast<const double*>(host);
+  for (int64_t r0 = 0; r0 < m.rows; r0 += chunk_rows) {
+    const int64_t nr = std::min(chunk_rows, m.rows - r0);
+    KS_CUDA(cudaMemcpy2DAsync(stage.p, sizeof(double) * m.cols, h + r0 * ld, sizeof(double) * ld, sizeof(double) * m.cols, nr,
+                              cudaMemcpyHostToDevice, c.st));
+    launch_f64_to_f32_rows(stage.as<double>(), m.cols, m.d + r0 * m.ld, m.ld, nr, m.cols, c.st);
+    c.launches += 1;
+    KS_CUDA(cudaStreamSynchronize(c.st));
+  }
+}
+
+KS_API int32_t ks_matrix_from_host_f64(int64_t ctx, const double* rowmajor, int64_t n_rows, int64_t n_cols, int64_t ld, int64_t* out_m) {
+  return guard(ctx, [&](Ctx& c) {
+    if (n_rows < 0 || n_cols <= 0 || ld < n_cols || (!rowmajor && n_rows > 0) || !out_m) throw KsError{KS_ERR_INVALID, "bad matrix arguments"};
+    auto m = new_matrix(n_rows, n_cols);
+    upload_rows(c, *m, rowmajor, ld, true);
+    *out_m = c.add(std::move(m));
+  });
+}
+KS_API int32_t ks_matrix_from_host_f32(int64_t ctx, const float* rowmajor, int64_t n_rows, int64_t n_cols, int64_t ld, int64_t* out_m) {
+  return guard(ctx, [&](Ctx& c) {
+    if (n_rows < 0 || n_cols <= 0 || ld < n_cols || (!rowmajor && n_rows > 0) || !out_m) throw KsError{KS_ERR_INVALID, "bad matrix arguments"};
+    auto m = new_matrix(n_rows, n_cols);
+    upload_rows(c, *m, rowmajor, ld, false);
+    *out_m = c.add(std::move(m));
+  });
+}
+KS_API int32_t ks_matrix_synthetic_normal(int64_t ctx, int64_t n_rows, int64_t n_cols, uint64_t seed, int64_t global_row_offset,
+                                   double mean, double stddev, int64_t* out_m) {
+  return guard(ctx, [&](Ctx& c) {
+    if (n_rows < 0 || n_cols <= 0 || !out_m) throw KsError{KS_ERR_INVALID, "bad matrix arguments"};
+    auto m = new_matrix(n_rows, n_cols);
+    launch_normal_f32(m->d, m->ld, n_rows, static_cast<int>(n_cols), seed, global_row_offset, static_cast<float>(mean),
+                      static_cast<float>(stddev), c.st);
+    c.launches += 1;
+    c.check_async("synthetic_normal");
+    *out_m = c.add(std::move(m));
+  });
+}
+KS_API int32_t ks_labels_from_classes(int64_t ctx, const int32_t* classes, int64_t n_rows, int32_t num_classes, int64_t* out_m) {
+  return guard(ctx, [&](Ctx& c) {
+    if (n_rows < 0 || num_classes <= 0 || (!classes && n_rows > 0) || !out_m) throw KsError{KS_ERR_INVALID, "bad label arguments"};
+    for (int64_t i = 0; i < n_rows; ++i)
+      if (classes[i] < 0 || classes[i] >= num_classes) throw KsError{KS_ERR_INVALID, "class index out of range at row " + std::to_string(i)};
+    auto m = new_matrix(n_rows, num_classes);
+    DevBuf cls;
+    cls.alloc(sizeof(int32_t) * static_cast<size_t>(std::max<int64_t>(n_rows, 1)));
+    KS_CUDA(cudaMemcpyAsync(cls.p, classes, sizeof(int32_t) * n_rows, cudaMemcpyHostToDevice, c.st));
+    launch_labels_from_classes(cls.as<int32_t>(), m->d, m->ld, n_rows, num_classes, c.st);
+    c.launches += 1;
+    c.check_async("labels_from_classes");
+    *out_m = c.add(std::move(m));
+  });
+}
+KS_API int32_t ks_matrix_shape(int64_t ctx, int64_t m, int64_t* n_rows, int64_t* n_cols) {
+  return guard(ctx, [&](Ctx& c) {
+    Matrix& mm = c.matrix(m);
+    if (n_rows) *n_rows = mm.rows;
+    if (n_cols) *n_cols = mm.cols;
+  });
+}
+KS_API int32_t ks_matrix_to_host_f32(int64_t ctx, int64_t m, float* out, int64_t ld) {
+  return guard(ctx, [&](Ctx& c) {
+    Matrix& mm = c.matrix(m);
+    if (!out || ld < mm.cols) throw KsError{KS_ERR_INVALID, "bad output buffer"};
+    if (mm.rows == 0) return;
+    KS_CUDA(cudaMemcpy2DAsync(out, sizeof(float) * ld, mm.d, sizeof(float) * mm.ld, sizeof(float) * mm.cols, mm.rows,
+                              cudaMemcpyDeviceToHost, c.st));
+    c.check_async("matrix_to_host_f32");
+  });
+}
+KS_API int32_t ks_matrix_to_host_f64(int64_t ctx, int64_t m, double* out, int64_t ld) {
+  return guard(ctx, [&](Ctx& c) {
+    Matrix& mm = c.matrix(m);
+    if (!out || ld < mm.cols) throw KsError{KS_ERR_INVALID, "bad output buffer"};
+    if (mm.rows == 0) return;
+    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t(256) << 20) / (8 * mm.cols));
+    DevBuf stage;
+    stage.alloc(sizeof(double) * static_cast<size_t>(std::min(chunk_rows, mm.rows) * mm.cols));
+    for (int64_t r0 = 0; r0 < mm.rows; r0 += chunk_rows) {
+      const int64_t nr = std::min(chunk_rows, mm.rows - r0);
+      launch_f32_to_f64_rows(mm.d + r0 * mm.ld, mm.ld, stage.as<double>(), mm.cols, nr, mm.cols, c.st);
+      c.launches += 1;
+      KS_CUDA(cudaMemcpy2DAsync(out + r0 * ld, sizeof(double) * ld, stage.p, sizeof(double) * mm.cols, sizeof(double) * mm.cols, nr,
+                                cudaMemcpyDeviceToHost, c.st));
+      KS_CUDA(cudaStreamSynchronize(c.st));
+    }
+  });
+}
+KS_API int32_t ks_matrix_destroy(int64_t ctx, int64_t m) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!c.matrices.erase(m)) throw KsError{KS_ERR_HANDLE, "unknown matrix handle"};
+  });
+}
+
+// ---------------------------------------------------------------- CosineRandomFeatures
+KS_API int32_t ks_cosine_rf_create(int64_t ctx, const double* W_colmajor, const double* b, int64_t n_out, int64_t n_in, int64_t* out_rf) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!W_colmajor || !b || n_out <= 0 || n_in <= 0 || !out_rf) throw KsError{KS_ERR_INVALID, "bad CosineRandomFeatures arguments"};
+    auto r = std::make_unique<CosRF>();
+    r->n_out = n_out;
+    r->n_in = n_in;
+    r->ld = round_up(n_in, kPadCols);
+    r->wbuf.alloc(sizeof(float) * static_cast<size_t>(n_out * r->ld));
+    r->bbuf.alloc(sizeof(float) * static_cast<size_t>(n_out));
+    r->W = r->wbuf.as<float>();
+    r->bias = r->bbuf.as<float>();
+    DevBuf stage;
+    stage.alloc(sizeof(double) * static_cast<size_t>(n_out * n_in + n_out));
+    KS_CUDA(cudaMemcpyAsync(stage.p, W_colmajor, sizeof(double) * n_out * n_in, cudaMemcpyHostToDevice, c.st));
+    KS_CUDA(cudaMemcpyAsync(stage.as<double>() + n_out * n_in, b, sizeof(double) * n_out, cudaMemcpyHostToDevice, c.st));
+    launch_w_to_operand(stage.as<double>(), n_out, n_in, r->W, r->ld, c.st);
+    launch_f64_to_f32_vec(stage.as<double>() + n_out * n_in, r->bias, n_out, c.st);
+    c.launches += 2;
+    c.check_async("cosine_rf_create");
+    const int64_t id = c.next_id++;
+    c.rfs[id] = std::move(r);
+    *out_rf = id;
+  });
+}
+KS_API int32_t ks_cosine_rf_apply(int64_t ctx, int64_t rf, int64_t x_in, int64_t* out_features) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!out_features) throw KsError{KS_ERR_INVALID, "null output"};
+    FeatSrc src;
+    make_feat_src(c, 0, x_in, &rf, 1, src);
+    auto out = new_matrix(src.n_rows, src.D);
+    KS_CUDA(cudaMemsetAsync(out->d, 0, out->buf.bytes, c.st));
+    produce_slab(c, src, 0, src.D, src.zeros.as<float>(), out->d, out->ld, 0, src.n_rows, /*round_out=*/false);
+    c.check_async("CosineRandomFeatures.apply");
+    *out_features = c.add(std::move(out));
+  });
+}
+KS_API int32_t ks_cosine_rf_destroy(int64_t ctx, int64_t rf) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!c.rfs.erase(rf)) throw KsError{KS_ERR_HANDLE, "unknown CosineRandomFeatures handle"};
+  });
+}
+
+// ---------------------------------------------------------------- estimators
+KS_API int32_t ks_blockls_fit(int64_t ctx, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, int64_t labels,
+                       int32_t block_size, int32_t num_iter, double lambda, int64_t num_features_or_0, int32_t precision_mode,
+                       int64_t* out_model) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!out_model) throw KsError{KS_ERR_INVALID, "null out_model"};
+    if (precision_mode != KS_PRECISION_TF32) throw KsError{KS_ERR_INVALID, "unsupported precision_mode"};
+    FeatSrc src;
+    make_feat_src(c, features, x_in, rfs, n_rfs, src);
+    *out_model = fit_blockls(c, src, c.matrix(labels), block_size, num_iter, lambda, num_features_or_0);
+  });
+}
+
+KS_API int32_t ks_blockwls_fit(int64_t ctx, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, int64_t labels,
+                        int32_t block_size, int32_t num_iter, double lambda, double mixture_weight, int64_t num_features_or_0,
+                        int32_t precision_mode, int64_t* out_model) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!out_model) throw KsError{KS_ERR_INVALID, "null out_model"};
+    if (precision_mode != KS_PRECISION_TF32) throw KsError{KS_ERR_INVALID, "unsupported precision_mode"};
+    FeatSrc src;
+    make_feat_src(c, features, x_in, rfs, n_rfs, src);
+    *out_model = fit_bwls(c, src, c.matrix(labels), block_size, num_iter, lambda, mixture_weight, num_features_or_0);
+  });
+}
+
+KS_API int32_t ks_linear_map_fit(int64_t ctx, int64_t features, int64_t labels, int32_t has_lambda, double lambda, int64_t* out_model) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!out_model) throw KsError{KS_ERR_INVALID, "null out_model"};
+    FeatSrc src;
+    make_feat_src(c, features, 0, nullptr, 0, src);
+    // one block spanning every feature, one pass: exactly (A^T A [+ lambda I]) \ A^T y on centred data
+    *out_model = fit_blockls(c, src, c.matrix(labels), static_cast<int>(src.D), 1, has_lambda ? lambda : 0.0, 0);
+  });
+}
+
+// ---------------------------------------------------------------- models
+KS_API int32_t ks_model_from_host(int64_t ctx, const double* const* xs, const int64_t* block_rows, int32_t n_blocks, int64_t k,
+                           const double* b_or_null, const double* const* means_or_null, int32_t block_size, int64_t* out_model) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!xs || !block_rows || n_blocks <= 0 || k <= 0 || block_size <= 0 || !out_model) throw KsError{KS_ERR_INVALID, "bad model arguments"};
+    auto m = std::make_unique<Model>();
+    m->block_size = block_size;
+    m->k = k;
+    m->has_mean = means_or_null != nullptr;
+    m->has_intercept = b_or_null != nullptr;
+    for (int j = 0; j < n_blocks; ++j) {
+      const int64_t b = block_rows[j];
+      if (b <= 0 || b > block_size) throw KsError{KS_ERR_INVALID, "block_rows out of range"};
+      auto W = std::make_unique<DevBuf>();
+      W->alloc(sizeof(double) * static_cast<size_t>(b * k));
+      KS_CUDA(cudaMemcpyAsync(W->p, xs[j], sizeof(double) * b * k, cudaMemcpyHostToDevice, c.st));
+      m->W.push_back(std::move(W));
+      m->brows.push_back(b);
+      if (m->has_mean) {
+        auto mu = std::make_unique<DevBuf>();
+        mu->alloc(sizeof(double) * static_cast<size_t>(b));
+        KS_CUDA(cudaMemcpyAsync(mu->p, means_or_null[j], sizeof(double) * b, cudaMemcpyHostToDevice, c.st));
+        m->mean.push_back(std::move(mu));
+      }
+    }
+    m->intercept.alloc(sizeof(double) * static_cast<size_t>(k));
+    if (b_or_null) KS_CUDA(cudaMemcpyAsync(m->intercept.p, b_or_null, sizeof(double) * k, cudaMemcpyHostToDevice, c.st));
+    KS_CUDA(cudaStreamSynchronize(c.st));
+    *out_model = c.add(std::move(m));
+  });
+}
+KS_API int32_t ks_model_num_blocks(int64_t ctx, int64_t model, int32_t* n_blocks, int64_t* k, int32_t* block_size) {
+  return guard(ctx, [&](Ctx& c) {
+    Model& m = c.model(model);
+    if (n_blocks) *n_blocks = static_cast<int32_t>(m.brows.size());
+    if (k) *k = m.k;
+    if (block_size) *block_size = m.block_size;
+  });
+}
+KS_API int32_t ks_model_block_rows(int64_t ctx, int64_t model, int32_t j, int64_t* rows) {
+  return guard(ctx, [&](Ctx& c) {
+    Model& m = c.model(model);
+    if (j < 0 || j >= static_cast<int>(m.brows.size()) || !rows) throw KsError{KS_ERR_INVALID, "block index out of range"};
+    *rows = m.brows[j];
+  });
+}
+KS_API int32_t ks_model_get_block(int64_t ctx, int64_t model, int32_t j, double* W_out, double* mean_out, int32_t* has_mean) {
+  return guard(ctx, [&](Ctx& c) {
+    Model& m = c.model(model);
+    if (j < 0 || j >= static_cast<int>(m.brows.size())) throw KsError{KS_ERR_INVALID, "block index out of range"};
+    if (W_out) KS_CUDA(cudaMemcpyAsync(W_out, m.W[j]->p, sizeof(double) * m.brows[j] * m.k, cudaMemcpyDeviceToHost, c.st));
+    if (mean_out && m.has_mean) KS_CUDA(cudaMemcpyAsync(mean_out, m.mean[j]->p, sizeof(double) * m.brows[j], cudaMemcpyDeviceToHost, c.st));
+    if (has_mean) *has_mean = m.has_mean ? 1 : 0;
+    KS_CUDA(cudaStreamSynchronize(c.st));
+  });
+}
+KS_API int32_t ks_model_get_intercept(int64_t ctx, int64_t model, double* b_out, int32_t* has_intercept) {
+  return guard(ctx, [&](Ctx& c) {
+    Model& m = c.model(model);
+    if (has_intercept) *has_intercept = m.has_intercept ? 1 : 0;
+    if (b_out && m.has_intercept) {
+      KS_CUDA(cudaMemcpyAsync(b_out, m.intercept.p, sizeof(double) * m.k, cudaMemcpyDeviceToHost, c.st));
+      KS_CUDA(cudaStreamSynchronize(c.st));
+    }
+  });
+}
+KS_API int32_t ks_model_apply(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, int64_t* out) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!out) throw KsError{KS_ERR_INVALID, "null output"};
+    FeatSrc src;
+    make_feat_src(c, features, x_in, rfs, n_rfs, src);
+    *out = c.add(apply_model(c, c.model(model), src, -1, true));
+  });
+}
+KS_API int32_t ks_model_apply_partial(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
+                               int32_t last_block, int64_t* out) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!out) throw KsError{KS_ERR_INVALID, "null output"};
+    FeatSrc src;
+    make_feat_src(c, features, x_in, rfs, n_rfs, src);
+    *out = c.add(apply_model(c, c.model(model), src, last_block, true));
+  });
+}
+KS_API int32_t ks_model_apply_argmax(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
+                              int32_t* host_out) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!host_out) throw KsError{KS_ERR_INVALID, "null output"};
+    FeatSrc src;
+    make_feat_src(c, features, x_in, rfs, n_rfs, src);
+    auto y = apply_model(c, c.model(model), src, -1, true);
+    DevBuf idx;
+    idx.alloc(sizeof(int32_t) * static_cast<size_t>(std::max<int64_t>(y->rows, 1)));
+    launch_argmax_rows(y->d, y->ld, y->rows, static_cast<int>(y->cols), idx.as<int32_t>(), c.st);
+    c.launches += 1;
+    KS_CUDA(cudaMemcpyAsync(host_out, idx.p, sizeof(int32_t) * y->rows, cudaMemcpyDeviceToHost, c.st));
+    c.check_async("apply_argmax");
+  });
+}
+KS_API int32_t ks_model_cost(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
+                      int64_t labels, double lambda, double* out_cost) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!out_cost) throw KsError{KS_ERR_INVALID, "null output"};
+    Model& m = c.model(model);
+    Matrix& L = c.matrix(labels);
+    FeatSrc src;
+    make_feat_src(c, features, x_in, rfs, n_rfs, src);
+    if (L.rows != src.n_rows || L.cols != m.k) throw KsError{KS_ERR_INVALID, "labels shape mismatch"};
+    auto y = apply_model(c, m, src, -1, /*use_means=*/false);  // computeCost applies no feature scalers (:149-156)
+    DevBuf acc;  // [0] squared error, [1] row count, [2] ||W||^2
+    acc.alloc(sizeof(double) * 3);
+    KS_CUDA(cudaMemsetAsync(acc.p, 0, acc.bytes, c.st));
+    launch_sq_err(y->d, y->ld, L.d, L.ld, L.rows, static_cast<int>(m.k), acc.as<double>(), c.st);
+    c.launches += 1;
+    const double nl = static_cast<double>(L.rows);
+    KS_CUDA(cudaMemcpyAsync(acc.as<double>() + 1, &nl, sizeof(double), cudaMemcpyHostToDevice, c.st));
+    KS_CUDA(cudaStreamSynchronize(c.st));
+    c.allreduce_f64(acc.as<double>(), 2);
+    for (size_t j = 0; j < m.W.size(); ++j) {
+      sumsq_f64_kernel<<<64, 256, 0, c.st>>>(m.W[j]->as<double>(), m.brows[j] * m.k, acc.as<double>() + 2);
+      c.launches += 1;
+    }
+    double h[3];
+    KS_CUDA(cudaMemcpyAsync(h, acc.p, sizeof(h), cudaMemcpyDeviceToHost, c.st));
+    c.check_async("computeCost");
+    *out_cost = h[0] / (2.0 * h[1]) + (lambda == 0 ? 0.0 : lambda / 2.0 * h[2]);
+  });
+}
+KS_API int32_t ks_model_destroy(int64_t ctx, int64_t model) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!c.models.erase(model)) throw KsError{KS_ERR_HANDLE, "unknown model handle"};
+  });
+}
+
+KS_API int32_t ks_last_fit_stats_json(int64_t ctx, char* buf, int64_t buflen) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!buf || buflen <= 0) throw KsError{KS_ERR_INVALID, "bad buffer"};
+    const std::string& s = c.stats_json;
+    if (static_cast<int64_t>(s.size()) + 1 > buflen) throw KsError{KS_ERR_INVALID, "buffer too small"};
+    memcpy(buf, s.c_str(), s.size() + 1);
+  });
+}
+
+// ---------------------------------------------------------------- debug / micro-benchmarks
+static void debug_gram_run(Ctx& c, Matrix& A, Matrix& B, DevBuf& gc, int* ldg, int* ldc) {
+  if (A.rows != B.rows) throw KsError{KS_ERR_INVALID, "row mismatch"};
+  const int b = static_cast<int>(A.cols), kc = static_cast<int>(B.cols);
+  *ldg = static_cast<int>(round_up(b, 32));
+  *ldc = static_cast<int>(round_up(kc, 32));
+  const size_t ge = static_cast<size_t>(b) * *ldg, ce = static_cast<size_t>(b) * *ldc;
+  gc.alloc(sizeof(float) * (ge + ce));
+  KS_CUDA(cudaMemsetAsync(gc.p, 0, gc.bytes, c.st));
+  launch_gram_block(c, A.d, A.ld, A.rows, b, B.d, B.ld, kc, gc.as<float>(), *ldg, gc.as<float>() + ge, *ldc, true, true);
+}
+KS_API int32_t ks_debug_gram(int64_t ctx, int64_t a, int64_t b, double* out_g, int64_t ld_g, double* out_c, int64_t ld_c) {
+  return guard(ctx, [&](Ctx& c) {
+    Matrix& A = c.matrix(a);
+    Matrix& B = c.matrix(b);
+    DevBuf gc;
+    int ldg, ldc;
+    debug_gram_run(c, A, B, gc, &ldg, &ldc);
+    c.check_async("debug_gram");
+    const int m = static_cast<int>(A.cols), kc = static_cast<int>(B.cols);
+    std::vector<float> h(gc.bytes / sizeof(float));
+    KS_CUDA(cudaMemcpy(h.data(), gc.p, gc.bytes, cudaMemcpyDeviceToHost));
+    const float* G = h.data();
+    const float* C = h.data() + static_cast<size_t>(m) * ldg;
+    if (out_g)
+      for (int r = 0; r < m; ++r)
+        for (int q = 0; q < m; ++q) out_g[r * ld_g + q] = G[static_cast<size_t>(std::min(r, q)) * ldg + std::max(r, q)];
+    if (out_c)
+      for (int r = 0; r < m; ++r)
+        for (int q = 0; q < kc; ++q) out_c[r * ld_c + q] = C[static_cast<size_t>(r) * ldc + q];
+  });
+}
+KS_API int32_t ks_debug_time_gram(int64_t ctx, int64_t a, int64_t b, int32_t iters, double* out_ms) {
+  return guard(ctx, [&](Ctx& c) {
+    Matrix& A = c.matrix(a);
+    Matrix& B = c.matrix(b);
+    DevBuf gc;
+    int ldg, ldc;
+    debug_gram_run(c, A, B, gc, &ldg, &ldc);  // warm-up + allocation
+    const size_t ge = static_cast<size_t>(A.cols) * ldg;
+    cudaEvent_t e0 = c.get_event(), e1 = c.get_event();
+    KS_CUDA(cudaEventRecord(e0, c.st));
+    for (int i = 0; i < iters; ++i)
+      launch_gram_block(c, A.d, A.ld, A.rows, static_cast<int>(A.cols), B.d, B.ld, static_cast<int>(B.cols), gc.as<float>(), ldg,
+                        gc.as<float>() + ge, ldc, true, true);
+    KS_CUDA(cudaEventRecord(e1, c.st));
+    c.check_async("debug_time_gram");
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    c.event_pool.push_back(e0);
+    c.event_pool.push_back(e1);
+    *out_ms = ms / std::max(iters, 1);
+  });
+}
+
+}  // extern "C"

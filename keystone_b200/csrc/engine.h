@@ -1,0 +1,167 @@
+// Host-side engine state shared by engine.cu (C ABI, BlockLS, apply) and bwls.cu (weighted solver).
+#pragma once
+#include <cuda_runtime.h>
+#include <cusolverDn.h>
+#include <nccl.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/keystone_b200.h"
+#include "kernels.h"
+
+namespace ks {
+
+struct KsError {
+  int code;
+  std::string msg;
+};
+
+#define KS_CUDA(call)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e__ = (call);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      throw ::ks::KsError{KS_ERR_CUDA, std::string(#call) + " failed: " + cudaGetErrorString(e__)};    \
+  } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  void alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    KS_CUDA(cudaMalloc(&p, n));
+    bytes = n;
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+struct Matrix {  // fp32 row-major, ld % 32 == 0, padding columns are zero
+  DevBuf buf;
+  float* d = nullptr;
+  int64_t rows = 0, cols = 0, ld = 0;
+};
+
+struct CosRF {
+  DevBuf wbuf, bbuf;
+  float* W = nullptr;     // [n_out][ld] tf32-rounded, K-major GEMM operand
+  float* bias = nullptr;  // [n_out]
+  int64_t n_out = 0, n_in = 0, ld = 0;
+};
+
+struct Model {  // BlockLinearMapper state (K/nodes/learning/BlockLinearMapper.scala:22-33)
+  int block_size = 0;
+  int64_t k = 0;
+  std::vector<int64_t> brows;
+  std::vector<std::unique_ptr<DevBuf>> W;     // column-major (rows_j x k) fp64
+  std::vector<std::unique_ptr<DevBuf>> mean;  // rows_j fp64 (if has_mean)
+  DevBuf intercept;                           // k fp64
+  bool has_mean = false, has_intercept = false;
+};
+
+struct SolverApi {
+  void* lib = nullptr;
+  cusolverStatus_t (*Create)(cusolverDnHandle_t*) = nullptr;
+  cusolverStatus_t (*Destroy)(cusolverDnHandle_t) = nullptr;
+  cusolverStatus_t (*SetStream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+  cusolverStatus_t (*DpotrfBufferSize)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, int*) = nullptr;
+  cusolverStatus_t (*Dpotrf)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, double*, int, int*) = nullptr;
+  cusolverStatus_t (*Dpotrs)(cusolverDnHandle_t, cublasFillMode_t, int, int, const double*, int, double*, int, int*) = nullptr;
+};
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+SolverApi& solver_api();  // throws KsError if libcusolver cannot be loaded
+NcclApi& nccl_api();      // throws KsError if libnccl cannot be loaded
+
+enum Phase { PH_FEATURIZE = 0, PH_GRAM, PH_ALLREDUCE, PH_SOLVE, PH_UPDATE, PH_OTHER, PH_COUNT };
+
+struct Ctx {
+  int device = 0, rank = 0, world = 1;
+  int num_sms = 148;
+  cudaStream_t st = nullptr;
+  ncclComm_t comm = nullptr;
+  cusolverDnHandle_t solver = nullptr;
+  DevBuf solver_work;
+  int solver_lwork = 0;
+  DevBuf dev_info;  // int[kMaxInfo]
+  std::string err;
+  std::string stats_json;
+  int64_t launches = 0;
+  int64_t gram_chunk_rows = 4096;
+  int64_t sample_rows = 16384;
+  int64_t next_id = 1;
+  std::unordered_map<int64_t, std::unique_ptr<Matrix>> matrices;
+  std::unordered_map<int64_t, std::unique_ptr<CosRF>> rfs;
+  std::unordered_map<int64_t, std::unique_ptr<Model>> models;
+  std::map<std::vector<int>, std::unique_ptr<DevBuf>> tile_cache;
+  // phase timing of the current fit
+  struct Span { int phase; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> event_pool;
+  bool timing = true;
+
+  Matrix& matrix(int64_t h);
+  CosRF& rf(int64_t h);
+  Model& model(int64_t h);
+  int64_t add(std::unique_ptr<Matrix> m);
+  int64_t add(std::unique_ptr<Model> m);
+  cudaEvent_t get_event();
+  void span_begin(int phase);
+  void span_end();
+  void collect_spans(double out_ms[PH_COUNT]);
+  void allreduce_f32(float* p, size_t n);
+  void allreduce_f64(double* p, size_t n);
+  void ensure_solver();
+  void potrf(double* H, int n, int info_slot);
+  void potrs(const double* H, int n, double* B, int nrhs, int info_slot);
+  void check_infos(int used_slots);
+  void check_async(const char* what);
+};
+
+// Feature source: a materialised matrix or raw input + concatenated CosineRandomFeatures parameters.
+struct FeatSrc {
+  Matrix* F = nullptr;
+  Matrix* X = nullptr;
+  DevBuf xop;   // tf32-rounded copy of X (GEMM operand)
+  DevBuf wcat, bcat;
+  float* Wall = nullptr;
+  float* ball = nullptr;
+  int64_t ldw = 0, d_in = 0;
+  int64_t D = 0, n_rows = 0;
+  DevBuf zeros;  // max(D-block, d_in) zero floats
+};
+void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out);
+// slab[rows x lds] = round_tf32(features[row_begin : row_begin+rows, c0 : c0+cols] - shift)   (shift may be the zero vector)
+void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, float* slab, int64_t lds,
+                  int64_t row_begin, int64_t rows, bool round_out = true);
+const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, int* num_tiles);
+void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* R, int64_t ldr, int kcols,
+                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c);
+void launch_update(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* bop, int64_t ldb, int k,
+                   float* r_hi, float* r_lo, int64_t ldr, const float* cbias, int epi, int accumulate);
+
+int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, double w, int64_t nf_opt);
+
+}  // namespace ks

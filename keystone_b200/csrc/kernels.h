@@ -1,0 +1,92 @@
+// Internal (C++) interface between the host engine (engine.cu) and the CUDA kernels.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ks {
+
+static constexpr int kGramStageRows = 32;  // rows per TMA stage of the Gram kernel
+static constexpr int kPadCols = 32;        // every device matrix has ld % 32 == 0 (128 B rows)
+
+enum { EPI_COS = 0, EPI_UPDATE = 1, EPI_APPLY = 2 };
+
+struct GramTile {
+  int m_blk;  // 128-wide block of A's columns
+  int n_blk;  // BN-wide block of B's columns
+  int which;  // 0: B = tmB0 -> out0,  1: B = tmB1 -> out1
+  int pad;
+};
+struct GramOut {
+  float* ptr;
+  int ld;
+  int m_valid;
+  int n_valid;
+};
+struct GramLaunch {
+  CUtensorMap tmA, tmB0, tmB1;
+  const GramTile* tiles;  // device
+  int num_tiles;
+  int rows;        // contraction length (rows of A and B)
+  int chunk_rows;  // split of the contraction across CTAs (multiple of kGramStageRows)
+  int bn;          // 256
+  GramOut out0, out1;
+};
+struct KmParams {
+  float* out_hi;
+  float* out_lo;  // may be null
+  const float* vec0;
+  const float* vec1;
+  int ld_out;
+  int M, N, K;
+  int n_keep;      // columns >= n_keep are left untouched (EPI_UPDATE / EPI_APPLY)
+  int accumulate;  // EPI_APPLY: add to the existing output
+};
+struct KmLaunch {
+  CUtensorMap tmA, tmB;
+  KmParams p;
+  int epi;
+  int num_sms;
+};
+
+int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+cudaError_t launch_gram(const GramLaunch& g, cudaStream_t st);
+cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st);
+unsigned int read_wait_timeout_flag();
+
+// ---- element-wise / reduction helpers (aux_kernels.cu) ----
+void launch_f64_to_f32_rows(const double* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int64_t cols,
+                            cudaStream_t st);
+void launch_f32_to_f64_rows(const float* src, int64_t src_ld, double* dst, int64_t dst_ld, int64_t rows, int64_t cols,
+                            cudaStream_t st);
+void launch_labels_from_classes(const int32_t* cls, float* dst, int64_t ld, int64_t rows, int k, cudaStream_t st);
+// column sums of [rows x cols] (optionally hi + lo planes) accumulated into fp64 sums[cols] (must be zeroed)
+void launch_colsum(const float* hi, const float* lo, int64_t ld, int64_t rows, int cols, double* sums, cudaStream_t st);
+// labels/residual initialisation: R_hi/R_lo[:, :k] = split(Y - ymean), column k = 1, columns > k = 0
+void launch_init_residual(const float* Y, int64_t ldy, const double* ymean, float* r_hi, float* r_lo, int64_t ldr,
+                          int64_t rows, int k, cudaStream_t st);
+// slab[:, :cols] = tf32(F[:, c0:c0+cols] - shift)  (+ lo remainder plane)
+void launch_center_round(const float* F, int64_t ldf, int c0, const float* shift, float* s_hi, float* s_lo, int64_t lds,
+                         int64_t rows, int cols, cudaStream_t st);
+// H (fp64, column-major b x b, ld = b) = sym(G) - n * d d^T + lam * I,  d = C[:, k_ones] / n
+void launch_build_system(const float* G, int ldg, const float* C, int ldc, int k_ones, double n_total, double lam,
+                         double* H, double* delta, int b, cudaStream_t st);
+// RHS (fp64 column-major b x k, ld = b) = C[:, :k] - n * delta * rbar^T - lam * Wold
+void launch_build_rhs(const float* C, int ldc, const double* delta, const double* rsum, double n_total, double lam,
+                      const double* Wold, double* rhs, int b, int k, cudaStream_t st);
+// Wmodel += dW;  Bop_hi/lo [kpad x ldb] = split(dW^T);  cbias[c] = sum_f delta[f] dW[f][c]
+void launch_pack_update(const double* dW, double* Wmodel, const double* delta, float* bop_hi, float* bop_lo, int ldb,
+                        float* cbias, int b, int k, int kpad, cudaStream_t st);
+// Bop [kpad x ldb] = split(W^T) for apply; cbias[c] = (add_intercept ? intercept[c] : 0) - sum_f mean[f] W[f][c]
+void launch_pack_apply(const double* W, const double* mean_or_null, const double* intercept_or_null, float* bop_hi,
+                       int ldb, float* cbias, int b, int k, int kpad, cudaStream_t st);
+void launch_argmax_rows(const float* Y, int64_t ld, int64_t rows, int k, int32_t* out, cudaStream_t st);
+void launch_sq_err(const float* Y, int64_t ldy, const float* L, int64_t ldl, int64_t rows, int k, double* out,
+                   cudaStream_t st);
+void launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
+void launch_normal_f32(float* dst, int64_t ld, int64_t rows, int cols, uint64_t seed, int64_t row_offset, float mean,
+                       float stddev, cudaStream_t st);
+void launch_w_to_operand(const double* W_colmajor, int64_t n_out, int64_t n_in, float* dst, int64_t ld, cudaStream_t st);
+void launch_f64_to_f32_vec(const double* src, float* dst, int64_t n, cudaStream_t st);
+
+}  // namespace ks

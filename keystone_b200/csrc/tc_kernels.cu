@@ -1,0 +1,450 @@
+// Tensor-core kernels of the block least-squares hot path (sm_100a, tcgen05 + TMA + TMEM).
+//
+//   gram_tn_kernel    D[M x N] += A^T B over a chunk of rows, A [rows x M] and B [rows x N] both
+//                     row-major (contraction over the slow axis => both operands MN-major).
+//                     Replaces the per-partition (A^T A, A^T R) + treeReduce of the reference
+//                     (K/nodes/learning/BlockWeightedLeastSquares.scala:212-214 and the mlmatrix
+//                     NormalEquations called from K/nodes/learning/BlockLinearMapper.scala:236-239).
+//   gemm_kmajor_kernel D[M x N] = A B^T, A [M x K] and B [N x K] row-major (K-major operands),
+//                     persistent, TMEM double-buffered, with three fused epilogues:
+//                       EPI_COS     cos(acc + bias) - shift, rounded to tf32   (CosineRandomFeatures.scala:30-32)
+//                       EPI_UPDATE  R <- R - acc + cbias                        (BlockWeightedLeastSquares.scala:287-290)
+//                       EPI_APPLY   Y <- [Y +] acc + cbias                      (BlockLinearMapper.scala:55-70)
+#include "tc_common.cuh"
+#include "kernels.h"
+
+namespace ks {
+
+static constexpr int kThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+__host__ __device__ constexpr uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
+
+// =====================================================================================
+// Gram / A^T B kernel (MN-major operands, split over row chunks, fp32 red.add epilogue)
+// =====================================================================================
+template <int BN, int SR, int STAGES>
+struct GramCfg {
+  static constexpr int BM = 128;
+  static constexpr int A_BYTES = BM * SR * 4;
+  static constexpr int B_BYTES = BN * SR * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BOX_BYTES = SR * 128;  // one TMA box: 32 floats (128 B) x SR rows
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN, int SR, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+gram_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+               const __grid_constant__ CUtensorMap tmB1, const GramTile* __restrict__ tiles, int num_tiles, int rows,
+               int chunk_rows, GramOut out0, GramOut out1) {
+  using Cfg = GramCfg<BN, SR, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const GramTile tile = tiles[blockIdx.x % num_tiles];
+  const int chunk = blockIdx.x / num_tiles;
+  const int row0 = chunk * chunk_rows;
+  const int nrows = min(chunk_rows, rows - row0);
+  const int ksteps = (nrows + SR - 1) / SR;
+  const int m0 = tile.m_blk * Cfg::BM;
+  const int n0 = tile.n_blk * BN;
+  const CUtensorMap* tmB = tile.which ? &tmB1 : &tmB0;
+  constexpr uint32_t kTmemCols = tmem_cols_for(BN);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(tmB);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (ks / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+        uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
+        uint8_t* sB = sA + Cfg::A_BYTES;
+        const int r = row0 + ks * SR;
+#pragma unroll
+        for (int i = 0; i < Cfg::BM / 32; ++i) tma_load_2d(sA + i * Cfg::BOX_BYTES, &tmA, &full_bar[s], m0 + 32 * i, r);
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) tma_load_2d(sB + i * Cfg::BOX_BYTES, tmB, &full_bar[s], n0 + 32 * i, r);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_tf32(Cfg::BM, BN, 1, 1);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (ks / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t sB = sA + Cfg::A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < SR / 8; ++kk) {
+          // MN-major, 128B swizzle: 32-float MN chunks are BOX_BYTES apart (LBO), 8-row K groups 1024 B apart (SBO)
+          const uint64_t ad = make_smem_desc_sw128(sA + kk * 1024, Cfg::BOX_BYTES, 1024);
+          const uint64_t bd = make_smem_desc_sw128(sB + kk * 1024, Cfg::BOX_BYTES, 1024);
+          umma_tf32(tmem_base, ad, bd, idesc, (ks | kk) != 0);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // epilogue: warp w owns TMEM lanes [32*(w&3), +32) == output rows m0 + 32*(w&3) + lane
+    const int q = warp & 3;
+    const GramOut out = tile.which ? out1 : out0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int m = m0 + q * 32 + lane;
+    float* orow = out.ptr + static_cast<size_t>(m) * out.ld;
+    const bool row_ok = m < out.m_valid;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (n0 + c0 >= out.n_valid) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int n = n0 + c0 + i;
+          if (n < out.n_valid) red_add_f32(orow + n, __uint_as_float(v[i]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// =====================================================================================
+// K-major GEMM with fused epilogues (persistent, double-buffered TMEM accumulator)
+// =====================================================================================
+template <int BN, int STAGES>
+struct KmCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 32;  // 32 fp32 = 128 B = one swizzle row
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ float cos_reduced(float x) {
+  // Cody-Waite reduction to [-pi, pi] then the SFU cosine (abs err ~ 5e-7 on the reduced range)
+  const float kInv2Pi = 0.15915494309189535f;
+  const float k2PiHi = 6.2831854820251465f;      // fp32(2*pi)
+  const float k2PiLo = -1.7484555314695172e-7f;  // 2*pi - fp32(2*pi)
+  const float k = rintf(x * kInv2Pi);
+  float r = fmaf(-k, k2PiHi, x);
+  r = fmaf(-k, k2PiLo, r);
+  return __cosf(r);
+}
+
+template <int EPI, int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, KmParams p) {
+  using Cfg = KmCfg<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + Cfg::BM - 1) / Cfg::BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int total_tiles = m_tiles * n_tiles;
+  const int ksteps = (p.K + Cfg::BK - 1) / Cfg::BK;
+  constexpr uint32_t kTmemCols = tmem_cols_for(2 * BN);
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        mbar_init(&tfull_bar[a], 1);
+        mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * Cfg::BM;
+        const int n0 = (t % n_tiles) * BN;
+        for (int ks = 0; ks < ksteps; ++ks, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
+          tma_load_2d(sA, &tmA, &full_bar[s], ks * Cfg::BK, m0);
+          tma_load_2d(sA + Cfg::A_BYTES, &tmB, &full_bar[s], ks * Cfg::BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_tf32(Cfg::BM, BN, 0, 0);
+      uint32_t it = 0, tl = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+        const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
+        mbar_wait(&tempty_bar[a], aph ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int ks = 0; ks < ksteps; ++ks, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t sB = sA + Cfg::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < Cfg::BK / 8; ++kk) {
+            // K-major, 128B swizzle: 8-row groups are 1024 B apart (SBO); K advances 32 B inside the swizzle row
+            const uint64_t ad = make_smem_desc_sw128(sA + kk * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc_sw128(sB + kk * 32, 16, 1024);
+            umma_tf32(d_tmem, ad, bd, idesc, (ks | kk) != 0);
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[a]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    uint32_t tl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
+      const int m0 = (t / n_tiles) * Cfg::BM;
+      const int n0 = (t % n_tiles) * BN;
+      mbar_wait(&tfull_bar[a], aph);
+      tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < p.M;
+      const size_t roff = static_cast<size_t>(m) * p.ld_out;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int nb = n0 + c0;
+          if (EPI == EPI_COS) {
+            // out_hi[m][n] = tf32(cos(acc + vec0[n]) - vec1[n]); optional out_lo = remainder
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              float o[4], l[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = nb + i + j;
+                float val = 0.f;
+                if (n < p.N) val = cos_reduced(__uint_as_float(v[i + j]) + __ldg(p.vec0 + n)) - __ldg(p.vec1 + n);
+                o[j] = round_tf32(val);
+                l[j] = val - o[j];
+              }
+              *reinterpret_cast<float4*>(p.out_hi + roff + nb + i) = make_float4(o[0], o[1], o[2], o[3]);
+              if (p.out_lo) *reinterpret_cast<float4*>(p.out_lo + roff + nb + i) = make_float4(l[0], l[1], l[2], l[3]);
+            }
+          } else if (EPI == EPI_UPDATE) {
+            // R = (R_hi + R_lo) - acc + vec0[n] for n < n_keep; other columns (ones column, padding) untouched
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (nb + i >= p.n_keep) break;
+              float4 rh = *reinterpret_cast<const float4*>(p.out_hi + roff + nb + i);
+              float4 rl = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.out_lo) rl = *reinterpret_cast<const float4*>(p.out_lo + roff + nb + i);
+              float hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = nb + i + j;
+                if (n < p.n_keep) {
+                  const float r = (hh[j] + ll[j]) - __uint_as_float(v[i + j]) + __ldg(p.vec0 + n);
+                  if (p.out_lo) {
+                    hh[j] = round_tf32(r);
+                    ll[j] = r - hh[j];
+                  } else {
+                    hh[j] = r;
+                  }
+                }
+              }
+              *reinterpret_cast<float4*>(p.out_hi + roff + nb + i) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+              if (p.out_lo) *reinterpret_cast<float4*>(p.out_lo + roff + nb + i) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+            }
+          } else {  // EPI_APPLY: Y = [Y +] acc + vec0[n]
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              if (nb + i >= p.n_keep) break;
+              float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.accumulate) y = *reinterpret_cast<const float4*>(p.out_hi + roff + nb + i);
+              float yy[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = nb + i + j;
+                if (n < p.n_keep) yy[j] = yy[j] + __uint_as_float(v[i + j]) + (p.vec0 ? __ldg(p.vec0 + n) : 0.f);
+              }
+              *reinterpret_cast<float4*>(p.out_hi + roff + nb + i) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[a]);
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// =====================================================================================
+// Host-side launchers
+// =====================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2D fp32 row-major matrix [rows x cols], leading dimension ld (floats); box = {32 floats, box_rows}, 128B swizzle.
+int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
+  cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
+}
+
+template <int BN, int SR, int STAGES>
+static cudaError_t launch_gram_t(const GramLaunch& g, cudaStream_t st) {
+  using Cfg = GramCfg<BN, SR, STAGES>;
+  auto kern = gram_tn_kernel<BN, SR, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int chunks = (g.rows + g.chunk_rows - 1) / g.chunk_rows;
+  const unsigned grid = static_cast<unsigned>(chunks) * static_cast<unsigned>(g.num_tiles);
+  if (grid == 0) return cudaSuccess;
+  kern<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(g.tmA, g.tmB0, g.tmB1, g.tiles, g.num_tiles, g.rows, g.chunk_rows,
+                                                g.out0, g.out1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gram(const GramLaunch& g, cudaStream_t st) {
+  if (g.chunk_rows % kGramStageRows != 0) return cudaErrorInvalidValue;
+  switch (g.bn) {
+    case 256: return launch_gram_t<256, kGramStageRows, 4>(g, st);
+    case 128: return launch_gram_t<128, kGramStageRows, 6>(g, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int EPI, int BN, int STAGES>
+static cudaError_t launch_km_t(const KmLaunch& k, cudaStream_t st) {
+  using Cfg = KmCfg<BN, STAGES>;
+  auto kern = gemm_kmajor_kernel<EPI, BN, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int m_tiles = (k.p.M + Cfg::BM - 1) / Cfg::BM;
+  const int n_tiles = (k.p.N + BN - 1) / BN;
+  const long long total = static_cast<long long>(m_tiles) * n_tiles;
+  if (total == 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>(total < k.num_sms ? total : k.num_sms);
+  kern<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(k.tmA, k.tmB, k.p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st) {
+  switch (k.epi) {
+    case EPI_COS: return launch_km_t<EPI_COS, 256, 4>(k, st);
+    case EPI_UPDATE: return launch_km_t<EPI_UPDATE, 256, 4>(k, st);
+    case EPI_APPLY: return launch_km_t<EPI_APPLY, 256, 4>(k, st);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+unsigned int read_wait_timeout_flag() {
+  unsigned int v = 0;
+  cudaMemcpyFromSymbol(&v, g_wait_timeout_flag, sizeof(v));
+  return v;
+}
+
+}  // namespace ks

@@ -1,0 +1,308 @@
+"""Node library of the hot path: same class names, constructor arguments and semantics as the
+reference nodes; the bodies marshal to the C ABI (which launches the sm_100a kernels).
+
+Reference classes (K/ = src/main/scala/keystoneml/):
+  CosineRandomFeatures                K/nodes/stats/CosineRandomFeatures.scala:19-60
+  StandardScaler / StandardScalerModel K/nodes/stats/StandardScaler.scala:16-59
+  VectorSplitter                      K/nodes/util/VectorSplitter.scala:10-36
+  VectorCombiner                      K/nodes/util/VectorCombiner.scala:11-14
+  ClassLabelIndicatorsFromIntLabels   K/nodes/util/ClassLabelIndicators.scala:15-29
+  MaxClassifier                       K/nodes/util/MaxClassifier.scala:9-11
+  BlockLeastSquaresEstimator          K/nodes/learning/BlockLinearMapper.scala:199-283
+  BlockWeightedLeastSquaresEstimator  K/nodes/learning/BlockWeightedLeastSquares.scala:36-84
+  BlockLinearMapper                   K/nodes/learning/BlockLinearMapper.scala:22-138
+  LinearMapper / LinearMapEstimator   K/nodes/learning/LinearMapper.scala:18-116
+
+Batches are ``DeviceMatrix`` / ``LazyFeatures`` (this rank's rows); 2-D numpy arrays are uploaded on
+the fly when a ``Context`` was given to the node.  No node computes on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+from ._capi import KeystoneError, check, lib
+from .context import Context, Dataset, DeviceMatrix, LazyFeatures, feature_source_args
+from .workflow import Estimator, LabelEstimator, Transformer, WeightedNode
+
+
+def _as_dataset(ctx: Optional[Context], data) -> Dataset:
+    if isinstance(data, Dataset):
+        return data
+    if ctx is None:
+        raise KeystoneError(-1, "numpy input needs a Context (pass ctx= to the node)")
+    return ctx.matrix(np.asarray(data))
+
+
+# ------------------------------------------------------------------------------------------
+class CosineRandomFeatures(Transformer):
+    """cos(x W^T + b); W is (numOutputFeatures x numInputFeatures), b has numOutputFeatures entries."""
+
+    def __init__(self, ctx: Context, W: np.ndarray, b: np.ndarray):
+        W = np.asarray(W, dtype=np.float64)
+        b = np.asarray(b, dtype=np.float64)
+        if b.shape[0] != W.shape[0]:  # CosineRandomFeatures.scala:24
+            raise ValueError("# of rows in W and size of b should match")
+        self.ctx, self.n_out, self.n_in = ctx, W.shape[0], W.shape[1]
+        wcol = np.asfortranarray(W)  # Breeze DenseMatrix storage
+        h = C.c_int64(0)
+        check(ctx.handle, lib().ks_cosine_rf_create(ctx.handle, wcol.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
+                                                     self.n_out, self.n_in, C.byref(h)))
+        self.handle = h.value
+
+    @classmethod
+    def create(cls, ctx: Context, num_input_features: int, num_output_features: int, gamma: float,
+               rng: Optional[np.random.Generator] = None, w_dist: str = "gaussian") -> "CosineRandomFeatures":
+        """Companion-object factory (CosineRandomFeatures.scala:51-60): W = gamma * rand(wDist), b = 2 pi U[0,1)."""
+        rng = rng or np.random.default_rng()
+        if w_dist == "gaussian":
+            W = rng.standard_normal((num_output_features, num_input_features))
+        elif w_dist == "cauchy":
+            W = rng.standard_cauchy((num_output_features, num_input_features))
+        else:
+            raise ValueError(w_dist)
+        return cls(ctx, W * gamma, rng.random(num_output_features) * (2 * math.pi))
+
+    def apply(self, data):
+        single = isinstance(data, np.ndarray) and data.ndim == 1
+        ds = _as_dataset(self.ctx, data)
+        if not isinstance(ds, DeviceMatrix):
+            raise KeystoneError(-1, "CosineRandomFeatures expects a dense input batch")
+        out = LazyFeatures(ds, [self.handle], [self.n_out], [self])
+        return out.to_numpy()[0] if single else out
+
+    def __del__(self):
+        try:
+            if self.handle and self.ctx.handle:
+                lib().ks_cosine_rf_destroy(self.ctx.handle, self.handle)
+        except Exception:
+            pass
+
+
+class VectorCombiner(Transformer):
+    """Concatenates the outputs of gathered branches (VectorCombiner.scala:11-14)."""
+
+    def apply(self, parts: Sequence):
+        if all(isinstance(p, LazyFeatures) for p in parts):
+            out = parts[0]
+            for p in parts[1:]:
+                out = out.concat(p)
+            return out
+        ctx = next(p.ctx for p in parts if isinstance(p, Dataset))
+        return ctx.matrix(np.concatenate([p.to_numpy(np.float32) if isinstance(p, Dataset) else np.asarray(p) for p in parts], axis=1))
+
+
+class VectorSplitter:
+    """Column blocks [j*blockSize, min(D, (j+1)*blockSize)) -- on the device a block is just a column offset, so
+    this node only reports the boundaries (VectorSplitter.scala:15-25)."""
+
+    def __init__(self, block_size: int, num_features_opt: Optional[int] = None):
+        self.block_size, self.num_features_opt = block_size, num_features_opt
+
+    def bounds(self, num_features: int):
+        d = self.num_features_opt if self.num_features_opt is not None else num_features
+        nb = int(math.ceil(d / float(self.block_size)))
+        return [(j * self.block_size, min(d, (j + 1) * self.block_size)) for j in range(nb)]
+
+
+class ClassLabelIndicatorsFromIntLabels(Transformer):
+    def __init__(self, ctx: Context, num_classes: int):
+        self.ctx, self.num_classes = ctx, num_classes
+
+    def apply(self, labels):
+        return self.ctx.labels_from_classes(np.asarray(labels), self.num_classes)
+
+
+class MaxClassifier(Transformer):
+    """argmax over scores.  Batches of predictions come back from the device as int32 class ids."""
+
+    def apply(self, scores):
+        if isinstance(scores, Dataset):
+            scores = scores.to_numpy(np.float32)
+        return np.argmax(np.asarray(scores), axis=-1).astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------------
+class BlockLinearMapper(Transformer):
+    """Fitted model: xs (per-block (rows_j x k) matrices), blockSize, optional intercept and feature means."""
+
+    def __init__(self, ctx: Context, handle: int):
+        self.ctx, self.handle = ctx, handle
+        nb, k, bs = C.c_int32(0), C.c_int64(0), C.c_int32(0)
+        check(ctx.handle, lib().ks_model_num_blocks(ctx.handle, handle, C.byref(nb), C.byref(k), C.byref(bs)))
+        self.num_blocks, self.k, self.block_size = nb.value, k.value, bs.value
+        self._xs = None
+
+    @classmethod
+    def from_arrays(cls, ctx: Context, xs: Sequence[np.ndarray], block_size: int, b_opt: Optional[np.ndarray] = None,
+                    feature_means: Optional[Sequence[np.ndarray]] = None) -> "BlockLinearMapper":
+        """new BlockLinearMapper(xs, blockSize, bOpt, featureScalersOpt) (BlockLinearMapper.scala:22-27)."""
+        xs_f = [np.asfortranarray(np.asarray(x, dtype=np.float64)) for x in xs]
+        k = xs_f[0].shape[1]
+        ptrs = (C.POINTER(C.c_double) * len(xs_f))(*[x.ctypes.data_as(C.POINTER(C.c_double)) for x in xs_f])
+        rows = (C.c_int64 * len(xs_f))(*[x.shape[0] for x in xs_f])
+        bb = None if b_opt is None else np.ascontiguousarray(b_opt, dtype=np.float64)
+        mptr, means_c = None, None
+        if feature_means is not None:
+            means_c = [np.ascontiguousarray(m, dtype=np.float64) for m in feature_means]
+            mptr = (C.POINTER(C.c_double) * len(means_c))(*[m.ctypes.data_as(C.POINTER(C.c_double)) for m in means_c])
+        h = C.c_int64(0)
+        check(ctx.handle, lib().ks_model_from_host(ctx.handle, ptrs, rows, len(xs_f), k,
+                                                    None if bb is None else bb.ctypes.data_as(C.c_void_p), mptr, block_size, C.byref(h)))
+        return cls(ctx, h.value)
+
+    # ---- model state (fp64, Breeze layouts) ----
+    def _block(self, j: int):
+        rows = C.c_int64(0)
+        check(self.ctx.handle, lib().ks_model_block_rows(self.ctx.handle, self.handle, j, C.byref(rows)))
+        W = np.empty((rows.value, self.k), dtype=np.float64, order="F")
+        mean = np.empty(rows.value, dtype=np.float64)
+        has = C.c_int32(0)
+        check(self.ctx.handle, lib().ks_model_get_block(self.ctx.handle, self.handle, j, W.ctypes.data_as(C.c_void_p),
+                                                         mean.ctypes.data_as(C.c_void_p), C.byref(has)))
+        return W, (mean if has.value else None)
+
+    @property
+    def xs(self) -> List[np.ndarray]:
+        if self._xs is None:
+            self._xs = [self._block(j) for j in range(self.num_blocks)]
+        return [w for w, _ in self._xs]
+
+    @property
+    def feature_means(self) -> Optional[List[np.ndarray]]:
+        _ = self.xs
+        return None if self._xs[0][1] is None else [m for _, m in self._xs]
+
+    @property
+    def b_opt(self) -> Optional[np.ndarray]:
+        b = np.empty(self.k, dtype=np.float64)
+        has = C.c_int32(0)
+        check(self.ctx.handle, lib().ks_model_get_intercept(self.ctx.handle, self.handle, b.ctypes.data_as(C.c_void_p), C.byref(has)))
+        return b if has.value else None
+
+    # ---- apply ----
+    def apply(self, data):
+        single = isinstance(data, np.ndarray) and data.ndim == 1
+        ds = _as_dataset(self.ctx, data)
+        f, x, rfs, n = feature_source_args(ds)
+        h = C.c_int64(0)
+        check(self.ctx.handle, lib().ks_model_apply(self.ctx.handle, self.handle, f, x, rfs, n, C.byref(h)))
+        out = DeviceMatrix(self.ctx, h.value, ds.rows, self.k)
+        return out.to_numpy()[0] if single else out
+
+    def apply_argmax(self, data) -> np.ndarray:
+        """apply followed by MaxClassifier, fused on the device."""
+        ds = _as_dataset(self.ctx, data)
+        f, x, rfs, n = feature_source_args(ds)
+        out = np.empty(ds.rows, dtype=np.int32)
+        check(self.ctx.handle, lib().ks_model_apply_argmax(self.ctx.handle, self.handle, f, x, rfs, n, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def applyAndEvaluate(self, data, evaluator) -> None:
+        """Calls ``evaluator(cumulative predictions incl. intercept)`` after every block (BlockLinearMapper.scala:95-137)."""
+        ds = _as_dataset(self.ctx, data)
+        f, x, rfs, n = feature_source_args(ds)
+        for j in range(self.num_blocks):
+            h = C.c_int64(0)
+            check(self.ctx.handle, lib().ks_model_apply_partial(self.ctx.handle, self.handle, f, x, rfs, n, j, C.byref(h)))
+            evaluator(DeviceMatrix(self.ctx, h.value, ds.rows, self.k))
+
+    def compute_cost(self, data, labels, lam: float) -> float:
+        """BlockLeastSquaresEstimator.computeCost (BlockLinearMapper.scala:142-187)."""
+        ds = _as_dataset(self.ctx, data)
+        lb = _as_dataset(self.ctx, labels)
+        f, x, rfs, n = feature_source_args(ds)
+        out = C.c_double(0)
+        check(self.ctx.handle, lib().ks_model_cost(self.ctx.handle, self.handle, f, x, rfs, n, lb.handle, lam, C.byref(out)))
+        return out.value
+
+    def __del__(self):
+        try:
+            if self.handle and self.ctx.handle:
+                lib().ks_model_destroy(self.ctx.handle, self.handle)
+        except Exception:
+            pass
+
+
+class LinearMapper(BlockLinearMapper):
+    """LinearMapper(x, bOpt, featureScaler): the single-block special case (LinearMapper.scala:18-63)."""
+
+    @classmethod
+    def from_arrays(cls, ctx: Context, x: np.ndarray, b_opt=None, feature_mean=None):  # type: ignore[override]
+        x = np.asarray(x, dtype=np.float64)
+        return super().from_arrays(ctx, [x], x.shape[0], b_opt, None if feature_mean is None else [feature_mean])
+
+    @property
+    def x(self) -> np.ndarray:
+        return self.xs[0]
+
+
+class BlockLeastSquaresEstimator(LabelEstimator, WeightedNode):
+    def __init__(self, block_size: int, num_iter: int, lam: float = 0.0, num_features_opt: Optional[int] = None,
+                 ctx: Optional[Context] = None):
+        self.block_size, self.num_iter, self.lam, self.num_features_opt, self.ctx = block_size, num_iter, lam, num_features_opt, ctx
+        self.weight = 3 * num_iter + 1  # BlockLinearMapper.scala:204
+
+    def fit(self, data, labels) -> BlockLinearMapper:
+        ds = _as_dataset(self.ctx, data)
+        ctx = ds.ctx
+        lb = _as_dataset(ctx, labels)
+        f, x, rfs, n = feature_source_args(ds)
+        h = C.c_int64(0)
+        check(ctx.handle, lib().ks_blockls_fit(ctx.handle, f, x, rfs, n, lb.handle, self.block_size, self.num_iter, self.lam,
+                                                self.num_features_opt or 0, _capi.KS_PRECISION_TF32, C.byref(h)))
+        return BlockLinearMapper(ctx, h.value)
+
+    def cost(self, n: int, d: int, k: int, sparsity: float, num_machines: int, cpu_weight: float, mem_weight: float,
+             network_weight: float) -> float:
+        """CostModel.cost (BlockLinearMapper.scala:268-282)."""
+        flops = float(n) * d * (self.block_size + k) / num_machines
+        bytes_scanned = float(n) * d / num_machines + float(d) * k
+        network = 2.0 * (float(d) * (self.block_size + k)) * math.log(num_machines) / math.log(2.0)
+        return self.num_iter * (max(cpu_weight * flops, mem_weight * bytes_scanned) + network_weight * network)
+
+
+class BlockWeightedLeastSquaresEstimator(LabelEstimator, WeightedNode):
+    def __init__(self, block_size: int, num_iter: int, lam: float, mixture_weight: float,
+                 num_features_opt: Optional[int] = None, ctx: Optional[Context] = None):
+        self.block_size, self.num_iter, self.lam, self.mixture_weight = block_size, num_iter, lam, mixture_weight
+        self.num_features_opt, self.ctx = num_features_opt, ctx
+        self.weight = 3 * num_iter + 1  # BlockWeightedLeastSquares.scala:44
+
+    def fit(self, data, labels) -> BlockLinearMapper:
+        ds = _as_dataset(self.ctx, data)
+        ctx = ds.ctx
+        lb = _as_dataset(ctx, labels)
+        f, x, rfs, n = feature_source_args(ds)
+        h = C.c_int64(0)
+        check(ctx.handle, lib().ks_blockwls_fit(ctx.handle, f, x, rfs, n, lb.handle, self.block_size, self.num_iter, self.lam,
+                                                 self.mixture_weight, self.num_features_opt or 0, _capi.KS_PRECISION_TF32, C.byref(h)))
+        return BlockLinearMapper(ctx, h.value)
+
+
+class LinearMapEstimator(LabelEstimator):
+    def __init__(self, lam: Optional[float] = None, ctx: Optional[Context] = None):
+        self.lam, self.ctx = lam, ctx
+
+    def fit(self, data, labels) -> LinearMapper:
+        ds = _as_dataset(self.ctx, data)
+        if not isinstance(ds, DeviceMatrix):
+            ds = ds.materialize()
+        ctx = ds.ctx
+        lb = _as_dataset(ctx, labels)
+        h = C.c_int64(0)
+        check(ctx.handle, lib().ks_linear_map_fit(ctx.handle, ds.handle, lb.handle, 0 if self.lam is None else 1,
+                                                   0.0 if self.lam is None else float(self.lam), C.byref(h)))
+        return LinearMapper(ctx, h.value)
+
+
+class StandardScalerModel(Transformer):
+    """(x - mean) [/ std] as a LinearMapper-free node is out of the hot path; the fits above centre internally
+    (BlockLinearMapper.scala:224-232).  Kept for API parity: holds the statistics a fitted model reports."""
+
+    def __init__(self, mean: np.ndarray, std: Optional[np.ndarray] = None):
+        self.mean, self.std = mean, std

@@ -1,0 +1,185 @@
+"""GPU parity tests (run with -m gpu on the B200 box): every call goes through the C ABI and is compared with the
+fp64 CPU oracle on the same seeded inputs.
+
+Tolerances (stated once, used everywhere below).  The MMA operands are tf32 (10-bit mantissa, round-to-nearest)
+with fp32 accumulation and the reduced system is solved in fp64:
+  * Gram / A^T B entries: |err| <= 2e-3 * sqrt(N) * rms(a) * rms(b)   (random-walk bound of the input rounding)
+  * cosine features: max abs err <= 2e-3 (the reference's own tolerance is 1e-2, CosineRandomFeaturesSuite.scala:33-35)
+  * fitted weights: rel-Frobenius(W) <= 5e-3 on well-conditioned problems; predictions max-abs <= 5e-3 * max|y|
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import keystone_b200 as ks
+from oracle import keystone_oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+W_TOL = 5e-3
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ks.Context(0)
+    yield c
+    c.close()
+
+
+def _debug_gram(ctx, A, B):
+    import ctypes as C
+    from keystone_b200._capi import lib, check
+    a, b = ctx.matrix(A.astype(np.float32)), ctx.matrix(B.astype(np.float32))
+    m, kc = A.shape[1], B.shape[1]
+    G = np.zeros((m, m)); Cm = np.zeros((m, kc))
+    check(ctx.handle, lib().ks_debug_gram(ctx.handle, a.handle, b.handle, G.ctypes.data_as(C.c_void_p), m,
+                                          Cm.ctypes.data_as(C.c_void_p), kc))
+    return G, Cm
+
+
+@pytest.mark.parametrize("n,m,kc", [(64, 32, 8), (1000, 300, 37), (5000, 640, 257), (40, 12, 3), (9000, 128, 1)])
+def test_gram_kernel(ctx, n, m, kc):
+    rng = np.random.default_rng(n + m)
+    A = rng.standard_normal((n, m)); B = rng.standard_normal((n, kc))
+    G, Cm = _debug_gram(ctx, A, B)
+    A32, B32 = A.astype(np.float32).astype(np.float64), B.astype(np.float32).astype(np.float64)
+    tol = 2e-3 * np.sqrt(n) + 1e-4
+    assert np.abs(G - A32.T @ A32).max() < tol, np.abs(G - A32.T @ A32).max()
+    assert np.abs(Cm - A32.T @ B32).max() < tol, np.abs(Cm - A32.T @ B32).max()
+
+
+def test_gram_exact_on_tf32_representable_inputs(ctx):
+    """Small integers are exact in tf32 and their sums exact in fp32: the kernel must be bit-exact here,
+    which pins the smem/instruction descriptors, the swizzle and the tile masks independently of rounding."""
+    rng = np.random.default_rng(7)
+    A = rng.integers(-3, 4, (777, 200)).astype(np.float64); B = rng.integers(-3, 4, (777, 70)).astype(np.float64)
+    G, Cm = _debug_gram(ctx, A, B)
+    assert np.array_equal(G, A.T @ A) and np.array_equal(Cm, A.T @ B)
+
+
+def test_cosine_random_features(ctx):
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((700, 50))
+    W, b = ko.cosine_random_features_params(50, 300, 0.3, rng)
+    rf = ks.CosineRandomFeatures(ctx, W, b)
+    out = rf(ctx.matrix(X)).to_numpy()
+    ref = ko.cosine_random_features(X, W, b)
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() < 2e-3, np.abs(out - ref).max()
+    one = rf(X[3])
+    assert np.abs(one - ref[3]).max() < 2e-3
+
+
+def _fit_compare(ctx, F, Y, bs, iters, lam, tol=W_TOL):
+    model = ks.BlockLeastSquaresEstimator(bs, iters, lam).fit(ctx.matrix(F), ctx.matrix(Y))
+    xs, b0, mus = ko.block_ls_fit(F, Y, bs, iters, lam)
+    Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
+    rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
+    assert [x.shape for x in model.xs] == [x.shape for x in xs]
+    assert rel < tol, rel
+    assert np.abs(model.b_opt - b0).max() < 1e-5
+    assert np.abs(np.concatenate(model.feature_means) - np.concatenate(mus)).max() < 1e-4
+    return model, xs, b0, mus, rel
+
+
+def test_blockls_fit_materialized(ctx):
+    rng = np.random.default_rng(2)
+    n, d, k = 3000, 700, 5
+    F = rng.standard_normal((n, d)) + 0.5 * rng.standard_normal(d)   # non-zero column means
+    Y = ko.class_label_indicators(rng.integers(0, k, n), k)
+    model, xs, b0, mus, rel = _fit_compare(ctx, F, Y, 256, 1, 1.0)
+    pred = model(ctx.matrix(F)).to_numpy()
+    ref = ko.block_linear_apply(F, xs, 256, b0, mus)
+    assert np.abs(pred - ref).max() < 5e-3, np.abs(pred - ref).max()
+    assert (model.apply_argmax(ctx.matrix(F)) == np.argmax(ref, 1)).mean() > 0.995
+
+
+def test_blockls_fit_multi_pass_and_ragged(ctx):
+    rng = np.random.default_rng(3)
+    n, d, k = 2000, 300, 3
+    F = rng.standard_normal((n, d)) * (1 + rng.random(d)) + 1.0
+    Y = rng.standard_normal((n, k))
+    _fit_compare(ctx, F, Y, 128, 3, 0.5)        # blocks 128,128,44 ; 3 sweeps
+    _fit_compare(ctx, F, Y, 300, 1, 0.0)        # nb = 1, lambda = 0 : LinearMapEstimator case
+
+
+def test_blockls_fit_reference_fixture(ctx, golden_dir):
+    """The reference's aMat/bMat fixture through the GPU BlockLS (b=4, 3 sweeps, lambda 0.1) vs the committed oracle output."""
+    A = np.loadtxt(os.path.join(golden_dir, "aMat.csv"), delimiter=",")
+    B = np.loadtxt(os.path.join(golden_dir, "bMat.csv"), delimiter=",")
+    g = json.load(open(os.path.join(golden_dir, "golden.json")))["block_ls_fixture"]
+    model = ks.BlockLeastSquaresEstimator(g["block_size"], g["num_iter"], g["lambda"]).fit(ctx.matrix(A), ctx.matrix(B))
+    W = np.concatenate(model.xs, 0)
+    assert np.linalg.norm(W - np.array(g["W"])) / np.linalg.norm(g["W"]) < W_TOL
+    assert np.abs(model.b_opt - np.array(g["intercept"])).max() < 1e-6
+
+
+def test_blockls_fit_cosine_features_regenerated(ctx):
+    """Config-3 shape in miniature: gather(CosineRandomFeatures x3) -> VectorCombiner -> BlockLS, features never stored."""
+    rng = np.random.default_rng(4)
+    n, d_in, n_out, k = 4000, 44, 256, 10
+    X = rng.standard_normal((n, d_in))
+    cls = rng.integers(0, k, n)
+    params = [ko.cosine_random_features_params(d_in, n_out, 0.17, rng) for _ in range(3)]
+    x = ctx.matrix(X.astype(np.float32))
+    rfs = [ks.CosineRandomFeatures(ctx, W, b) for W, b in params]
+    feats = ks.Pipeline.gather(rfs).andThen(ks.VectorCombiner())(x)
+    y = ctx.labels_from_classes(cls, k)
+    model = ks.BlockLeastSquaresEstimator(n_out, 1, 2.0).fit(feats, y)
+    Xd = X.astype(np.float32).astype(np.float64)
+    F = np.concatenate([ko.cosine_random_features(Xd, W, b) for W, b in params], 1)
+    Y = ko.class_label_indicators(cls, k)
+    xs, b0, mus = ko.block_ls_fit(F, Y, n_out, 1, 2.0)
+    Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
+    rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
+    assert rel < W_TOL, rel
+    pred = model(feats).to_numpy()
+    ref = ko.block_linear_apply(F, xs, n_out, b0, mus)
+    assert np.abs(pred - ref).max() < 5e-3
+    # computeCost (no centring; BlockLinearMapper.scala:142-187)
+    cost = model.compute_cost(feats, y, 2.0)
+    assert abs(cost - ko.compute_cost(F, Y, 2.0, xs, n_out, b0)) / cost < 2e-3
+    # block size different from the feature-map width (blocks straddle maps)
+    m2 = ks.BlockLeastSquaresEstimator(200, 1, 2.0).fit(feats, y)
+    xs2, _, _ = ko.block_ls_fit(F, Y, 200, 1, 2.0)
+    W2, R2 = np.concatenate(m2.xs, 0), np.concatenate(xs2, 0)
+    assert np.linalg.norm(W2 - R2) / np.linalg.norm(R2) < W_TOL
+
+
+def test_linear_map_estimator_known_answer(ctx):
+    """T/nodes/learning/LinearMapperSuite.scala:13-36 through the GPU path."""
+    rng = np.random.default_rng(42)
+    A = rng.standard_normal((128, 5))
+    x = np.array([5.0, 4.0, 3.0, 2.0, -1.0])[:, None]
+    mapper = ks.LinearMapEstimator().fit(ctx.matrix(A), ctx.matrix(A @ x))
+    assert np.abs(mapper.x - x).max() < 5e-3
+    assert abs(mapper(np.array([2.0, -3.0, 2.0, 3.0, 5.0]))[0] - 5.0) < 2e-2
+
+
+def test_block_linear_mapper_equals_linear_mapper(ctx):
+    """T/nodes/learning/BlockLinearMapperSuite.scala:18-55 on the device, incl. applyAndEvaluate's last callback."""
+    rng = np.random.default_rng(5)
+    in_dim, out_dim, bs, n = 1000, 100, 200, 50
+    mat = rng.standard_normal((in_dim, out_dim)); b = rng.standard_normal(out_dim)
+    X = rng.standard_normal((n, in_dim))
+    blm = ks.BlockLinearMapper.from_arrays(ctx, [mat[s:e] for s, e in ko.block_bounds(in_dim, bs)], bs, b)
+    lm = ks.LinearMapper.from_arrays(ctx, mat, b)
+    x = ctx.matrix(X)
+    o1, o2 = blm(x).to_numpy(), lm(x).to_numpy()
+    ref = X @ mat + b
+    scale = np.abs(ref).max()
+    assert np.abs(o1 - ref).max() < 2e-3 * scale and np.abs(o2 - ref).max() < 2e-3 * scale
+    seen = []
+    blm.applyAndEvaluate(x, lambda part: seen.append(part.to_numpy()))
+    assert len(seen) == 5 and np.abs(seen[-1] - o1).max() < 1e-5 * scale
+
+
+def test_error_paths(ctx):
+    with pytest.raises(ks.KeystoneError):
+        ks.BlockLeastSquaresEstimator(0, 1, 0.0).fit(ctx.matrix(np.ones((4, 4))), ctx.matrix(np.ones((4, 1))))
+    with pytest.raises(ks.KeystoneError):
+        ks.BlockLeastSquaresEstimator(4, 1, 0.0).fit(ctx.matrix(np.ones((4, 4))), ctx.matrix(np.ones((5, 1))))
+    with pytest.raises(ks.KeystoneError):   # singular system, lambda = 0 -> not SPD, reported (no crash / exit)
+        ks.BlockLeastSquaresEstimator(4, 1, 0.0).fit(ctx.matrix(np.ones((6, 4))), ctx.matrix(np.ones((6, 1))))
