@@ -247,8 +247,9 @@ void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, i
   c.launches += 1;
 }
 
-static void tmap_or_throw(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
-  const int r = make_tmap_2d(m, base, rows, cols, ld, box_rows);
+static void tmap_or_throw(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                          bool atom32 = false) {
+  const int r = make_tmap_2d(m, base, rows, cols, ld, box_rows, atom32);
   if (r != 0)
     throw KsError{KS_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string(r) + ") rows=" + std::to_string(rows) +
                                    " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld)};
@@ -317,9 +318,9 @@ void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int
   int nt = 0;
   g.tiles = gram_tiles(c, b, kcols, with_g, with_c, &nt);
   g.num_tiles = nt;
-  tmap_or_throw(&g.tmA, slab, rows, b, lds, kGramStageRows);
+  tmap_or_throw(&g.tmA, slab, rows, b, lds, kGramStageRows, true);
   g.tmB0 = g.tmA;
-  if (with_c) tmap_or_throw(&g.tmB1, R, rows, kcols, ldr, kGramStageRows);
+  if (with_c) tmap_or_throw(&g.tmB1, R, rows, kcols, ldr, kGramStageRows, true);
   else g.tmB1 = g.tmA;
   g.rows = static_cast<int>(rows);
   int64_t chunk = c.gram_chunk_rows;
@@ -505,14 +506,16 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       c.span_end();
 
       // ---------------- Gram: [G | C] = S^T [S | R | 1]  (pass > 0: C only, the factor is cached)
-      c.span_begin(PH_GRAM);
       const bool with_g = (it == 0);
+      c.span_begin(PH_OTHER);
       if (with_g) KS_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (g_elems + c_elems), c.st));
       else KS_CUDA(cudaMemsetAsync(Cm, 0, sizeof(float) * c_elems, c.st));
-      launch_gram_block(c, slab.as<float>(), lds, n_loc, b, r_hi.as<float>(), kpad, kcols, G, ldg, Cm, ldc, with_g, true);
       KS_CUDA(cudaMemsetAsync(rsum.p, 0, rsum.bytes, c.st));
       launch_colsum(r_hi.as<float>(), r_lo.as<float>(), kpad, n_loc, k, rsum.as<double>(), c.st);
       c.launches += 1;
+      c.span_end();
+      c.span_begin(PH_GRAM);  // exactly one gram_tn_kernel launch: bench.py's roofline reads this span
+      launch_gram_block(c, slab.as<float>(), lds, n_loc, b, r_hi.as<float>(), kpad, kcols, G, ldg, Cm, ldc, with_g, true);
       flops += (with_g ? 2.0 * n_loc * static_cast<double>(b) * b : 0.0) + 2.0 * n_loc * static_cast<double>(b) * k;
       c.span_end();
 

@@ -49,7 +49,7 @@ struct KmLaunch {
   int num_sms;
 };
 
-int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool atom32 = false);
 cudaError_t launch_gram(const GramLaunch& g, cudaStream_t st);
 cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st);
 unsigned int read_wait_timeout_flag();

@@ -137,14 +137,21 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   [0,14)  start address >> 4      [16,30) leading-dim byte offset >> 4
 //   [32,46) stride-dim byte offset >> 4   [46,48) version = 1 (sm_100)
 //   [49,52) base offset (0: tiles are 1024 B aligned)   [61,64) swizzle: 2 = 128 B
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//           1 = 128 B swizzle with 32 B atoms (the only layout accepted for MN-major tf32 operands)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= 1ull << 46;
-  d |= 2ull << 61;
+  d |= static_cast<uint64_t>(layout_type & 7) << 61;
   return d;
+}
+static constexpr uint32_t kLayoutSw128 = 2;       // K-major operands: Swizzle<3,4,3> (16 B chunks ^ row % 8)
+static constexpr uint32_t kLayoutSw128Base32 = 1; // MN-major tf32: Swizzle<2,5,2> (32 B chunks ^ row % 4), 4-row K groups
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_smem_desc(saddr, lbo_bytes, sbo_bytes, kLayoutSw128);
 }
 // Instruction descriptor, kind::tf32, fp32 accumulate.
 //   [4,6) D fmt: 1 = f32   [7,10) A fmt: 2 = tf32   [10,13) B fmt: 2 = tf32

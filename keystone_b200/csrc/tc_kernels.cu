@@ -107,9 +107,10 @@ gram_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sB = sA + Cfg::A_BYTES;
 #pragma unroll
         for (int kk = 0; kk < SR / 8; ++kk) {
-          // MN-major, 128B swizzle: 32-float MN chunks are BOX_BYTES apart (LBO), 8-row K groups 1024 B apart (SBO)
-          const uint64_t ad = make_smem_desc_sw128(sA + kk * 1024, Cfg::BOX_BYTES, 1024);
-          const uint64_t bd = make_smem_desc_sw128(sB + kk * 1024, Cfg::BOX_BYTES, 1024);
+          // MN-major tf32 => SWIZZLE_128B_BASE32B: 32-float MN chunks are BOX_BYTES apart (LBO), the two 4-row
+          // K groups of one K=8 MMA are 512 B apart (SBO); consecutive MMAs advance 8 rows = 1024 B.
+          const uint64_t ad = make_smem_desc(sA + kk * 1024, Cfg::BOX_BYTES, 512, kLayoutSw128Base32);
+          const uint64_t bd = make_smem_desc(sB + kk * 1024, Cfg::BOX_BYTES, 512, kLayoutSw128Base32);
           umma_tf32(tmem_base, ad, bd, idesc, (ks | kk) != 0);
         }
         umma_commit(&empty_bar[s]);
@@ -372,8 +373,9 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// 2D fp32 row-major matrix [rows x cols], leading dimension ld (floats); box = {32 floats, box_rows}, 128B swizzle.
-int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2D fp32 row-major matrix [rows x cols], leading dimension ld (floats); box = {32 floats, box_rows}, 128B swizzle
+// (atom32: the 32 B-atom flavour required by MN-major tf32 MMA operands).
+int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool atom32) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return -1;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
@@ -381,7 +383,8 @@ int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols
   cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
