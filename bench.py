@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--lam", type=float, default=1.0)
     ap.add_argument("--num-iter", type=int, default=1)
     ap.add_argument("--gamma", type=float, default=0.0555)
-    ap.add_argument("--cpu-rows", type=int, default=8192, help="rows of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rows", type=int, default=4096, help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

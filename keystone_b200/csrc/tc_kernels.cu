@@ -159,7 +159,7 @@ struct KmCfg {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 256 * 4;  // + barriers + per-warp vectors
 };
 
 __device__ __forceinline__ float cos_reduced(float x) {
@@ -173,10 +173,13 @@ __device__ __forceinline__ float cos_reduced(float x) {
   return __cosf(r);
 }
 
+static constexpr int kKmThreads = 320;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-9: epilogue (2 per TMEM lane quarter)
+
 template <int EPI, int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kKmThreads, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, KmParams p) {
   using Cfg = KmCfg<BN, STAGES>;
+  static_assert(BN == 256, "epilogue column split assumes BN == 256");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
@@ -184,6 +187,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* vec_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // 8 warps x 256 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -205,7 +209,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
-        mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+        mbar_init(&tempty_bar[a], 8);  // one arrive per epilogue warp
       }
       fence_barrier_init();
     }
@@ -264,22 +268,37 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
+    // 8 epilogue warps: TMEM lane quarter q = warp % 4 (hardware rule), column half = (warp - 2) / 4
+    const int ew = warp - 2;
     const int q = warp & 3;
+    const int half = ew >> 2;
+    float* v0s = vec_smem + ew * 256;  // this warp's 128 vec0 values
+    float* v1s = v0s + 128;            // and 128 vec1 values
     uint32_t tl = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
       const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
       const int m0 = (t / n_tiles) * Cfg::BM;
-      const int n0 = (t % n_tiles) * BN;
+      const int n0 = (t % n_tiles) * BN + half * 128;
+      // stage the per-column vectors of this warp's 128 columns in shared memory (broadcast reads below)
+      {
+        const int n = n0 + lane * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v0s[lane * 4 + j] = (p.vec0 && n + j < p.N) ? __ldg(p.vec0 + n + j) : 0.f;
+          v1s[lane * 4 + j] = (p.vec1 && n + j < p.N) ? __ldg(p.vec1 + n + j) : 0.f;
+        }
+      }
+      __syncwarp();
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < p.M;
       const size_t roff = static_cast<size_t>(m) * p.ld_out;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < 128; c0 += 32) {
         if (n0 + c0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + c0, v);
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + half * 128 + c0, v);
         tmem_ld_wait();
         if (row_ok) {
           const int nb = n0 + c0;
@@ -291,9 +310,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int n = nb + i + j;
-                float val = 0.f;
-                if (n < p.N) val = cos_reduced(__uint_as_float(v[i + j]) + __ldg(p.vec0 + n)) - __ldg(p.vec1 + n);
-                o[j] = round_tf32(val);
+                float val = cos_reduced(__uint_as_float(v[i + j]) + v0s[c0 + i + j]) - v1s[c0 + i + j];
+                if (n >= p.N) val = 0.f;
+                o[j] = p.accumulate ? val : round_tf32(val);
                 l[j] = val - o[j];
               }
               *reinterpret_cast<float4*>(p.out_hi + roff + nb + i) = make_float4(o[0], o[1], o[2], o[3]);
@@ -312,7 +331,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
               for (int j = 0; j < 4; ++j) {
                 const int n = nb + i + j;
                 if (n < p.n_keep) {
-                  const float r = (hh[j] + ll[j]) - __uint_as_float(v[i + j]) + __ldg(p.vec0 + n);
+                  const float r = (hh[j] + ll[j]) - __uint_as_float(v[i + j]) + v0s[c0 + i + j];
                   if (p.out_lo) {
                     hh[j] = round_tf32(r);
                     ll[j] = r - hh[j];
@@ -334,7 +353,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int n = nb + i + j;
-                if (n < p.n_keep) yy[j] = yy[j] + __uint_as_float(v[i + j]) + (p.vec0 ? __ldg(p.vec0 + n) : 0.f);
+                if (n < p.n_keep) yy[j] = yy[j] + __uint_as_float(v[i + j]) + v0s[c0 + i + j];
               }
               *reinterpret_cast<float4*>(p.out_hi + roff + nb + i) = make_float4(yy[0], yy[1], yy[2], yy[3]);
             }
@@ -431,7 +450,7 @@ static cudaError_t launch_km_t(const KmLaunch& k, cudaStream_t st) {
   const long long total = static_cast<long long>(m_tiles) * n_tiles;
   if (total == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>(total < k.num_sms ? total : k.num_sms);
-  kern<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(k.tmA, k.tmB, k.p);
+  kern<<<grid, kKmThreads, Cfg::SMEM_BYTES, st>>>(k.tmA, k.tmB, k.p);
   return cudaGetLastError();
 }
 
