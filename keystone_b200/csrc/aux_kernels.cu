@@ -162,28 +162,64 @@ void launch_colsum(const float* hi, const float* lo, int64_t ld, int64_t rows, i
 
 // ------------------------------------------------------------------ residual init / slab from materialised features
 __global__ void init_residual_kernel(const float* __restrict__ Y, int64_t ldy, const double* __restrict__ ymean,
-                                     float* __restrict__ r_hi, float* __restrict__ r_lo, int64_t ldr, int64_t rows, int k) {
+                                     float* __restrict__ R, int64_t ldr, int64_t rows, int k) {
   const int64_t total = rows * ldr;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = i / ldr;
     const int c = static_cast<int>(i - r * ldr);
-    float h = 0.f, l = 0.f;
-    if (c < k) {
-      const float v = static_cast<float>(static_cast<double>(Y[r * ldy + c]) - ymean[c]);
-      h = round_tf32_aux(v);
-      l = v - h;
-    } else if (c == k) {
-      h = 1.f;  // ones column: A^T [R | 1] yields the column sums of the slab in the same pass
-    }
-    r_hi[i] = h;
-    r_lo[i] = l;
+    R[i] = c < k ? static_cast<float>(static_cast<double>(Y[r * ldy + c]) - ymean[c]) : 0.f;
   }
 }
-void launch_init_residual(const float* Y, int64_t ldy, const double* ymean, float* r_hi, float* r_lo, int64_t ldr,
-                          int64_t rows, int k, cudaStream_t st) {
+void launch_init_residual(const float* Y, int64_t ldy, const double* ymean, float* R, int64_t ldr, int64_t rows, int k,
+                          cudaStream_t st) {
   if (rows == 0) return;
-  init_residual_kernel<<<grid_for(rows * ldr, 256), 256, 0, st>>>(Y, ldy, ymean, r_hi, r_lo, ldr, rows, k);
+  init_residual_kernel<<<grid_for(rows * ldr, 256), 256, 0, st>>>(Y, ldy, ymean, R, ldr, rows, k);
+}
+
+// block (32, 8), 4 columns per thread: same access pattern as colsum_kernel, plus the rounded copy.
+__global__ void round_colsum_kernel(const float* __restrict__ R, float* __restrict__ Rr, int64_t ld, int64_t rows, int k,
+                                    double* __restrict__ sums, int64_t rows_per_block) {
+  __shared__ double red[8][128];
+  const int c4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int64_t r_begin = blockIdx.y * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  double a[4] = {0, 0, 0, 0};
+  if (c4 < ld) {
+    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(R + r * ld + c4);
+      const float in[4] = {v.x, v.y, v.z, v.w};
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c4 + j;
+        if (c < k) {
+          a[j] += in[j];
+          o[j] = round_tf32_aux(in[j]);
+        } else {
+          o[j] = (c == k) ? 1.f : 0.f;  // ones column: S^T [R | 1] yields the column sums of the slab in the same pass
+        }
+      }
+      *reinterpret_cast<float4*>(Rr + r * ld + c4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[threadIdx.y][threadIdx.x * 4 + j] = a[j];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 128) {
+    double s = 0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += red[y][t];
+    const int c = blockIdx.x * 128 + t;
+    if (c < k) atomicAdd(sums + c, s);
+  }
+}
+void launch_round_colsum(const float* R, float* Rr, int64_t ld, int64_t rows, int k, double* sums, cudaStream_t st) {
+  if (rows == 0) return;
+  const int64_t rpb = 1024;
+  dim3 grid(static_cast<unsigned>((ld + 127) / 128), static_cast<unsigned>((rows + rpb - 1) / rpb));
+  round_colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(R, Rr, ld, rows, k, sums, rpb);
 }
 
 __global__ void center_round_kernel(const float* __restrict__ F, int64_t ldf, int c0, const float* __restrict__ shift,

@@ -6,6 +6,7 @@
 #include "engine.h"
 
 #include <dlfcn.h>
+#include <stdlib.h>
 #include <math.h>
 #include <string.h>
 
@@ -75,6 +76,57 @@ NcclApi& nccl_api() {
     if (r__ != ncclSuccess)                                                                                \
       throw KsError{KS_ERR_NCCL, std::string(#call) + " failed: " + nccl_api().GetErrorString(r__)};      \
   } while (0)
+
+// ------------------------------------------------------------------------------------ caching device-memory pool
+// Blocks are keyed by (device, size rounded up to 2 MiB); freed blocks are kept for reuse and released when the last
+// context is destroyed.  Buffers freed here may still be in use by work queued on the context's stream: every path that
+// frees workspace synchronises the stream first (check_async at the end of each entry point), as with cudaFree.
+static std::mutex g_pool_mu;
+static std::multimap<std::pair<int, size_t>, void*> g_pool_free;
+static size_t pool_round(size_t n) { return (n + (size_t(2) << 20) - 1) & ~((size_t(2) << 20) - 1); }
+void* pool_alloc(size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const size_t key = pool_round(bytes);
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_pool_free.find({dev, key});
+    if (it != g_pool_free.end()) {
+      void* p = it->second;
+      g_pool_free.erase(it);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, key);
+  if (e != cudaSuccess) {  // give cached blocks back to the driver and retry once
+    cudaGetLastError();
+    pool_release_all();
+    e = cudaMalloc(&p, key);
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw KsError{KS_ERR_CUDA, "cudaMalloc(" + std::to_string(key) + " bytes) failed: " + cudaGetErrorString(e)};
+  }
+  return p;
+}
+void pool_free(void* p, size_t bytes) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_pool_free.insert({{dev, pool_round(bytes)}, p});
+}
+void pool_release_all() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (auto& kv : g_pool_free) {
+    cudaSetDevice(kv.first.first);
+    cudaFree(kv.second);
+  }
+  g_pool_free.clear();
+  cudaSetDevice(cur);
+}
 
 // ------------------------------------------------------------------------------------ Ctx
 static constexpr int kMaxInfo = 4096;
@@ -268,35 +320,33 @@ void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* s
   KmLaunch k;
   tmap_or_throw(&k.tmA, src.xop.as<float>() + row_begin * src.X->ld, rows, src.d_in, src.X->ld, 128);
   tmap_or_throw(&k.tmB, src.Wall + c0 * src.ldw, cols, src.d_in, src.ldw, 256);
-  k.p.out_hi = slab;
-  k.p.out_lo = nullptr;
+  tmap_or_throw(&k.tmOut, slab, rows, cols, lds, 32);
   k.p.vec0 = src.ball + c0;
   k.p.vec1 = shift;
-  k.p.ld_out = static_cast<int>(lds);
   k.p.M = static_cast<int>(rows);
   k.p.N = static_cast<int>(cols);
   k.p.K = static_cast<int>(src.d_in);
-  k.p.n_keep = static_cast<int>(cols);
-  k.p.accumulate = round_out ? 0 : 1;  // EPI_COS: non-zero => keep full fp32 output
+  k.p.flags = round_out ? 0 : KM_FLAG_NO_ROUND;
   k.epi = EPI_COS;
   k.num_sms = c.num_sms;
   KS_CUDA(launch_kmajor(k, c.st));
   c.launches += 1;
 }
 
-const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, int* num_tiles) {
-  std::vector<int> key = {b, kcols, with_g ? 1 : 0, with_c ? 1 : 0};
+const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, bool pair, int* num_tiles) {
+  std::vector<int> key = {b, kcols, with_g ? 1 : 0, with_c ? 1 : 0, pair ? 1 : 0};
   auto it = c.tile_cache.find(key);
   std::vector<GramTile> t;
-  const int mb = (b + 127) / 128;
+  const int tm = pair ? 256 : 128, tn = pair ? 512 : 256;
+  const int mb = (b + tm - 1) / tm;
   if (with_g) {
-    const int nbk = (b + 255) / 256;
+    const int nbk = (b + tn - 1) / tn;
     for (int i = 0; i < mb; ++i)
       for (int j = 0; j < nbk; ++j)
-        if ((j + 1) * 256 - 1 >= i * 128) t.push_back(GramTile{i, j, 0, 0});  // tile touches the upper triangle
+        if ((j + 1) * tn - 1 >= i * tm) t.push_back(GramTile{i, j, 0, 0});  // tile touches the upper triangle
   }
   if (with_c) {
-    const int nck = (kcols + 255) / 256;
+    const int nck = (kcols + tn - 1) / tn;
     for (int i = 0; i < mb; ++i)
       for (int j = 0; j < nck; ++j) t.push_back(GramTile{i, j, 1, 0});
   }
@@ -316,7 +366,8 @@ void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int
   if (rows <= 0 || b <= 0 || (!with_g && !with_c)) return;
   GramLaunch g;
   int nt = 0;
-  g.tiles = gram_tiles(c, b, kcols, with_g, with_c, &nt);
+  g.pair = c.gram_pair;
+  g.tiles = gram_tiles(c, b, kcols, with_g, with_c, g.pair != 0, &nt);
   g.num_tiles = nt;
   tmap_or_throw(&g.tmA, slab, rows, b, lds, kGramStageRows, true);
   g.tmB0 = g.tmA;
@@ -326,29 +377,28 @@ void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int
   int64_t chunk = c.gram_chunk_rows;
   chunk = std::max<int64_t>(kGramStageRows, chunk / kGramStageRows * kGramStageRows);
   g.chunk_rows = static_cast<int>(chunk);
-  g.bn = 256;
-  g.out0 = GramOut{G, ldg, b, b};
-  g.out1 = GramOut{C, ldc, b, kcols};
+  tmap_or_throw(&g.tmOut0, G, b, b, ldg, 32);
+  if (with_c) tmap_or_throw(&g.tmOut1, C, b, kcols, ldc, 32);
+  else g.tmOut1 = g.tmOut0;
+  g.n_valid0 = b;
+  g.n_valid1 = kcols;
   KS_CUDA(launch_gram(g, c.st));
   c.launches += 1;
 }
 
 void launch_update(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* bop, int64_t ldb, int k,
-                   float* r_hi, float* r_lo, int64_t ldr, const float* cbias, int epi, int accumulate) {
+                   float* out, int64_t ldo, const float* cbias, int epi, bool reduce) {
   if (rows <= 0 || k <= 0 || b <= 0) return;
   KmLaunch u;
   tmap_or_throw(&u.tmA, slab, rows, b, lds, 128);
   tmap_or_throw(&u.tmB, bop, k, b, ldb, 256);
-  u.p.out_hi = r_hi;
-  u.p.out_lo = r_lo;
+  tmap_or_throw(&u.tmOut, out, rows, k, ldo, 32);  // k valid columns: the store never touches columns >= k
   u.p.vec0 = cbias;
   u.p.vec1 = nullptr;
-  u.p.ld_out = static_cast<int>(ldr);
   u.p.M = static_cast<int>(rows);
   u.p.N = k;
   u.p.K = b;
-  u.p.n_keep = k;
-  u.p.accumulate = accumulate;
+  u.p.flags = reduce ? KM_FLAG_REDUCE : 0;
   u.epi = epi;
   u.num_sms = c.num_sms;
   KS_CUDA(launch_kmajor(u, c.st));
@@ -428,11 +478,11 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
                                                              model->intercept.as<double>(), k);
   c.launches += 1;
 
-  // ---- residual R = Y - mean (hi/lo planes) with the ones column
-  DevBuf r_hi, r_lo, slab, gc, H, rhs, rsum, bop, cbias;
-  r_hi.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * kpad));
-  r_lo.alloc(r_hi.bytes);
-  launch_init_residual(Y.d, Y.ld, model->intercept.as<double>(), r_hi.as<float>(), r_lo.as<float>(), kpad, n_loc, k, c.st);
+  // ---- residual R = Y - mean (fp32 master) and Rr = its tf32-rounded copy with the ones column (Gram operand)
+  DevBuf r_f32, r_tf32, slab, gc, H, rhs, rsum, bop, cbias;
+  r_f32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * kpad));
+  r_tf32.alloc(r_f32.bytes);
+  launch_init_residual(Y.d, Y.ld, model->intercept.as<double>(), r_f32.as<float>(), kpad, n_loc, k, c.st);
   c.launches += 1;
   c.span_end();
 
@@ -511,11 +561,11 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       if (with_g) KS_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (g_elems + c_elems), c.st));
       else KS_CUDA(cudaMemsetAsync(Cm, 0, sizeof(float) * c_elems, c.st));
       KS_CUDA(cudaMemsetAsync(rsum.p, 0, rsum.bytes, c.st));
-      launch_colsum(r_hi.as<float>(), r_lo.as<float>(), kpad, n_loc, k, rsum.as<double>(), c.st);
+      launch_round_colsum(r_f32.as<float>(), r_tf32.as<float>(), kpad, n_loc, k, rsum.as<double>(), c.st);
       c.launches += 1;
       c.span_end();
       c.span_begin(PH_GRAM);  // exactly one gram_tn_kernel launch: bench.py's roofline reads this span
-      launch_gram_block(c, slab.as<float>(), lds, n_loc, b, r_hi.as<float>(), kpad, kcols, G, ldg, Cm, ldc, with_g, true);
+      launch_gram_block(c, slab.as<float>(), lds, n_loc, b, r_tf32.as<float>(), kpad, kcols, G, ldg, Cm, ldc, with_g, true);
       flops += (with_g ? 2.0 * n_loc * static_cast<double>(b) * b : 0.0) + 2.0 * n_loc * static_cast<double>(b) * k;
       c.span_end();
 
@@ -569,8 +619,8 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
 
       // ---------------- residual update R -= (S - 1 delta^T) dW
       c.span_begin(PH_UPDATE);
-      launch_update(c, slab.as<float>(), lds, n_loc, b, bop.as<float>(), lds, k, r_hi.as<float>(), r_lo.as<float>(), kpad,
-                    cbias.as<float>(), EPI_UPDATE, 0);
+      launch_update(c, slab.as<float>(), lds, n_loc, b, bop.as<float>(), lds, k, r_f32.as<float>(), kpad, cbias.as<float>(),
+                    EPI_UPDATE, /*reduce=*/true);
       flops += 2.0 * n_loc * static_cast<double>(b) * k;
       c.span_end();
     }
@@ -638,8 +688,8 @@ static std::unique_ptr<Matrix> apply_model(Ctx& c, Model& md, FeatSrc& src, int 
     launch_pack_apply(md.W[j]->as<double>(), nullptr, (j == 0 && md.has_intercept) ? md.intercept.as<double>() : nullptr,
                       bop.as<float>(), static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), c.st);
     c.launches += 1;
-    launch_update(c, slab.as<float>(), lds, n_loc, b, bop.as<float>(), lds, k, out->d, nullptr, out->ld, cbias.as<float>(),
-                  EPI_APPLY, j > 0 ? 1 : 0);
+    launch_update(c, slab.as<float>(), lds, n_loc, b, bop.as<float>(), lds, k, out->d, out->ld, cbias.as<float>(), EPI_APPLY,
+                  /*reduce=*/j > 0);
     c0 += md.block_size;
   }
   c.check_async("BlockLinearMapper.apply");
@@ -722,6 +772,11 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
     c->world = world_size;
     c->num_sms = prop.multiProcessorCount;
     KS_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    if (const char* e = getenv("KS_GRAM_CHUNK_ROWS")) {
+      const long v = atol(e);
+      if (v >= kGramStageRows) c->gram_chunk_rows = v;
+    }
+    if (const char* e = getenv("KS_GRAM_PAIR")) c->gram_pair = atoi(e) != 0;
     if (world_size > 1) {
       if (!nccl_id) throw KsError{KS_ERR_INVALID, "nccl_id required for world_size > 1"};
       ncclUniqueId id;
@@ -757,7 +812,16 @@ KS_API int32_t ks_ctx_destroy(int64_t ctx) {
   for (auto e : c->event_pool) cudaEventDestroy(e);
   if (c->solver) solver_api().Destroy(c->solver);
   if (c->comm) nccl_api().CommDestroy(c->comm);
+  c->solver_work.release();
+  c->dev_info.release();
   cudaStreamDestroy(c->st);
+  c.reset();
+  bool last;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    last = g_ctxs.empty();
+  }
+  if (last) pool_release_all();
   return KS_OK;
 }
 
@@ -775,6 +839,7 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     const std::string n = name ? name : "";
     if (n == "gram_chunk_rows" && value >= kGramStageRows) c.gram_chunk_rows = value;
     else if (n == "sample_rows" && value >= 1) c.sample_rows = value;
+    else if (n == "gram_pair") c.gram_pair = value != 0;
     else if (n == "timing") c.timing = value != 0;
     else throw KsError{KS_ERR_INVALID, "unknown option or bad value: " + n};
   });

@@ -30,6 +30,12 @@ struct KsError {
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// Device memory comes from a per-process caching pool (engine.cu): a fit needs ~35 GB of workspace (slab, residuals,
+// operand copies) and cudaMalloc/cudaFree of that much costs ~0.25 s per call -- more than the featurize phase.
+void* pool_alloc(size_t bytes);
+void pool_free(void* p, size_t bytes);
+void pool_release_all();
+
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
@@ -38,14 +44,14 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) pool_free(p, bytes);
     p = nullptr;
     bytes = 0;
   }
   void alloc(size_t n) {
     release();
     if (n == 0) n = 16;
-    KS_CUDA(cudaMalloc(&p, n));
+    p = pool_alloc(n);
     bytes = n;
   }
   template <class T>
@@ -110,6 +116,7 @@ struct Ctx {
   std::string stats_json;
   int64_t launches = 0;
   int64_t gram_chunk_rows = 4096;
+  int gram_pair = 1;  // CTA-pair (cta_group::2) Gram kernel
   int64_t sample_rows = 16384;
   int64_t next_id = 1;
   std::unordered_map<int64_t, std::unique_ptr<Matrix>> matrices;
@@ -156,11 +163,12 @@ void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, i
 // slab[rows x lds] = round_tf32(features[row_begin : row_begin+rows, c0 : c0+cols] - shift)   (shift may be the zero vector)
 void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, float* slab, int64_t lds,
                   int64_t row_begin, int64_t rows, bool round_out = true);
-const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, int* num_tiles);
+const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, bool pair, int* num_tiles);
 void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* R, int64_t ldr, int kcols,
                        float* G, int ldg, float* C, int ldc, bool with_g, bool with_c);
+// out[rows x k] (+)= (epi == EPI_UPDATE ? -1 : +1) * slab[rows x b] * bop[k x b]^T + cbias   (reduce: add into out)
 void launch_update(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* bop, int64_t ldb, int k,
-                   float* r_hi, float* r_lo, int64_t ldr, const float* cbias, int epi, int accumulate);
+                   float* out, int64_t ldo, const float* cbias, int epi, bool reduce);
 
 int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, double w, int64_t nf_opt);
 

@@ -17,33 +17,26 @@ struct GramTile {
   int which;  // 0: B = tmB0 -> out0,  1: B = tmB1 -> out1
   int pad;
 };
-struct GramOut {
-  float* ptr;
-  int ld;
-  int m_valid;
-  int n_valid;
-};
 struct GramLaunch {
-  CUtensorMap tmA, tmB0, tmB1;
-  const GramTile* tiles;  // device
+  CUtensorMap tmA, tmB0, tmB1;   // operands: box {32, kGramStageRows}, SWIZZLE_128B_ATOM_32B
+  CUtensorMap tmOut0, tmOut1;    // outputs:  box {32, 32}, SWIZZLE_128B; dims clip the reduce-add at the matrix edge
+  const GramTile* tiles;         // device
   int num_tiles;
   int rows;        // contraction length (rows of A and B)
   int chunk_rows;  // split of the contraction across CTAs (multiple of kGramStageRows)
-  int bn;          // 256
-  GramOut out0, out1;
+  int n_valid0, n_valid1;  // valid output columns per target (whole 32-column chunks beyond are skipped)
+  int pair;                // 1: CTA-pair kernel (tiles are 256 x 512), 0: single-CTA kernel (tiles are 128 x 256)
 };
+enum { KM_FLAG_NO_ROUND = 1, KM_FLAG_REDUCE = 2 };
 struct KmParams {
-  float* out_hi;
-  float* out_lo;  // may be null
-  const float* vec0;
-  const float* vec1;
-  int ld_out;
+  const float* vec0;  // EPI_COS: bias;  EPI_UPDATE / EPI_APPLY: per-column constant
+  const float* vec1;  // EPI_COS: shift
   int M, N, K;
-  int n_keep;      // columns >= n_keep are left untouched (EPI_UPDATE / EPI_APPLY)
-  int accumulate;  // EPI_APPLY: add to the existing output
+  int flags;  // KM_FLAG_NO_ROUND: EPI_COS keeps fp32;  KM_FLAG_REDUCE: add into the output instead of overwriting it
 };
 struct KmLaunch {
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB;  // operands: box {32, 128} / {32, 256}, SWIZZLE_128B
+  CUtensorMap tmOut;     // output: box {32, 32}, SWIZZLE_128B
   KmParams p;
   int epi;
   int num_sms;
@@ -62,9 +55,12 @@ void launch_f32_to_f64_rows(const float* src, int64_t src_ld, double* dst, int64
 void launch_labels_from_classes(const int32_t* cls, float* dst, int64_t ld, int64_t rows, int k, cudaStream_t st);
 // column sums of [rows x cols] (optionally hi + lo planes) accumulated into fp64 sums[cols] (must be zeroed)
 void launch_colsum(const float* hi, const float* lo, int64_t ld, int64_t rows, int cols, double* sums, cudaStream_t st);
-// labels/residual initialisation: R_hi/R_lo[:, :k] = split(Y - ymean), column k = 1, columns > k = 0
-void launch_init_residual(const float* Y, int64_t ldy, const double* ymean, float* r_hi, float* r_lo, int64_t ldr,
-                          int64_t rows, int k, cudaStream_t st);
+// residual initialisation: R[:, :k] = Y - ymean (fp32 master copy), other columns 0
+void launch_init_residual(const float* Y, int64_t ldy, const double* ymean, float* R, int64_t ldr, int64_t rows, int k,
+                          cudaStream_t st);
+// Rr[:, :k] = tf32_rn(R[:, :k]) (the Gram's MN-major operand), Rr[:, k] = 1 (ones column), Rr[:, > k] = 0, and
+// sums[c] += column sums of R (fp64; must be zeroed) -- one pass over R per block
+void launch_round_colsum(const float* R, float* Rr, int64_t ld, int64_t rows, int k, double* sums, cudaStream_t st);
 // slab[:, :cols] = tf32(F[:, c0:c0+cols] - shift)  (+ lo remainder plane)
 void launch_center_round(const float* F, int64_t ldf, int c0, const float* shift, float* s_hi, float* s_lo, int64_t lds,
                          int64_t rows, int cols, cudaStream_t st);

@@ -6,22 +6,26 @@
 //                     (K/nodes/learning/BlockWeightedLeastSquares.scala:212-214 and the mlmatrix
 //                     NormalEquations called from K/nodes/learning/BlockLinearMapper.scala:236-239).
 //   gemm_kmajor_kernel D[M x N] = A B^T, A [M x K] and B [N x K] row-major (K-major operands),
-//                     persistent, TMEM double-buffered, with three fused epilogues:
-//                       EPI_COS     cos(acc + bias) - shift, rounded to tf32   (CosineRandomFeatures.scala:30-32)
-//                       EPI_UPDATE  R <- R - acc + cbias                        (BlockWeightedLeastSquares.scala:287-290)
-//                       EPI_APPLY   Y <- [Y +] acc + cbias                      (BlockLinearMapper.scala:55-70)
+//                     persistent, TMEM double-buffered, with fused epilogues:
+//                       EPI_COS     out  = tf32(cos(acc + bias) - shift)     (CosineRandomFeatures.scala:30-32)
+//                       EPI_UPDATE  R   += -acc + cbias                      (BlockWeightedLeastSquares.scala:287-290)
+//                       EPI_APPLY   Y [+]= acc + cbias                       (BlockLinearMapper.scala:55-70)
+//
+// Every epilogue goes TMEM -> registers -> 128 B-swizzled shared staging -> TMA store / TMA reduce-add, so global
+// memory only ever sees full 128 B rows (the first version stored 16 B per row per lane: 32 wavefronts per warp
+// instruction, which made the cosine epilogue 3x longer than its MMAs -- profiles/README.md).
 #include "tc_common.cuh"
 #include "kernels.h"
 
 namespace ks {
 
-static constexpr int kThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
-
 __host__ __device__ constexpr uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
 
 // =====================================================================================
-// Gram / A^T B kernel (MN-major operands, split over row chunks, fp32 red.add epilogue)
+// Gram / A^T B kernel (MN-major operands, split over row chunks, TMA reduce-add epilogue)
 // =====================================================================================
+static constexpr int kGramThreads = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
 template <int BN, int SR, int STAGES>
 struct GramCfg {
   static constexpr int BM = 128;
@@ -29,18 +33,21 @@ struct GramCfg {
   static constexpr int B_BYTES = BN * SR * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BOX_BYTES = SR * 128;  // one TMA box: 32 floats (128 B) x SR rows
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int STAGING_BYTES = 4 * 4096;  // one 32 x 32 fp32 chunk per epilogue warp
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 template <int BN, int SR, int STAGES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kGramThreads, 1)
 gram_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
-               const __grid_constant__ CUtensorMap tmB1, const GramTile* __restrict__ tiles, int num_tiles, int rows,
-               int chunk_rows, GramOut out0, GramOut out1) {
+               const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmOut0,
+               const __grid_constant__ CUtensorMap tmOut1, const GramTile* __restrict__ tiles, int num_tiles, int rows,
+               int chunk_rows, int n_valid0, int n_valid1) {
   using Cfg = GramCfg<BN, SR, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
@@ -55,11 +62,13 @@ gram_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m0 = tile.m_blk * Cfg::BM;
   const int n0 = tile.n_blk * BN;
   const CUtensorMap* tmB = tile.which ? &tmB1 : &tmB0;
+  const CUtensorMap* tmOut = tile.which ? &tmOut1 : &tmOut0;
   constexpr uint32_t kTmemCols = tmem_cols_for(BN);
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(tmB);
+    tma_prefetch_desc(tmOut);
   }
   if (warp == 1) {
     if (elect_one()) {
@@ -118,28 +127,33 @@ gram_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(tmem_full_bar);
     }
   } else {
-    // epilogue: warp w owns TMEM lanes [32*(w&3), +32) == output rows m0 + 32*(w&3) + lane
+    // epilogue: warp w owns TMEM lanes [32*(w&3), +32) == output rows m0 + 32*(w&3) + lane.  The partial tile is
+    // added to the fp32 output with one TMA reduce-add per 32 x 32 chunk (clipped at the matrix edge by the map).
     const int q = warp & 3;
-    const GramOut out = tile.which ? out1 : out0;
+    const int n_valid = tile.which ? n_valid1 : n_valid0;
+    uint8_t* buf = staging + (warp - 2) * 4096;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int m = m0 + q * 32 + lane;
-    float* orow = out.ptr + static_cast<size_t>(m) * out.ld;
-    const bool row_ok = m < out.m_valid;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= out.n_valid) break;  // warp-uniform
+      if (n0 + c0 >= n_valid) break;  // warp-uniform
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
       tmem_ld_wait();
-      if (row_ok) {
+      float o[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int n = n0 + c0 + i;
-          if (n < out.n_valid) red_add_f32(orow + n, __uint_as_float(v[i]));
-        }
+      for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
+      if (lane == 0) bulk_wait_read0();  // previous chunk's reduce has finished reading the staging buffer
+      __syncwarp();
+      stage_row_sw128(buf, lane, o);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(tmOut, buf, n0 + c0, m0 + q * 32);
+        bulk_commit();
       }
     }
+    if (lane == 0) bulk_wait0();
     tc_fence_before();
   }
   __syncthreads();
@@ -150,8 +164,158 @@ gram_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // =====================================================================================
+// Gram / A^T B kernel on CTA pairs (cta_group::2): one pair computes a 256 x 512 tile as two M=256, N=256 MMAs per
+// K step.  Each CTA stages only its own 128 columns of A and its 128-column half of each B tile, so the shared-memory
+// traffic per MMA drops from 12 KB (1-CTA 128 x 256) to 8 KB and the L2 -> SM traffic halves; the 1-CTA kernel
+// saturates shared-memory bandwidth at ~2/3 of the tensor peak (profiles/README.md).
+// =====================================================================================
+template <int SR, int STAGES>
+struct Gram2Cfg {
+  static constexpr int PM = 256, PN = 512;          // pair tile
+  static constexpr int A_BYTES = 128 * SR * 4;      // this CTA's 128 columns of A
+  static constexpr int BH_BYTES = 128 * SR * 4;     // this CTA's half (128 columns) of one N=256 B tile
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * BH_BYTES;
+  static constexpr int BOX_BYTES = SR * 128;
+  static constexpr int STAGING_BYTES = 4 * 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
+};
+
+template <int SR, int STAGES>
+__global__ void __launch_bounds__(kGramThreads, 1)
+gram2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmOut0,
+                const __grid_constant__ CUtensorMap tmOut1, const GramTile* __restrict__ tiles, int num_tiles, int rows,
+                int chunk_rows, int n_valid0, int n_valid1) {
+  using Cfg = Gram2Cfg<SR, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();  // 0 = leader (issues the MMAs), 1 = peer
+  const int work = blockIdx.x >> 1;
+  const GramTile tile = tiles[work % num_tiles];
+  const int chunk = work / num_tiles;
+  const int row0 = chunk * chunk_rows;
+  const int nrows = min(chunk_rows, rows - row0);
+  const int ksteps = (nrows + SR - 1) / SR;
+  const int m0 = tile.m_blk * Cfg::PM + static_cast<int>(rank) * 128;  // this CTA's 128 output rows / A columns
+  const int n0 = tile.n_blk * Cfg::PN;
+  const CUtensorMap* tmB = tile.which ? &tmB1 : &tmB0;
+  const CUtensorMap* tmOut = tile.which ? &tmOut1 : &tmOut0;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(tmB);
+    tma_prefetch_desc(tmOut);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);   // leader: its producer's arrive.expect_tx; bytes come from both CTAs
+        mbar_init(&empty_bar[s], 1);  // one multicast commit per use
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / complete_tx can land
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (ks / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+        uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
+        uint8_t* sB = sA + Cfg::A_BYTES;
+        const int r = row0 + ks * SR;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tma_load_2d_pair(sA + i * Cfg::BOX_BYTES, &tmA, &full_bar[s], m0 + 32 * i, r);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            tma_load_2d_pair(sB + h * Cfg::BH_BYTES + i * Cfg::BOX_BYTES, tmB, &full_bar[s],
+                             n0 + h * 256 + static_cast<int>(rank) * 128 + 32 * i, r);
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_tf32(256, 256, 1, 1);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (ks / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t sB = sA + Cfg::A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < SR / 8; ++kk) {
+          const uint64_t ad = make_smem_desc(sA + kk * 1024, Cfg::BOX_BYTES, 512, kLayoutSw128Base32);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t bd = make_smem_desc(sB + h * Cfg::BH_BYTES + kk * 1024, Cfg::BOX_BYTES, 512, kLayoutSw128Base32);
+            umma_tf32_pair(tmem_base + h * 256, ad, bd, idesc, (ks | kk) != 0);
+          }
+        }
+        umma_commit_pair(&empty_bar[s]);
+      }
+      umma_commit_pair(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int n_valid = tile.which ? n_valid1 : n_valid0;
+    uint8_t* buf = staging + (warp - 2) * 4096;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < Cfg::PN; c0 += 32) {
+      if (n0 + c0 >= n_valid) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      float o[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      stage_row_sw128(buf, lane, o);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_2d(tmOut, buf, n0 + c0, m0 + q * 32);
+        bulk_commit();
+      }
+    }
+    if (lane == 0) bulk_wait0();
+    tc_fence_before();
+  }
+  tc_fence_before();
+  cluster_sync_all();  // the peer's shared memory and barriers stay valid until the leader's MMAs / commits are done
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// =====================================================================================
 // K-major GEMM with fused epilogues (persistent, double-buffered TMEM accumulator)
 // =====================================================================================
+static constexpr int kKmThreads = 320;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-9: epilogue (2 per TMEM lane quarter)
+
 template <int BN, int STAGES>
 struct KmCfg {
   static constexpr int BM = 128;
@@ -159,35 +323,39 @@ struct KmCfg {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 256 * 4;  // + barriers + per-warp vectors
+  static constexpr int STAGING_BYTES = 8 * 4096;  // one 32 x 32 fp32 chunk per epilogue warp
+  static constexpr int VEC_BYTES = 8 * 256 * 4;   // per-warp bias / shift vectors
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + VEC_BYTES + 1024 + 256;
 };
 
 __device__ __forceinline__ float cos_reduced(float x) {
-  // Cody-Waite reduction to [-pi, pi] then the SFU cosine (abs err ~ 5e-7 on the reduced range)
+  // Cody-Waite reduction to [-pi, pi] (round-to-nearest multiple of 2 pi via the 1.5 * 2^23 trick: FMA pipe only),
+  // then the SFU cosine (abs err ~ 5e-7 on the reduced range)
   const float kInv2Pi = 0.15915494309189535f;
   const float k2PiHi = 6.2831854820251465f;      // fp32(2*pi)
   const float k2PiLo = -1.7484555314695172e-7f;  // 2*pi - fp32(2*pi)
-  const float k = rintf(x * kInv2Pi);
+  const float kMagic = 12582912.0f;              // 1.5 * 2^23
+  const float k = __fadd_rn(__fmaf_rn(x, kInv2Pi, kMagic), -kMagic);
   float r = fmaf(-k, k2PiHi, x);
   r = fmaf(-k, k2PiLo, r);
   return __cosf(r);
 }
 
-static constexpr int kKmThreads = 320;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-9: epilogue (2 per TMEM lane quarter)
-
 template <int EPI, int BN, int STAGES>
 __global__ void __launch_bounds__(kKmThreads, 1)
-gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, KmParams p) {
+gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmOut, KmParams p) {
   using Cfg = KmCfg<BN, STAGES>;
   static_assert(BN == 256, "epilogue column split assumes BN == 256");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  float* vec_smem = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES + Cfg::VEC_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* vec_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256);  // 8 warps x 256 floats
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -200,6 +368,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
   }
   if (warp == 1) {
     if (elect_one()) {
@@ -274,13 +443,13 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int half = ew >> 2;
     float* v0s = vec_smem + ew * 256;  // this warp's 128 vec0 values
     float* v1s = v0s + 128;            // and 128 vec1 values
+    uint8_t* buf = staging + ew * 4096;
     uint32_t tl = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
       const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
       const int m0 = (t / n_tiles) * Cfg::BM;
       const int n0 = (t % n_tiles) * BN + half * 128;
-      // stage the per-column vectors of this warp's 128 columns in shared memory (broadcast reads below)
-      {
+      {  // stage the per-column vectors of this warp's 128 columns in shared memory (broadcast reads below)
         const int n = n0 + lane * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -291,79 +460,42 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       __syncwarp();
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
-      const int m = m0 + q * 32 + lane;
-      const bool row_ok = m < p.M;
-      const size_t roff = static_cast<size_t>(m) * p.ld_out;
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         if (n0 + c0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + half * 128 + c0, v);
         tmem_ld_wait();
-        if (row_ok) {
-          const int nb = n0 + c0;
-          if (EPI == EPI_COS) {
-            // out_hi[m][n] = tf32(cos(acc + vec0[n]) - vec1[n]); optional out_lo = remainder
+        float o[32];
+        if (EPI == EPI_COS) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              float o[4], l[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int n = nb + i + j;
-                float val = cos_reduced(__uint_as_float(v[i + j]) + v0s[c0 + i + j]) - v1s[c0 + i + j];
-                if (n >= p.N) val = 0.f;
-                o[j] = p.accumulate ? val : round_tf32(val);
-                l[j] = val - o[j];
-              }
-              *reinterpret_cast<float4*>(p.out_hi + roff + nb + i) = make_float4(o[0], o[1], o[2], o[3]);
-              if (p.out_lo) *reinterpret_cast<float4*>(p.out_lo + roff + nb + i) = make_float4(l[0], l[1], l[2], l[3]);
-            }
-          } else if (EPI == EPI_UPDATE) {
-            // R = (R_hi + R_lo) - acc + vec0[n] for n < n_keep; other columns (ones column, padding) untouched
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (nb + i >= p.n_keep) break;
-              float4 rh = *reinterpret_cast<const float4*>(p.out_hi + roff + nb + i);
-              float4 rl = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.out_lo) rl = *reinterpret_cast<const float4*>(p.out_lo + roff + nb + i);
-              float hh[4] = {rh.x, rh.y, rh.z, rh.w}, ll[4] = {rl.x, rl.y, rl.z, rl.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int n = nb + i + j;
-                if (n < p.n_keep) {
-                  const float r = (hh[j] + ll[j]) - __uint_as_float(v[i + j]) + v0s[c0 + i + j];
-                  if (p.out_lo) {
-                    hh[j] = round_tf32(r);
-                    ll[j] = r - hh[j];
-                  } else {
-                    hh[j] = r;
-                  }
-                }
-              }
-              *reinterpret_cast<float4*>(p.out_hi + roff + nb + i) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-              if (p.out_lo) *reinterpret_cast<float4*>(p.out_lo + roff + nb + i) = make_float4(ll[0], ll[1], ll[2], ll[3]);
-            }
-          } else {  // EPI_APPLY: Y = [Y +] acc + vec0[n]
-#pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              if (nb + i >= p.n_keep) break;
-              float4 y = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.accumulate) y = *reinterpret_cast<const float4*>(p.out_hi + roff + nb + i);
-              float yy[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int n = nb + i + j;
-                if (n < p.n_keep) yy[j] = yy[j] + __uint_as_float(v[i + j]) + v0s[c0 + i + j];
-              }
-              *reinterpret_cast<float4*>(p.out_hi + roff + nb + i) = make_float4(yy[0], yy[1], yy[2], yy[3]);
-            }
+          for (int i = 0; i < 32; ++i) {
+            const float val = cos_reduced(__uint_as_float(v[i]) + v0s[c0 + i]) - v1s[c0 + i];
+            o[i] = (p.flags & KM_FLAG_NO_ROUND) ? val : round_tf32(val);
           }
+        } else if (EPI == EPI_UPDATE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] - __uint_as_float(v[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] + __uint_as_float(v[i]);
+        }
+        if (lane == 0) bulk_wait_read0();  // the previous chunk's store has finished reading the staging buffer
+        __syncwarp();
+        stage_row_sw128(buf, lane, o);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.flags & KM_FLAG_REDUCE) tma_reduce_add_2d(&tmOut, buf, n0 + c0, m0 + q * 32);
+          else tma_store_2d(&tmOut, buf, n0 + c0, m0 + q * 32);
+          bulk_commit();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[a]);
     }
+    if (lane == 0) bulk_wait0();
   }
   __syncthreads();
   if (warp == 1) {
@@ -403,8 +535,7 @@ int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols
   cuuint32_t estr[2] = {1u, 1u};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
 
@@ -421,18 +552,44 @@ static cudaError_t launch_gram_t(const GramLaunch& g, cudaStream_t st) {
   const int chunks = (g.rows + g.chunk_rows - 1) / g.chunk_rows;
   const unsigned grid = static_cast<unsigned>(chunks) * static_cast<unsigned>(g.num_tiles);
   if (grid == 0) return cudaSuccess;
-  kern<<<grid, kThreads, Cfg::SMEM_BYTES, st>>>(g.tmA, g.tmB0, g.tmB1, g.tiles, g.num_tiles, g.rows, g.chunk_rows,
-                                                g.out0, g.out1);
+  kern<<<grid, kGramThreads, Cfg::SMEM_BYTES, st>>>(g.tmA, g.tmB0, g.tmB1, g.tmOut0, g.tmOut1, g.tiles, g.num_tiles, g.rows,
+                                                   g.chunk_rows, g.n_valid0, g.n_valid1);
   return cudaGetLastError();
+}
+
+template <int SR, int STAGES>
+static cudaError_t launch_gram2_t(const GramLaunch& g, cudaStream_t st) {
+  using Cfg = Gram2Cfg<SR, STAGES>;
+  auto kern = gram2_tn_kernel<SR, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int chunks = (g.rows + g.chunk_rows - 1) / g.chunk_rows;
+  const unsigned grid = 2u * static_cast<unsigned>(chunks) * static_cast<unsigned>(g.num_tiles);
+  if (grid == 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGramThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, g.tmA, g.tmB0, g.tmB1, g.tmOut0, g.tmOut1, g.tiles, g.num_tiles, g.rows, g.chunk_rows,
+                            g.n_valid0, g.n_valid1);
 }
 
 cudaError_t launch_gram(const GramLaunch& g, cudaStream_t st) {
   if (g.chunk_rows % kGramStageRows != 0) return cudaErrorInvalidValue;
-  switch (g.bn) {
-    case 256: return launch_gram_t<256, kGramStageRows, 4>(g, st);
-    case 128: return launch_gram_t<128, kGramStageRows, 6>(g, st);
-    default: return cudaErrorInvalidValue;
-  }
+  if (g.pair) return launch_gram2_t<kGramStageRows, 4>(g, st);
+  return launch_gram_t<256, kGramStageRows, 4>(g, st);
 }
 
 template <int EPI, int BN, int STAGES>
@@ -450,15 +607,15 @@ static cudaError_t launch_km_t(const KmLaunch& k, cudaStream_t st) {
   const long long total = static_cast<long long>(m_tiles) * n_tiles;
   if (total == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>(total < k.num_sms ? total : k.num_sms);
-  kern<<<grid, kKmThreads, Cfg::SMEM_BYTES, st>>>(k.tmA, k.tmB, k.p);
+  kern<<<grid, kKmThreads, Cfg::SMEM_BYTES, st>>>(k.tmA, k.tmB, k.tmOut, k.p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st) {
   switch (k.epi) {
-    case EPI_COS: return launch_km_t<EPI_COS, 256, 4>(k, st);
-    case EPI_UPDATE: return launch_km_t<EPI_UPDATE, 256, 4>(k, st);
-    case EPI_APPLY: return launch_km_t<EPI_APPLY, 256, 4>(k, st);
+    case EPI_COS: return launch_km_t<EPI_COS, 256, 3>(k, st);
+    case EPI_UPDATE: return launch_km_t<EPI_UPDATE, 256, 3>(k, st);
+    case EPI_APPLY: return launch_km_t<EPI_APPLY, 256, 3>(k, st);
     default: return cudaErrorInvalidValue;
   }
 }
