@@ -197,7 +197,7 @@ __global__ void round_colsum_kernel(const float* __restrict__ R, float* __restri
           a[j] += in[j];
           o[j] = round_tf32_aux(in[j]);
         } else {
-          o[j] = (c == k) ? 1.f : 0.f;  // ones column: S^T [R | 1] yields the column sums of the slab in the same pass
+          o[j] = 0.f;
         }
       }
       *reinterpret_cast<float4*>(Rr + r * ld + c4) = make_float4(o[0], o[1], o[2], o[3]);
@@ -222,50 +222,94 @@ void launch_round_colsum(const float* R, float* Rr, int64_t ld, int64_t rows, in
   round_colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(R, Rr, ld, rows, k, sums, rpb);
 }
 
+// block (32, 8), 4 columns per thread, rows strided by 8 (coalesced 512 B per warp-row); optional column sums
 __global__ void center_round_kernel(const float* __restrict__ F, int64_t ldf, int c0, const float* __restrict__ shift,
-                                    float* __restrict__ s_hi, float* __restrict__ s_lo, int64_t lds, int64_t rows, int cols) {
-  const int64_t total = rows * lds;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t r = i / lds;
-    const int c = static_cast<int>(i - r * lds);
-    float h = 0.f, l = 0.f;
-    if (c < cols) {
-      const float v = F[r * ldf + c0 + c] - shift[c];
-      h = round_tf32_aux(v);
-      l = v - h;
+                                    float* __restrict__ slab, float* __restrict__ colsum, int64_t lds, int64_t rows, int cols,
+                                    int64_t rows_per_block) {
+  __shared__ float red[8][128];
+  const int c4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int64_t r_begin = blockIdx.y * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  float a[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c4 < lds) {
+    float sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sh[j] = (c4 + j < cols) ? shift[c4 + j] : 0.f;
+    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[j] = (c4 + j < cols) ? round_tf32_aux(F[r * ldf + c0 + c4 + j] - sh[j]) : 0.f;  // c0 may be unaligned: scalar loads
+        a[j] += o[j];
+      }
+      *reinterpret_cast<float4*>(slab + r * lds + c4) = make_float4(o[0], o[1], o[2], o[3]);
     }
-    s_hi[i] = h;
-    if (s_lo) s_lo[i] = l;
+  }
+  if (colsum == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[threadIdx.y][threadIdx.x * 4 + j] = a[j];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 128) {
+    float s = 0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += red[y][t];
+    const int c = blockIdx.x * 128 + t;
+    if (c < cols) atomicAdd(colsum + c, s);
   }
 }
-void launch_center_round(const float* F, int64_t ldf, int c0, const float* shift, float* s_hi, float* s_lo, int64_t lds,
+void launch_center_round(const float* F, int64_t ldf, int c0, const float* shift, float* slab, float* colsum, int64_t lds,
                          int64_t rows, int cols, cudaStream_t st) {
   if (rows == 0) return;
-  center_round_kernel<<<grid_for(rows * lds, 256), 256, 0, st>>>(F, ldf, c0, shift, s_hi, s_lo, lds, rows, cols);
+  const int64_t rpb = 256;
+  dim3 grid(static_cast<unsigned>((lds + 127) / 128), static_cast<unsigned>((rows + rpb - 1) / rpb));
+  center_round_kernel<<<grid, dim3(32, 8), 0, st>>>(F, ldf, c0, shift, slab, colsum, lds, rows, cols, rpb);
+}
+
+__global__ void divide_by_count_kernel(const double* __restrict__ sums, const double* __restrict__ count, float* out,
+                                       double* out64, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double v = sums[i] / fmax(*count, 1.0);
+    if (out) out[i] = static_cast<float>(v);
+    if (out64) out64[i] = v;
+  }
+}
+void launch_divide_by_count(const double* sums, const double* count, float* out, double* out64, int n, cudaStream_t st) {
+  if (n == 0) return;
+  divide_by_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(sums, count, out, out64, n);
+}
+
+__global__ void delta_mean_kernel(const float* __restrict__ ssum, const float* __restrict__ shift, double n_total,
+                                  double* __restrict__ delta, double* __restrict__ mean, int b) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < b) {
+    const double d = static_cast<double>(ssum[i]) / n_total;
+    delta[i] = d;
+    if (mean) mean[i] = static_cast<double>(shift[i]) + d;
+  }
+}
+void launch_delta_mean(const float* ssum, const float* shift, double n_total, double* delta, double* mean, int b, cudaStream_t st) {
+  if (b == 0) return;
+  delta_mean_kernel<<<(b + 255) / 256, 256, 0, st>>>(ssum, shift, n_total, delta, mean, b);
 }
 
 // ------------------------------------------------------------------ reduced system assembly (fp64)
-__global__ void build_system_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ C, int ldc,
-                                    int k_ones, double n_total, double lam, double* __restrict__ H,
-                                    double* __restrict__ delta, int b) {
+__global__ void build_system_kernel(const float* __restrict__ G, int ldg, const double* __restrict__ delta, double n_total,
+                                    double lam, double* __restrict__ H, int b) {
   const int64_t total = static_cast<int64_t>(b) * b;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i / b), r = static_cast<int>(i - static_cast<int64_t>(c) * b);
     const int lo = min(r, c), hi = max(r, c);
     const double g = static_cast<double>(G[static_cast<int64_t>(lo) * ldg + hi]);  // upper triangle is the computed one
-    const double dr = static_cast<double>(C[static_cast<int64_t>(r) * ldc + k_ones]) / n_total;
-    const double dc = static_cast<double>(C[static_cast<int64_t>(c) * ldc + k_ones]) / n_total;
-    H[i] = g - n_total * dr * dc + (r == c ? lam : 0.0);
-    if (c == 0) delta[r] = dr;
+    H[i] = g - n_total * delta[r] * delta[c] + (r == c ? lam : 0.0);
   }
 }
-void launch_build_system(const float* G, int ldg, const float* C, int ldc, int k_ones, double n_total, double lam,
-                         double* H, double* delta, int b, cudaStream_t st) {
+void launch_build_system(const float* G, int ldg, const double* delta, double n_total, double lam, double* H, int b,
+                         cudaStream_t st) {
   if (b == 0) return;
-  build_system_kernel<<<grid_for(static_cast<int64_t>(b) * b, 256), 256, 0, st>>>(G, ldg, C, ldc, k_ones, n_total, lam, H,
-                                                                              delta, b);
+  build_system_kernel<<<grid_for(static_cast<int64_t>(b) * b, 256), 256, 0, st>>>(G, ldg, delta, n_total, lam, H, b);
 }
 
 __global__ void build_rhs_kernel(const float* __restrict__ C, int ldc, const double* __restrict__ delta,

@@ -63,6 +63,7 @@ NcclApi& nccl_api() {
       load_sym(api.lib, "ncclCommDestroy", api.CommDestroy, "libnccl");
       load_sym(api.lib, "ncclAllReduce", api.AllReduce, "libnccl");
       load_sym(api.lib, "ncclGetErrorString", api.GetErrorString, "libnccl");
+      api.CommSplit = reinterpret_cast<decltype(api.CommSplit)>(dlsym(api.lib, "ncclCommSplit"));
     } catch (const KsError& e) {
       fail = e.msg;
     }
@@ -166,15 +167,15 @@ cudaEvent_t Ctx::get_event() {
   KS_CUDA(cudaEventCreate(&e));
   return e;
 }
-void Ctx::span_begin(int phase) {
+void Ctx::span_begin(int phase, cudaStream_t s) {
   if (!timing) return;
-  Span s{phase, get_event(), get_event()};
-  KS_CUDA(cudaEventRecord(s.a, st));
-  spans.push_back(s);
+  Span sp{phase, get_event(), get_event()};
+  KS_CUDA(cudaEventRecord(sp.a, s ? s : st));
+  spans.push_back(sp);
 }
-void Ctx::span_end() {
+void Ctx::span_end(cudaStream_t s) {
   if (!timing) return;
-  KS_CUDA(cudaEventRecord(spans.back().b, st));
+  KS_CUDA(cudaEventRecord(spans.back().b, s ? s : st));
 }
 void Ctx::collect_spans(double out_ms[PH_COUNT]) {
   for (int i = 0; i < PH_COUNT; ++i) out_ms[i] = 0;
@@ -188,13 +189,13 @@ void Ctx::collect_spans(double out_ms[PH_COUNT]) {
   }
   spans.clear();
 }
-void Ctx::allreduce_f32(float* p, size_t n) {
+void Ctx::allreduce_f32(float* p, size_t n, bool prep) {
   if (world <= 1 || n == 0) return;
-  KS_NCCL(nccl_api().AllReduce(p, p, n, ncclFloat32, ncclSum, comm, st));
+  KS_NCCL(nccl_api().AllReduce(p, p, n, ncclFloat32, ncclSum, prep ? comm2 : comm, prep ? st2 : st));
 }
-void Ctx::allreduce_f64(double* p, size_t n) {
+void Ctx::allreduce_f64(double* p, size_t n, bool prep) {
   if (world <= 1 || n == 0) return;
-  KS_NCCL(nccl_api().AllReduce(p, p, n, ncclFloat64, ncclSum, comm, st));
+  KS_NCCL(nccl_api().AllReduce(p, p, n, ncclFloat64, ncclSum, prep ? comm2 : comm, prep ? st2 : st));
 }
 void Ctx::ensure_solver() {
   if (solver) return;
@@ -204,14 +205,16 @@ void Ctx::ensure_solver() {
   dev_info.alloc(sizeof(int) * kMaxInfo);
   KS_CUDA(cudaMemsetAsync(dev_info.p, 0, sizeof(int) * kMaxInfo, st));
 }
-void Ctx::potrf(double* H, int n, int info_slot) {
+void Ctx::potrf(double* H, int n, int info_slot, cudaStream_t s) {
   ensure_solver();
   SolverApi& api = solver_api();
+  if (api.SetStream(solver, s) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
   int lwork = 0;
   if (api.DpotrfBufferSize(solver, CUBLAS_FILL_MODE_LOWER, n, H, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
     throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrf_bufferSize failed"};
   if (lwork > solver_lwork) {
     KS_CUDA(cudaStreamSynchronize(st));
+    KS_CUDA(cudaStreamSynchronize(st2));
     solver_work.alloc(sizeof(double) * static_cast<size_t>(lwork));
     solver_lwork = lwork;
   }
@@ -220,9 +223,10 @@ void Ctx::potrf(double* H, int n, int info_slot) {
     throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrf failed"};
   launches += 1;
 }
-void Ctx::potrs(const double* H, int n, double* B, int nrhs, int info_slot) {
+void Ctx::potrs(const double* H, int n, double* B, int nrhs, int info_slot, cudaStream_t s) {
   ensure_solver();
   if (nrhs == 0 || n == 0) return;
+  if (solver_api().SetStream(solver, s) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
   if (solver_api().Dpotrs(solver, CUBLAS_FILL_MODE_LOWER, n, nrhs, H, n, B, n, dev_info.as<int>() + (info_slot % kMaxInfo)) !=
       CUSOLVER_STATUS_SUCCESS)
     throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrs failed"};
@@ -242,6 +246,7 @@ void Ctx::check_infos(int used_slots) {
 }
 void Ctx::check_async(const char* what) {
   cudaError_t e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && st2) e = cudaStreamSynchronize(st2);
   if (e != cudaSuccess) {
     std::string extra;
     if (e == cudaErrorLaunchFailure || e == cudaErrorIllegalInstruction) extra = " (kernel trapped: barrier wait budget exceeded or illegal instruction)";
@@ -308,12 +313,13 @@ static void tmap_or_throw(CUtensorMap* m, const float* base, int64_t rows, int64
 }
 
 void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, float* slab, int64_t lds,
-                  int64_t row_begin, int64_t rows, bool round_out) {
+                  int64_t row_begin, int64_t rows, bool round_out, float* colsum, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return;
+  if (!st) st = c.st;
   if (src.F) {
     if (!round_out) throw KsError{KS_ERR_INVALID, "unrounded slab only for generated features"};
-    launch_center_round(src.F->d + row_begin * src.F->ld, src.F->ld, static_cast<int>(c0), shift, slab, nullptr, lds, rows,
-                        static_cast<int>(cols), c.st);
+    launch_center_round(src.F->d + row_begin * src.F->ld, src.F->ld, static_cast<int>(c0), shift, slab, colsum, lds, rows,
+                        static_cast<int>(cols), st);
     c.launches += 1;
     return;
   }
@@ -323,13 +329,14 @@ void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* s
   tmap_or_throw(&k.tmOut, slab, rows, cols, lds, 32);
   k.p.vec0 = src.ball + c0;
   k.p.vec1 = shift;
+  k.p.colsum = colsum;
   k.p.M = static_cast<int>(rows);
   k.p.N = static_cast<int>(cols);
   k.p.K = static_cast<int>(src.d_in);
   k.p.flags = round_out ? 0 : KM_FLAG_NO_ROUND;
   k.epi = EPI_COS;
   k.num_sms = c.num_sms;
-  KS_CUDA(launch_kmajor(k, c.st));
+  KS_CUDA(launch_kmajor(k, st));
   c.launches += 1;
 }
 
@@ -362,8 +369,9 @@ const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, b
 }
 
 void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* R, int64_t ldr, int kcols,
-                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c) {
+                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c, cudaStream_t st) {
   if (rows <= 0 || b <= 0 || (!with_g && !with_c)) return;
+  if (!st) st = c.st;
   GramLaunch g;
   int nt = 0;
   g.pair = c.gram_pair;
@@ -377,39 +385,38 @@ void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int
   int64_t chunk = c.gram_chunk_rows;
   chunk = std::max<int64_t>(kGramStageRows, chunk / kGramStageRows * kGramStageRows);
   g.chunk_rows = static_cast<int>(chunk);
-  tmap_or_throw(&g.tmOut0, G, b, b, ldg, 32);
+  if (with_g) tmap_or_throw(&g.tmOut0, G, b, b, ldg, 32);
   if (with_c) tmap_or_throw(&g.tmOut1, C, b, kcols, ldc, 32);
-  else g.tmOut1 = g.tmOut0;
+  if (!with_g) g.tmOut0 = g.tmOut1;
+  if (!with_c) g.tmOut1 = g.tmOut0;
   g.n_valid0 = b;
   g.n_valid1 = kcols;
-  KS_CUDA(launch_gram(g, c.st));
+  KS_CUDA(launch_gram(g, st));
   c.launches += 1;
 }
 
 void launch_update(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* bop, int64_t ldb, int k,
-                   float* out, int64_t ldo, const float* cbias, int epi, bool reduce) {
+                   float* out, int64_t ldo, const float* cbias, int epi, bool reduce, cudaStream_t st) {
   if (rows <= 0 || k <= 0 || b <= 0) return;
+  if (!st) st = c.st;
   KmLaunch u;
   tmap_or_throw(&u.tmA, slab, rows, b, lds, 128);
   tmap_or_throw(&u.tmB, bop, k, b, ldb, 256);
   tmap_or_throw(&u.tmOut, out, rows, k, ldo, 32);  // k valid columns: the store never touches columns >= k
   u.p.vec0 = cbias;
   u.p.vec1 = nullptr;
+  u.p.colsum = nullptr;
   u.p.M = static_cast<int>(rows);
   u.p.N = k;
   u.p.K = b;
   u.p.flags = reduce ? KM_FLAG_REDUCE : 0;
   u.epi = epi;
   u.num_sms = c.num_sms;
-  KS_CUDA(launch_kmajor(u, c.st));
+  KS_CUDA(launch_kmajor(u, st));
   c.launches += 1;
 }
 
 // ------------------------------------------------------------------------------------ small device helpers
-__global__ void mean_from_shift_kernel(const float* shift, const double* delta, double* mean, int b) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < b) mean[i] = static_cast<double>(shift[i]) + delta[i];
-}
 __global__ void scale_f64_to_f32_kernel(const double* src, double scale, float* dst, double* dst64, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -418,6 +425,7 @@ __global__ void scale_f64_to_f32_kernel(const double* src, double scale, float* 
     if (dst64) dst64[i] = v;
   }
 }
+__global__ void set_f64_kernel(double* p, double v) { *p = v; }
 __global__ void sumsq_f64_kernel(const double* p, int64_t n, double* out) {
   double acc = 0;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
@@ -433,6 +441,13 @@ __global__ void sumsq_f64_kernel(const double* p, int64_t n, double* out) {
 }
 
 // ------------------------------------------------------------------------------------ BlockLS fit
+// Two-stream software pipeline.  Per block j the work splits into a part that does NOT depend on the residual
+//   prep(j)  [stream st2]: shift estimate, slab S_j, G_j = S_j^T S_j, all-reduce, H_j = G_j - N d d^T + lambda I, Cholesky
+// and the residual-dependent chain
+//   main(j)  [stream st ]: Rr = tf32(R), C_j = S_j^T Rr, all-reduce, triangular solves, W_j += dW, R -= S_j dW.
+// prep(j+1) is enqueued before main(j), so the latency-bound Cholesky (about 100 small cuSOLVER kernels per block) and
+// the next block's featurization overlap with the tensor-core work of the current block; slabs / G / H are double
+// buffered and cross-stream dependencies are CUDA events.  No host synchronisation inside the loop.
 static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, int64_t nf_opt) {
   if (bs <= 0 || num_iter < 1) throw KsError{KS_ERR_INVALID, "blockSize must be > 0 and numIter >= 1"};
   if (Y.rows != src.n_rows) throw KsError{KS_ERR_INVALID, "features and labels have different row counts"};
@@ -444,29 +459,30 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   const int nb = static_cast<int>((D + bs - 1) / bs);
   const int bmax = static_cast<int>(std::min<int64_t>(bs, D));
   const int64_t lds = round_up(bmax, 32);
-  const int kcols = k + 1;  // residual + ones column
-  const int64_t kpad = round_up(kcols, 32);
+  const int64_t kpad = round_up(k, 32);
+  cudaStream_t S1 = c.st, S2 = c.st2;
   c.spans.clear();
   const int64_t launches0 = c.launches;
-  cudaEvent_t ev0 = c.get_event(), ev1 = c.get_event();
-  KS_CUDA(cudaEventRecord(ev0, c.st));
+  cudaEvent_t ev0 = c.get_event(), ev1 = c.get_event(), ev_init = c.get_event();
+  KS_CUDA(cudaStreamSynchronize(S2));
+  KS_CUDA(cudaEventRecord(ev0, S1));
 
   // ---- label mean (StandardScaler on labels, BlockLinearMapper.scala:215) + global row count
   DevBuf ysum;  // [k] sums, [k] = local row count
   ysum.alloc(sizeof(double) * (k + 1));
-  KS_CUDA(cudaMemsetAsync(ysum.p, 0, ysum.bytes, c.st));
+  KS_CUDA(cudaMemsetAsync(ysum.p, 0, ysum.bytes, S1));
   c.span_begin(PH_OTHER);
-  launch_colsum(Y.d, nullptr, Y.ld, n_loc, k, ysum.as<double>(), c.st);
+  launch_colsum(Y.d, nullptr, Y.ld, n_loc, k, ysum.as<double>(), S1);
   c.launches += 1;
   {
     const double nl = static_cast<double>(n_loc);
-    KS_CUDA(cudaMemcpyAsync(ysum.as<double>() + k, &nl, sizeof(double), cudaMemcpyHostToDevice, c.st));
-    KS_CUDA(cudaStreamSynchronize(c.st));
+    KS_CUDA(cudaMemcpyAsync(ysum.as<double>() + k, &nl, sizeof(double), cudaMemcpyHostToDevice, S1));
+    KS_CUDA(cudaStreamSynchronize(S1));
   }
   c.allreduce_f64(ysum.as<double>(), k + 1);
   double n_total_d = 0;
-  KS_CUDA(cudaMemcpyAsync(&n_total_d, ysum.as<double>() + k, sizeof(double), cudaMemcpyDeviceToHost, c.st));
-  KS_CUDA(cudaStreamSynchronize(c.st));
+  KS_CUDA(cudaMemcpyAsync(&n_total_d, ysum.as<double>() + k, sizeof(double), cudaMemcpyDeviceToHost, S1));
+  KS_CUDA(cudaStreamSynchronize(S1));
   if (n_total_d < 1) throw KsError{KS_ERR_INVALID, "no training rows"};
   auto model = std::make_unique<Model>();
   model->block_size = bs;
@@ -474,164 +490,206 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   model->has_mean = true;
   model->has_intercept = true;
   model->intercept.alloc(sizeof(double) * k);
-  scale_f64_to_f32_kernel<<<(k + 255) / 256, 256, 0, c.st>>>(ysum.as<double>(), 1.0 / n_total_d, nullptr,
-                                                             model->intercept.as<double>(), k);
+  scale_f64_to_f32_kernel<<<(k + 255) / 256, 256, 0, S1>>>(ysum.as<double>(), 1.0 / n_total_d, nullptr,
+                                                          model->intercept.as<double>(), k);
   c.launches += 1;
 
-  // ---- residual R = Y - mean (fp32 master) and Rr = its tf32-rounded copy with the ones column (Gram operand)
-  DevBuf r_f32, r_tf32, slab, gc, H, rhs, rsum, bop, cbias;
+  // ---- residual R = Y - mean (fp32 master) and Rr = its tf32-rounded copy (the Gram kernel's B operand)
+  DevBuf r_f32, r_tf32, slab[2], gbuf[2], Hbuf[2], ssum[2], cm, rhs, rsum, bop, cbias, samp, fsum;
   r_f32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * kpad));
   r_tf32.alloc(r_f32.bytes);
-  launch_init_residual(Y.d, Y.ld, model->intercept.as<double>(), r_f32.as<float>(), kpad, n_loc, k, c.st);
+  launch_init_residual(Y.d, Y.ld, model->intercept.as<double>(), r_f32.as<float>(), kpad, n_loc, k, S1);
   c.launches += 1;
   c.span_end();
 
-  slab.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));
   const int ldg = static_cast<int>(lds), ldc = static_cast<int>(kpad);
   const size_t g_elems = static_cast<size_t>(bmax) * ldg, c_elems = static_cast<size_t>(bmax) * ldc;
-  gc.alloc(sizeof(float) * (g_elems + c_elems));
-  float* G = gc.as<float>();
-  float* Cm = G + g_elems;
+  const bool cache_factors = num_iter > 1;
+  for (int i = 0; i < 2; ++i) {
+    slab[i].alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));
+    gbuf[i].alloc(sizeof(float) * g_elems);
+    ssum[i].alloc(sizeof(float) * lds);
+    if (!cache_factors) Hbuf[i].alloc(sizeof(double) * static_cast<size_t>(bmax) * bmax);
+  }
+  cm.alloc(sizeof(float) * c_elems);
   rhs.alloc(sizeof(double) * static_cast<size_t>(bmax) * k);
   rsum.alloc(sizeof(double) * kpad);
   bop.alloc(sizeof(float) * static_cast<size_t>(kpad) * lds);
   cbias.alloc(sizeof(float) * kpad);
-  const bool cache_factors = num_iter > 1;
+  samp.alloc(sizeof(double) * (bmax + 1));  // sample column sums + sample row count (generated features)
   std::vector<std::unique_ptr<DevBuf>> factors(nb), deltas(nb), shifts(nb);
-  if (!cache_factors) H.alloc(sizeof(double) * static_cast<size_t>(bmax) * bmax);
 
   // ---- exact column means for materialised features (one pass over F for all blocks)
-  DevBuf fsum;
   if (src.F) {
     c.span_begin(PH_FEATURIZE);
     fsum.alloc(sizeof(double) * static_cast<size_t>(src.F->ld));
-    KS_CUDA(cudaMemsetAsync(fsum.p, 0, fsum.bytes, c.st));
-    launch_colsum(src.F->d, nullptr, src.F->ld, n_loc, static_cast<int>(src.F->cols), fsum.as<double>(), c.st);
+    KS_CUDA(cudaMemsetAsync(fsum.p, 0, fsum.bytes, S1));
+    launch_colsum(src.F->d, nullptr, src.F->ld, n_loc, static_cast<int>(src.F->cols), fsum.as<double>(), S1);
     c.launches += 1;
     c.allreduce_f64(fsum.as<double>(), static_cast<size_t>(src.F->cols));
     c.span_end();
   }
-  DevBuf ssum;  // sample column sums for generated features: [bmax] sums + [1] count
-  if (!src.F) ssum.alloc(sizeof(double) * (bmax + 1));
+  KS_CUDA(cudaEventRecord(ev_init, S1));
+  KS_CUDA(cudaStreamWaitEvent(S2, ev_init, 0));
 
+  struct Step { int it, j; };
+  std::vector<Step> steps;
+  for (int it = 0; it < num_iter; ++it)
+    for (int j = 0; j < nb; ++j) steps.push_back({it, j});
+  const int T = static_cast<int>(steps.size());
+  std::vector<cudaEvent_t> ev_slab(T), ev_fact(T), ev_upd(T);
+  for (int t = 0; t < T; ++t) {
+    ev_slab[t] = c.get_event();
+    ev_fact[t] = c.get_event();
+    ev_upd[t] = c.get_event();
+  }
   int info_slot = 0;
   double flops = 0;
-  for (int it = 0; it < num_iter; ++it) {
-    for (int j = 0; j < nb; ++j) {
-      const int64_t c0 = static_cast<int64_t>(j) * bs;
-      const int b = static_cast<int>(std::min<int64_t>(D, c0 + bs) - c0);
-      // ---------------- featurize: shift estimate (pass 0) + centred, tf32-rounded slab
-      c.span_begin(PH_FEATURIZE);
-      if (it == 0) {
-        shifts[j] = std::make_unique<DevBuf>();
-        shifts[j]->alloc(sizeof(float) * lds);
-        KS_CUDA(cudaMemsetAsync(shifts[j]->p, 0, shifts[j]->bytes, c.st));
-        if (src.F) {
-          scale_f64_to_f32_kernel<<<(b + 255) / 256, 256, 0, c.st>>>(fsum.as<double>() + c0, 1.0 / n_total_d,
-                                                                     shifts[j]->as<float>(), nullptr, b);
-          c.launches += 1;
-        } else {
-          // mean estimate from the first sample_rows rows of every rank (exactness is restored by the rank-1
-          // correction with delta below; the estimate only has to be close enough to avoid cancellation)
-          const int64_t ns = std::min<int64_t>(n_loc, c.sample_rows);
-          KS_CUDA(cudaMemsetAsync(ssum.p, 0, ssum.bytes, c.st));
-          produce_slab(c, src, c0, b, src.zeros.as<float>(), slab.as<float>(), lds, 0, ns, /*round_out=*/false);
-          launch_colsum(slab.as<float>(), nullptr, lds, ns, b, ssum.as<double>(), c.st);
-          c.launches += 1;
-          const double nsd = static_cast<double>(ns);
-          KS_CUDA(cudaMemcpyAsync(ssum.as<double>() + bmax, &nsd, sizeof(double), cudaMemcpyHostToDevice, c.st));
-          KS_CUDA(cudaStreamSynchronize(c.st));
-          c.allreduce_f64(ssum.as<double>(), bmax + 1);
-          double cnt = 0;
-          KS_CUDA(cudaMemcpyAsync(&cnt, ssum.as<double>() + bmax, sizeof(double), cudaMemcpyDeviceToHost, c.st));
-          KS_CUDA(cudaStreamSynchronize(c.st));
-          scale_f64_to_f32_kernel<<<(b + 255) / 256, 256, 0, c.st>>>(ssum.as<double>(), 1.0 / std::max(cnt, 1.0),
-                                                                     shifts[j]->as<float>(), nullptr, b);
-          c.launches += 1;
-          flops += 2.0 * static_cast<double>(ns) * src.d_in * b;
-        }
-      }
-      produce_slab(c, src, c0, b, shifts[j]->as<float>(), slab.as<float>(), lds, 0, n_loc);
-      if (!src.F) flops += 2.0 * static_cast<double>(n_loc) * src.d_in * b;
-      c.span_end();
 
-      // ---------------- Gram: [G | C] = S^T [S | R | 1]  (pass > 0: C only, the factor is cached)
-      const bool with_g = (it == 0);
-      c.span_begin(PH_OTHER);
-      if (with_g) KS_CUDA(cudaMemsetAsync(G, 0, sizeof(float) * (g_elems + c_elems), c.st));
-      else KS_CUDA(cudaMemsetAsync(Cm, 0, sizeof(float) * c_elems, c.st));
-      KS_CUDA(cudaMemsetAsync(rsum.p, 0, rsum.bytes, c.st));
-      launch_round_colsum(r_f32.as<float>(), r_tf32.as<float>(), kpad, n_loc, k, rsum.as<double>(), c.st);
-      c.launches += 1;
-      c.span_end();
-      c.span_begin(PH_GRAM);  // exactly one gram_tn_kernel launch: bench.py's roofline reads this span
-      launch_gram_block(c, slab.as<float>(), lds, n_loc, b, r_tf32.as<float>(), kpad, kcols, G, ldg, Cm, ldc, with_g, true);
-      flops += (with_g ? 2.0 * n_loc * static_cast<double>(b) * b : 0.0) + 2.0 * n_loc * static_cast<double>(b) * k;
-      c.span_end();
+  auto block_cols = [&](int j, int64_t* c0) {
+    *c0 = static_cast<int64_t>(j) * bs;
+    return static_cast<int>(std::min<int64_t>(D, *c0 + bs) - *c0);
+  };
 
-      // ---------------- all-reduce (replaces treeReduce, BlockWeightedLeastSquares.scala:212-225)
-      c.span_begin(PH_ALLREDUCE);
-      if (with_g) c.allreduce_f32(G, g_elems + c_elems);
-      else c.allreduce_f32(Cm, c_elems);
-      c.allreduce_f64(rsum.as<double>(), k);
-      c.span_end();
-
-      // ---------------- solve (G_c + lambda I) dW = C_c - lambda W_old in fp64
-      c.span_begin(PH_SOLVE);
-      double* Hj;
-      if (it == 0) {
-        deltas[j] = std::make_unique<DevBuf>();
-        deltas[j]->alloc(sizeof(double) * b);
-        if (cache_factors) {
-          factors[j] = std::make_unique<DevBuf>();
-          factors[j]->alloc(sizeof(double) * static_cast<size_t>(b) * b);
-          Hj = factors[j]->as<double>();
-        } else {
-          Hj = H.as<double>();
-        }
-        launch_build_system(G, ldg, Cm, ldc, k, n_total_d, lam, Hj, deltas[j]->as<double>(), b, c.st);
+  // ---------------- prep(t): everything that does not depend on the residual, on stream S2
+  auto prep = [&](int t) {
+    const int it = steps[t].it, j = steps[t].j, buf = t & 1;
+    int64_t c0;
+    const int b = block_cols(j, &c0);
+    if (t >= 2) KS_CUDA(cudaStreamWaitEvent(S2, ev_upd[t - 2], 0));  // slab / G / H buffers of step t-2 are free
+    c.span_begin(PH_FEATURIZE, S2);
+    if (it == 0) {
+      shifts[j] = std::make_unique<DevBuf>();
+      shifts[j]->alloc(sizeof(float) * lds);
+      KS_CUDA(cudaMemsetAsync(shifts[j]->p, 0, shifts[j]->bytes, S2));
+      if (src.F) {
+        scale_f64_to_f32_kernel<<<(b + 255) / 256, 256, 0, S2>>>(fsum.as<double>() + c0, 1.0 / n_total_d,
+                                                                 shifts[j]->as<float>(), nullptr, b);
         c.launches += 1;
-        c.potrf(Hj, b, info_slot++);
-        auto mean = std::make_unique<DevBuf>();
-        mean->alloc(sizeof(double) * b);
-        mean_from_shift_kernel<<<(b + 255) / 256, 256, 0, c.st>>>(shifts[j]->as<float>(), deltas[j]->as<double>(),
-                                                                  mean->as<double>(), b);
-        c.launches += 1;
-        auto W = std::make_unique<DevBuf>();
-        W->alloc(sizeof(double) * static_cast<size_t>(b) * k);
-        KS_CUDA(cudaMemsetAsync(W->p, 0, W->bytes, c.st));
-        model->brows.push_back(b);
-        model->W.push_back(std::move(W));
-        model->mean.push_back(std::move(mean));
-        flops += static_cast<double>(b) * b * b / 3.0;
       } else {
-        Hj = factors[j]->as<double>();
+        // mean estimate from the first sample_rows rows of every rank; exactness is restored by the rank-1 correction
+        // with delta below, the estimate only has to be close enough to avoid cancellation
+        const int64_t ns = std::min<int64_t>(n_loc, c.sample_rows);
+        KS_CUDA(cudaMemsetAsync(samp.p, 0, samp.bytes, S2));
+        KS_CUDA(cudaMemsetAsync(ssum[buf].p, 0, ssum[buf].bytes, S2));
+        produce_slab(c, src, c0, b, src.zeros.as<float>(), slab[buf].as<float>(), lds, 0, ns, /*round_out=*/false,
+                     ssum[buf].as<float>(), S2);
+        launch_f32_to_f64_rows(ssum[buf].as<float>(), lds, samp.as<double>(), bmax, 1, b, S2);  // 1 x b "matrix"
+        c.launches += 1;
+        set_f64_kernel<<<1, 1, 0, S2>>>(samp.as<double>() + bmax, static_cast<double>(ns));
+        c.launches += 1;
+        c.allreduce_f64(samp.as<double>(), bmax + 1, /*prep=*/true);
+        launch_divide_by_count(samp.as<double>(), samp.as<double>() + bmax, shifts[j]->as<float>(), nullptr, b, S2);
+        c.launches += 1;
+        flops += 2.0 * static_cast<double>(ns) * src.d_in * b;
       }
-      launch_build_rhs(Cm, ldc, deltas[j]->as<double>(), rsum.as<double>(), n_total_d, lam,
-                       it > 0 ? model->W[j]->as<double>() : nullptr, rhs.as<double>(), b, k, c.st);
-      c.launches += 1;
-      c.potrs(Hj, b, rhs.as<double>(), k, info_slot++);
-      launch_pack_update(rhs.as<double>(), model->W[j]->as<double>(), deltas[j]->as<double>(), bop.as<float>(), nullptr,
-                         static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), c.st);
-      c.launches += 1;
-      flops += 2.0 * static_cast<double>(b) * b * k;
-      c.span_end();
-
-      // ---------------- residual update R -= (S - 1 delta^T) dW
-      c.span_begin(PH_UPDATE);
-      launch_update(c, slab.as<float>(), lds, n_loc, b, bop.as<float>(), lds, k, r_f32.as<float>(), kpad, cbias.as<float>(),
-                    EPI_UPDATE, /*reduce=*/true);
-      flops += 2.0 * n_loc * static_cast<double>(b) * k;
-      c.span_end();
     }
+    KS_CUDA(cudaMemsetAsync(ssum[buf].p, 0, ssum[buf].bytes, S2));
+    produce_slab(c, src, c0, b, shifts[j]->as<float>(), slab[buf].as<float>(), lds, 0, n_loc, true,
+                 it == 0 ? ssum[buf].as<float>() : nullptr, S2);
+    if (!src.F) flops += 2.0 * static_cast<double>(n_loc) * src.d_in * b;
+    c.span_end(S2);
+    KS_CUDA(cudaEventRecord(ev_slab[t], S2));
+    if (it == 0) {
+      c.span_begin(PH_GRAM, S2);  // G part of the Gram
+      KS_CUDA(cudaMemsetAsync(gbuf[buf].p, 0, gbuf[buf].bytes, S2));
+      launch_gram_block(c, slab[buf].as<float>(), lds, n_loc, b, nullptr, 0, 0, gbuf[buf].as<float>(), ldg, nullptr, 0, true,
+                        false, S2);
+      flops += 2.0 * n_loc * static_cast<double>(b) * b;
+      c.span_end(S2);
+      c.span_begin(PH_ALLREDUCE, S2);
+      c.allreduce_f32(gbuf[buf].as<float>(), g_elems, true);
+      c.allreduce_f32(ssum[buf].as<float>(), static_cast<size_t>(b), true);
+      c.span_end(S2);
+      c.span_begin(PH_SOLVE, S2);
+      deltas[j] = std::make_unique<DevBuf>();
+      deltas[j]->alloc(sizeof(double) * b);
+      auto mean = std::make_unique<DevBuf>();
+      mean->alloc(sizeof(double) * b);
+      launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), mean->as<double>(), b, S2);
+      double* Hj;
+      if (cache_factors) {
+        factors[j] = std::make_unique<DevBuf>();
+        factors[j]->alloc(sizeof(double) * static_cast<size_t>(b) * b);
+        Hj = factors[j]->as<double>();
+      } else {
+        Hj = Hbuf[buf].as<double>();
+      }
+      launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S2);
+      c.launches += 2;
+      c.potrf(Hj, b, info_slot++, S2);
+      auto W = std::make_unique<DevBuf>();
+      W->alloc(sizeof(double) * static_cast<size_t>(b) * k);
+      KS_CUDA(cudaMemsetAsync(W->p, 0, W->bytes, S2));
+      model->brows.push_back(b);
+      model->W.push_back(std::move(W));
+      model->mean.push_back(std::move(mean));
+      flops += static_cast<double>(b) * b * b / 3.0;
+      c.span_end(S2);
+    }
+    KS_CUDA(cudaEventRecord(ev_fact[t], S2));
+  };
+
+  // ---------------- main(t): the residual-dependent chain, on stream S1
+  auto mainstep = [&](int t) {
+    const int it = steps[t].it, j = steps[t].j, buf = t & 1;
+    int64_t c0;
+    const int b = block_cols(j, &c0);
+    c.span_begin(PH_OTHER);
+    KS_CUDA(cudaMemsetAsync(cm.p, 0, sizeof(float) * c_elems, S1));
+    KS_CUDA(cudaMemsetAsync(rsum.p, 0, rsum.bytes, S1));
+    launch_round_colsum(r_f32.as<float>(), r_tf32.as<float>(), kpad, n_loc, k, rsum.as<double>(), S1);
+    c.launches += 1;
+    c.span_end();
+    KS_CUDA(cudaStreamWaitEvent(S1, ev_slab[t], 0));
+    c.span_begin(PH_UPDATE);  // A^T R part of the Gram (accounted with the residual chain)
+    launch_gram_block(c, slab[buf].as<float>(), lds, n_loc, b, r_tf32.as<float>(), kpad, k, nullptr, 0, cm.as<float>(), ldc,
+                      false, true, S1);
+    flops += 2.0 * n_loc * static_cast<double>(b) * k;
+    c.span_end();
+    c.span_begin(PH_ALLREDUCE);
+    c.allreduce_f32(cm.as<float>(), c_elems);
+    c.allreduce_f64(rsum.as<double>(), k);
+    c.span_end();
+    KS_CUDA(cudaStreamWaitEvent(S1, ev_fact[t], 0));
+    c.span_begin(PH_SOLVE);
+    double* Hj = cache_factors ? factors[j]->as<double>() : Hbuf[buf].as<double>();
+    launch_build_rhs(cm.as<float>(), ldc, deltas[j]->as<double>(), rsum.as<double>(), n_total_d, lam,
+                     it > 0 ? model->W[j]->as<double>() : nullptr, rhs.as<double>(), b, k, S1);
+    c.launches += 1;
+    c.potrs(Hj, b, rhs.as<double>(), k, info_slot++, S1);
+    launch_pack_update(rhs.as<double>(), model->W[j]->as<double>(), deltas[j]->as<double>(), bop.as<float>(), nullptr,
+                       static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), S1);
+    c.launches += 1;
+    flops += 2.0 * static_cast<double>(b) * b * k;
+    c.span_end();
+    c.span_begin(PH_UPDATE);
+    launch_update(c, slab[buf].as<float>(), lds, n_loc, b, bop.as<float>(), lds, k, r_f32.as<float>(), kpad, cbias.as<float>(),
+                  EPI_UPDATE, /*reduce=*/true, S1);
+    flops += 2.0 * n_loc * static_cast<double>(b) * k;
+    c.span_end();
+    KS_CUDA(cudaEventRecord(ev_upd[t], S1));
+  };
+
+  prep(0);
+  for (int t = 0; t < T; ++t) {
+    if (t + 1 < T) prep(t + 1);
+    mainstep(t);
   }
-  KS_CUDA(cudaEventRecord(ev1, c.st));
+  KS_CUDA(cudaStreamWaitEvent(S1, ev_fact[T - 1], 0));
+  KS_CUDA(cudaEventRecord(ev1, S1));
   c.check_async("BlockLeastSquaresEstimator.fit");
   c.check_infos(info_slot);
   float total_ms = 0;
   cudaEventElapsedTime(&total_ms, ev0, ev1);
   c.event_pool.push_back(ev0);
   c.event_pool.push_back(ev1);
+  c.event_pool.push_back(ev_init);
+  for (int t = 0; t < T; ++t) {
+    c.event_pool.push_back(ev_slab[t]);
+    c.event_pool.push_back(ev_fact[t]);
+    c.event_pool.push_back(ev_upd[t]);
+  }
   double ms[PH_COUNT];
   c.collect_spans(ms);
   std::ostringstream js;
@@ -640,7 +698,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
      << ",\"world\":" << c.world << ",\"total_ms\":" << total_ms << ",\"featurize_ms\":" << ms[PH_FEATURIZE]
      << ",\"gram_ms\":" << ms[PH_GRAM] << ",\"allreduce_ms\":" << ms[PH_ALLREDUCE] << ",\"solve_ms\":" << ms[PH_SOLVE]
      << ",\"update_ms\":" << ms[PH_UPDATE] << ",\"other_ms\":" << ms[PH_OTHER] << ",\"local_flops\":" << flops
-     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"tf32x1\"}";
+     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"tf32x1\",\"streams\":2}";
   c.stats_json = js.str();
   return c.add(std::move(model));
 }
@@ -777,11 +835,17 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
       if (v >= kGramStageRows) c->gram_chunk_rows = v;
     }
     if (const char* e = getenv("KS_GRAM_PAIR")) c->gram_pair = atoi(e) != 0;
+    KS_CUDA(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
     if (world_size > 1) {
       if (!nccl_id) throw KsError{KS_ERR_INVALID, "nccl_id required for world_size > 1"};
       ncclUniqueId id;
       memcpy(&id, nccl_id, KS_NCCL_ID_BYTES);
       KS_NCCL(nccl_api().CommInitRank(&c->comm, world_size, id, rank));
+      c->comm2 = c->comm;
+      if (nccl_api().CommSplit) {  // a second communicator so that collectives of the two streams never interleave
+        ncclComm_t c2 = nullptr;
+        if (nccl_api().CommSplit(c->comm, 0, rank, &c2, nullptr) == ncclSuccess && c2) c->comm2 = c2;
+      }
     }
     std::lock_guard<std::mutex> lk(g_mu);
     const int64_t h = g_next_ctx++;
@@ -805,16 +869,19 @@ KS_API int32_t ks_ctx_destroy(int64_t ctx) {
   }
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
+  if (c->st2) cudaStreamSynchronize(c->st2);
   c->matrices.clear();
   c->rfs.clear();
   c->models.clear();
   c->tile_cache.clear();
   for (auto e : c->event_pool) cudaEventDestroy(e);
   if (c->solver) solver_api().Destroy(c->solver);
+  if (c->comm2 && c->comm2 != c->comm) nccl_api().CommDestroy(c->comm2);
   if (c->comm) nccl_api().CommDestroy(c->comm);
   c->solver_work.release();
   c->dev_info.release();
   cudaStreamDestroy(c->st);
+  if (c->st2) cudaStreamDestroy(c->st2);
   c.reset();
   bool last;
   {

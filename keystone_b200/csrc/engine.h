@@ -95,6 +95,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;  // optional (NCCL >= 2.18)
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -106,8 +107,10 @@ enum Phase { PH_FEATURIZE = 0, PH_GRAM, PH_ALLREDUCE, PH_SOLVE, PH_UPDATE, PH_OT
 struct Ctx {
   int device = 0, rank = 0, world = 1;
   int num_sms = 148;
-  cudaStream_t st = nullptr;
-  ncclComm_t comm = nullptr;
+  cudaStream_t st = nullptr;   // main stream: residual-dependent chain (A^T R, triangular solves, update)
+  cudaStream_t st2 = nullptr;  // prep stream: featurize + Gram + Cholesky of the NEXT block (independent of the residual)
+  ncclComm_t comm = nullptr;   // collectives issued on st
+  ncclComm_t comm2 = nullptr;  // collectives issued on st2 (split of comm; falls back to comm)
   cusolverDnHandle_t solver = nullptr;
   DevBuf solver_work;
   int solver_lwork = 0;
@@ -135,14 +138,14 @@ struct Ctx {
   int64_t add(std::unique_ptr<Matrix> m);
   int64_t add(std::unique_ptr<Model> m);
   cudaEvent_t get_event();
-  void span_begin(int phase);
-  void span_end();
+  void span_begin(int phase, cudaStream_t s = nullptr);
+  void span_end(cudaStream_t s = nullptr);
   void collect_spans(double out_ms[PH_COUNT]);
-  void allreduce_f32(float* p, size_t n);
-  void allreduce_f64(double* p, size_t n);
+  void allreduce_f32(float* p, size_t n, bool prep = false);
+  void allreduce_f64(double* p, size_t n, bool prep = false);
   void ensure_solver();
-  void potrf(double* H, int n, int info_slot);
-  void potrs(const double* H, int n, double* B, int nrhs, int info_slot);
+  void potrf(double* H, int n, int info_slot, cudaStream_t s);
+  void potrs(const double* H, int n, double* B, int nrhs, int info_slot, cudaStream_t s);
   void check_infos(int used_slots);
   void check_async(const char* what);
 };
@@ -161,14 +164,15 @@ struct FeatSrc {
 };
 void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out);
 // slab[rows x lds] = round_tf32(features[row_begin : row_begin+rows, c0 : c0+cols] - shift)   (shift may be the zero vector)
+// colsum (optional, fp32[cols], must be zeroed): receives the column sums of the stored slab
 void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, float* slab, int64_t lds,
-                  int64_t row_begin, int64_t rows, bool round_out = true);
+                  int64_t row_begin, int64_t rows, bool round_out = true, float* colsum = nullptr, cudaStream_t st = nullptr);
 const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, bool pair, int* num_tiles);
 void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* R, int64_t ldr, int kcols,
-                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c);
+                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c, cudaStream_t st = nullptr);
 // out[rows x k] (+)= (epi == EPI_UPDATE ? -1 : +1) * slab[rows x b] * bop[k x b]^T + cbias   (reduce: add into out)
 void launch_update(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* bop, int64_t ldb, int k,
-                   float* out, int64_t ldo, const float* cbias, int epi, bool reduce);
+                   float* out, int64_t ldo, const float* cbias, int epi, bool reduce, cudaStream_t st = nullptr);
 
 int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, double w, int64_t nf_opt);
 

@@ -31,6 +31,7 @@ enum { KM_FLAG_NO_ROUND = 1, KM_FLAG_REDUCE = 2 };
 struct KmParams {
   const float* vec0;  // EPI_COS: bias;  EPI_UPDATE / EPI_APPLY: per-column constant
   const float* vec1;  // EPI_COS: shift
+  float* colsum;      // EPI_COS: if non-null, colsum[n] += sum over valid rows of the stored values (fp32 atomics)
   int M, N, K;
   int flags;  // KM_FLAG_NO_ROUND: EPI_COS keeps fp32;  KM_FLAG_REDUCE: add into the output instead of overwriting it
 };
@@ -61,12 +62,16 @@ void launch_init_residual(const float* Y, int64_t ldy, const double* ymean, floa
 // Rr[:, :k] = tf32_rn(R[:, :k]) (the Gram's MN-major operand), Rr[:, k] = 1 (ones column), Rr[:, > k] = 0, and
 // sums[c] += column sums of R (fp64; must be zeroed) -- one pass over R per block
 void launch_round_colsum(const float* R, float* Rr, int64_t ld, int64_t rows, int k, double* sums, cudaStream_t st);
-// slab[:, :cols] = tf32(F[:, c0:c0+cols] - shift)  (+ lo remainder plane)
-void launch_center_round(const float* F, int64_t ldf, int c0, const float* shift, float* s_hi, float* s_lo, int64_t lds,
+// slab[:, :cols] = tf32(F[:, c0:c0+cols] - shift); if colsum != null, colsum[c] += column sums of the slab (fp32 atomics)
+void launch_center_round(const float* F, int64_t ldf, int c0, const float* shift, float* slab, float* colsum, int64_t lds,
                          int64_t rows, int cols, cudaStream_t st);
-// H (fp64, column-major b x b, ld = b) = sym(G) - n * d d^T + lam * I,  d = C[:, k_ones] / n
-void launch_build_system(const float* G, int ldg, const float* C, int ldc, int k_ones, double n_total, double lam,
-                         double* H, double* delta, int b, cudaStream_t st);
+// out[i] = float(sums[i] / *count) (and out64 if non-null); the count lives on the device (no host round trip)
+void launch_divide_by_count(const double* sums, const double* count, float* out, double* out64, int n, cudaStream_t st);
+// delta[i] = double(ssum[i]) / n_total ; mean[i] = shift[i] + delta[i]
+void launch_delta_mean(const float* ssum, const float* shift, double n_total, double* delta, double* mean, int b, cudaStream_t st);
+// H (fp64, column-major b x b, ld = b) = sym(G) - n * delta delta^T + lam * I
+void launch_build_system(const float* G, int ldg, const double* delta, double n_total, double lam, double* H, int b,
+                         cudaStream_t st);
 // RHS (fp64 column-major b x k, ld = b) = C[:, :k] - n * delta * rbar^T - lam * Wold
 void launch_build_rhs(const float* C, int ldc, const double* delta, const double* rsum, double n_total, double lam,
                       const double* Wold, double* rhs, int b, int k, cudaStream_t st);

@@ -480,6 +480,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] + __uint_as_float(v[i]);
         }
+        if (EPI == EPI_COS && p.colsum != nullptr && m0 + q * 32 + lane >= p.M) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = 0.f;  // rows past the end must not pollute the column sums
+        }
         if (lane == 0) bulk_wait_read0();  // the previous chunk's store has finished reading the staging buffer
         __syncwarp();
         stage_row_sw128(buf, lane, o);
@@ -489,6 +493,16 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           if (p.flags & KM_FLAG_REDUCE) tma_reduce_add_2d(&tmOut, buf, n0 + c0, m0 + q * 32);
           else tma_store_2d(&tmOut, buf, n0 + c0, m0 + q * 32);
           bulk_commit();
+        }
+        if (EPI == EPI_COS && p.colsum != nullptr) {
+          // column sums of the chunk straight from the staged copy: lane c adds column c over the 32 rows
+          // (row r keeps 16 B chunk j at (j ^ (r & 7)): 32 lanes read 32 distinct words of one 128 B row, no conflicts)
+          float cs = 0.f;
+#pragma unroll
+          for (int r = 0; r < 32; ++r)
+            cs += *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+          const int n = n0 + c0 + lane;
+          if (n < p.N) atomicAdd(p.colsum + n, cs);
         }
       }
       tc_fence_before();

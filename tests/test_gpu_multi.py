@@ -1,0 +1,54 @@
+"""Multi-GPU parity (needs >= 2 visible GPUs; skipped otherwise): rows sharded over 2 ranks, NCCL all-reduce of the Gram
+inside ks_blockls_fit, every rank solves redundantly -> all ranks hold the same model and it matches the fp64 oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, id_holder, ret):
+    sys.path.insert(0, ROOT)
+    import keystone_b200 as ks
+    from oracle import keystone_oracle as ko
+    rng = np.random.default_rng(21)
+    n, d_in, n_out, k = 6001, 40, 256, 6
+    X = rng.standard_normal((n, d_in)).astype(np.float32)
+    cls = rng.integers(0, k, n)
+    params = [ko.cosine_random_features_params(d_in, n_out, 0.2, rng) for _ in range(2)]
+    lo, hi = ks.shard_range(n, rank, world)
+    ctx = ks.Context(device=rank, rank=rank, world_size=world, nccl_id=id_holder["id"])
+    x = ctx.matrix(X[lo:hi]); y = ctx.labels_from_classes(cls[lo:hi], k)
+    rfs = [ks.CosineRandomFeatures(ctx, W, b) for W, b in params]
+    feats = ks.Pipeline.gather(rfs).andThen(ks.VectorCombiner())(x)
+    model = ks.BlockLeastSquaresEstimator(n_out, 2, 0.5).fit(feats, y)
+    W = np.concatenate(model.xs, 0)
+    cost = model.compute_cost(feats, y, 0.5)
+    if rank == 0:
+        F = np.concatenate([ko.cosine_random_features(X.astype(np.float64), Wm, b) for Wm, b in params], 1)
+        Y = ko.class_label_indicators(cls, k)
+        xs, b0, mus = ko.block_ls_fit(F, Y, n_out, 2, 0.5)
+        Wr = np.concatenate(xs, 0)
+        ret["rel"] = float(np.linalg.norm(W - Wr) / np.linalg.norm(Wr))
+        ret["cost_rel"] = float(abs(cost - ko.compute_cost(F, Y, 0.5, xs, n_out, b0)) / cost)
+        ret["b_err"] = float(np.abs(model.b_opt - b0).max())
+    ret[f"W{rank}"] = W
+    ctx.close()
+
+
+def test_two_rank_fit_matches_oracle():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import keystone_b200 as ks
+    mgr = mp.Manager()
+    id_holder = mgr.dict(); ret = mgr.dict()
+    id_holder["id"] = ks.Context.new_nccl_id()
+    mp.spawn(_worker, args=(2, id_holder, ret), nprocs=2, join=True)
+    assert ret["rel"] < 5e-3, ret["rel"]
+    assert ret["cost_rel"] < 2e-3 and ret["b_err"] < 1e-5
+    assert np.array_equal(ret["W0"], ret["W1"])      # redundant solves are bit-identical across ranks
