@@ -198,3 +198,70 @@ def test_error_paths(ctx):
         ks.BlockLeastSquaresEstimator(4, 1, 0.0).fit(ctx.matrix(np.ones((4, 4))), ctx.matrix(np.ones((5, 1))))
     with pytest.raises(ks.KeystoneError):   # singular system, lambda = 0 -> not SPD, reported (no crash / exit)
         ks.BlockLeastSquaresEstimator(4, 1, 0.0).fit(ctx.matrix(np.ones((6, 4))), ctx.matrix(np.ones((6, 1))))
+
+
+# ---- BlockWeightedLeastSquaresEstimator on the device (T/nodes/learning/BlockWeightedLeastSquaresSuite.scala) ----
+def _bwls_compare(ctx, A, B, bs, iters, lam=0.1, w=0.3, tol=W_TOL):
+    model = ks.BlockWeightedLeastSquaresEstimator(bs, iters, lam, w).fit(ctx.matrix(A), ctx.matrix(B))
+    xs, fb = ko.bwls_fit(A, B, bs, iters, lam, w)
+    Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
+    assert [x.shape for x in model.xs] == [x.shape for x in xs]
+    assert model.feature_means is None                       # no feature scalers (BlockWeightedLeastSquares.scala:320)
+    err, ref = np.linalg.norm(Wg - Wr), np.linalg.norm(Wr)
+    assert err <= tol * ref + 1e-6, (err, ref)      # the single-class fixture has W == 0 exactly
+    assert np.abs(model.b_opt - fb).max() < tol * max(1.0, np.abs(fb).max())
+    return model, Wg, Wr, fb
+
+
+def test_bwls_reference_fixture(ctx, golden_dir):
+    """:142-166 (b=4, 10 iters, gradient of the weighted objective ~ 0) and :188-223 (ragged b=5) on aMat/bMat."""
+    A = np.loadtxt(os.path.join(golden_dir, "aMat.csv"), delimiter=",")
+    B = np.loadtxt(os.path.join(golden_dir, "bMat.csv"), delimiter=",")
+    model, Wg, Wr, fb = _bwls_compare(ctx, A, B, 4, 10)
+    g = ko.compute_gradient(A, B, 0.1, 0.3, Wg, model.b_opt)
+    g_ref = ko.compute_gradient(A, B, 0.1, 0.3, Wr, fb)
+    # the reference bound is 1e-2 and the fp64 oracle sits at 8.1e-3; tf32 operands may add a few 1e-4
+    assert np.linalg.norm(g) < np.linalg.norm(g_ref) + 2e-3
+    model5, W5, _, _ = _bwls_compare(ctx, A, B, 5, 10)
+    assert np.linalg.norm(ko.compute_gradient(A, B, 0.1, 0.3, W5, model5.b_opt)) < 1e-1
+    # predictions through BlockLinearMapper.apply (no scalers, intercept = finalB)
+    pred = model(ctx.matrix(A)).to_numpy()
+    assert np.abs(pred - (A @ Wr + fb)).max() < 5e-3
+
+
+def test_bwls_group_by_classes_and_degenerate_cases(ctx, golden_dir):
+    """:225-253 (rows not grouped by class -> reshuffled on the device), :72-113 (a class with no rows), :168-186 (one class)."""
+    A = np.loadtxt(os.path.join(golden_dir, "aMatShuffled.csv"), delimiter=",")
+    B = np.loadtxt(os.path.join(golden_dir, "bMatShuffled.csv"), delimiter=",")
+    _bwls_compare(ctx, A, B, 4, 10)
+    stats = ctx.last_fit_stats()
+    assert stats["solver"] == "blockwls" and stats["reshuffled"] == 1
+    A0 = np.loadtxt(os.path.join(golden_dir, "aMat.csv"), delimiter=",")
+    B0 = np.loadtxt(os.path.join(golden_dir, "bMat.csv"), delimiter=",")
+    keep = np.r_[0:5, 10:15]                                   # class 1 has no rows
+    m, Wg, Wr, fb = _bwls_compare(ctx, A0[keep], B0[keep], 4, 10)
+    assert np.all(Wg[:, 1] == 0.0)
+    A1 = np.loadtxt(os.path.join(golden_dir, "aMat-1class.csv"), delimiter=",")
+    B1 = np.loadtxt(os.path.join(golden_dir, "bMat-1class.csv"), delimiter=",", ndmin=2)
+    _bwls_compare(ctx, A1, B1, 4, 10)
+
+
+def test_bwls_larger_problem_cosine_features(ctx):
+    """Class-imbalanced synthetic problem, features generated on the fly, 2 passes."""
+    rng = np.random.default_rng(9)
+    n, d_in, n_out, k = 3000, 30, 128, 5
+    X = rng.standard_normal((n, d_in))
+    cls = np.sort(rng.choice(k, n, p=[0.4, 0.25, 0.2, 0.1, 0.05]))
+    params = [ko.cosine_random_features_params(d_in, n_out, 0.25, rng) for _ in range(2)]
+    x = ctx.matrix(X.astype(np.float32)); y = ctx.labels_from_classes(cls, k)
+    rfs = [ks.CosineRandomFeatures(ctx, W, b) for W, b in params]
+    feats = ks.Pipeline.gather(rfs).andThen(ks.VectorCombiner())(x)
+    model = ks.BlockWeightedLeastSquaresEstimator(n_out, 2, 0.01, 0.25).fit(feats, y)
+    Xd = X.astype(np.float32).astype(np.float64)
+    F = np.concatenate([ko.cosine_random_features(Xd, W, b) for W, b in params], 1)
+    xs, fb = ko.bwls_fit(F, ko.class_label_indicators(cls, k), n_out, 2, 0.01, 0.25)
+    Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
+    assert np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr) < 2e-2    # lambda = 0.01 on n_c as small as 150: conditioning ~1e3
+    pred = model(feats).to_numpy()
+    ref = F @ Wr + fb
+    assert np.abs(pred - ref).max() < 2e-2
