@@ -335,6 +335,7 @@ void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* s
   k.p.K = static_cast<int>(src.d_in);
   k.p.flags = round_out ? 0 : KM_FLAG_NO_ROUND;
   k.epi = EPI_COS;
+  k.pair = 0;
   k.num_sms = c.num_sms;
   KS_CUDA(launch_kmajor(k, st));
   c.launches += 1;
@@ -400,8 +401,9 @@ void launch_update(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, 
   if (rows <= 0 || k <= 0 || b <= 0) return;
   if (!st) st = c.st;
   KmLaunch u;
+  u.pair = c.gram_pair;
   tmap_or_throw(&u.tmA, slab, rows, b, lds, 128);
-  tmap_or_throw(&u.tmB, bop, k, b, ldb, 256);
+  tmap_or_throw(&u.tmB, bop, k, b, ldb, u.pair ? 128 : 256);
   tmap_or_throw(&u.tmOut, out, rows, k, ldo, 32);  // k valid columns: the store never touches columns >= k
   u.p.vec0 = cbias;
   u.p.vec1 = nullptr;

@@ -41,6 +41,7 @@ struct KmLaunch {
   KmParams p;
   int epi;
   int num_sms;
+  int pair;  // 1: CTA-pair kernel (EPI_UPDATE / EPI_APPLY; tmB box is {32, 128}), 0: single-CTA persistent kernel
 };
 
 int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool atom32 = false);

@@ -519,6 +519,156 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 }
 
 // =====================================================================================
+// K-major GEMM on CTA pairs (cta_group::2) for the two K = blockSize GEMMs (residual update, model apply):
+// one pair computes a 256 x 512 output tile (two M=256, N=256 MMAs per K step); each CTA stages its own 128 rows of A
+// and its 128-row half of each 256-row B tile.  Same shared-memory argument as gram2_tn_kernel: 8 KB instead of 12 KB of
+// operand reads per MMA.  All 512 TMEM columns hold the accumulator, so the epilogue is not overlapped with the next
+// tile's main loop; with K = 4096 it is ~5 % of the tile time.
+// =====================================================================================
+template <int STAGES>
+struct Km2Cfg {
+  static constexpr int PM = 256, PN = 512, BK = 32;
+  static constexpr int A_BYTES = 128 * BK * 4;
+  static constexpr int BH_BYTES = 128 * BK * 4;
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * BH_BYTES;
+  static constexpr int STAGING_BYTES = 4 * 4096;
+  static constexpr int VEC_BYTES = 4 * 512 * 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + VEC_BYTES + 1024 + 256;
+};
+
+template <int EPI, int STAGES>
+__global__ void __launch_bounds__(kGramThreads, 1)
+gemm2_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmOut, KmParams p) {
+  using Cfg = Km2Cfg<STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
+  float* vec_smem = reinterpret_cast<float*>(staging + Cfg::STAGING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES + Cfg::VEC_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_tiles = (p.N + Cfg::PN - 1) / Cfg::PN;
+  const int t = blockIdx.x >> 1;
+  const int m0 = (t / n_tiles) * Cfg::PM + static_cast<int>(rank) * 128;
+  const int n0 = (t % n_tiles) * Cfg::PN;
+  const int ksteps = (p.K + Cfg::BK - 1) / Cfg::BK;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+  }
+  if (warp == 1) {
+    if (elect_one()) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc_pair(tmem_slot, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (ks / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * Cfg::STAGE_BYTES);
+        uint8_t* sA = smem + s * Cfg::STAGE_BYTES;
+        tma_load_2d_pair(sA, &tmA, &full_bar[s], ks * Cfg::BK, m0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_2d_pair(sA + Cfg::A_BYTES + h * Cfg::BH_BYTES, &tmB, &full_bar[s], ks * Cfg::BK,
+                           n0 + h * 256 + static_cast<int>(rank) * 128);
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0 && elect_one()) {
+      constexpr uint32_t idesc = make_idesc_tf32(256, 256, 0, 0);
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int s = ks % STAGES;
+        const uint32_t ph = (ks / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sA = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t sB = sA + Cfg::A_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < Cfg::BK / 8; ++kk) {
+          const uint64_t ad = make_smem_desc_sw128(sA + kk * 32, 16, 1024);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t bd = make_smem_desc_sw128(sB + h * Cfg::BH_BYTES + kk * 32, 16, 1024);
+            umma_tf32_pair(tmem_base + h * 256, ad, bd, idesc, (ks | kk) != 0);
+          }
+        }
+        umma_commit_pair(&empty_bar[s]);
+      }
+      umma_commit_pair(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    float* v0s = vec_smem + (warp - 2) * 512;
+    uint8_t* buf = staging + (warp - 2) * 4096;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int n = n0 + j * 32 + lane;
+      v0s[j * 32 + lane] = (p.vec0 && n < p.N) ? __ldg(p.vec0 + n) : 0.f;
+    }
+    __syncwarp();
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < Cfg::PN; c0 += 32) {
+      if (n0 + c0 >= p.N) break;  // warp-uniform
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, v);
+      tmem_ld_wait();
+      float o[32];
+      if (EPI == EPI_UPDATE) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] - __uint_as_float(v[i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] + __uint_as_float(v[i]);
+      }
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+      stage_row_sw128(buf, lane, o);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (p.flags & KM_FLAG_REDUCE) tma_reduce_add_2d(&tmOut, buf, n0 + c0, m0 + q * 32);
+        else tma_store_2d(&tmOut, buf, n0 + c0, m0 + q * 32);
+        bulk_commit();
+      }
+    }
+    if (lane == 0) bulk_wait0();
+    tc_fence_before();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+// =====================================================================================
 // Host-side launchers
 // =====================================================================================
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -625,7 +775,38 @@ static cudaError_t launch_km_t(const KmLaunch& k, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+template <int EPI, int STAGES>
+static cudaError_t launch_km2_t(const KmLaunch& k, cudaStream_t st) {
+  using Cfg = Km2Cfg<STAGES>;
+  auto kern = gemm2_kmajor_kernel<EPI, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const long long m_tiles = (k.p.M + Cfg::PM - 1) / Cfg::PM;
+  const long long n_tiles = (k.p.N + Cfg::PN - 1) / Cfg::PN;
+  const long long total = m_tiles * n_tiles;
+  if (total == 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(2 * total));
+  cfg.blockDim = dim3(kGramThreads);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, k.tmA, k.tmB, k.tmOut, k.p);
+}
+
 cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st) {
+  if (k.pair && k.epi == EPI_UPDATE) return launch_km2_t<EPI_UPDATE, 4>(k, st);
+  if (k.pair && k.epi == EPI_APPLY) return launch_km2_t<EPI_APPLY, 4>(k, st);
   switch (k.epi) {
     case EPI_COS: return launch_km_t<EPI_COS, 256, 3>(k, st);
     case EPI_UPDATE: return launch_km_t<EPI_UPDATE, 256, 3>(k, st);
