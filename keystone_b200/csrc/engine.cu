@@ -10,6 +10,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <chrono>
 #include <mutex>
 #include <sstream>
 
@@ -201,6 +202,7 @@ void Ctx::ensure_solver() {
   if (solver) return;
   SolverApi& api = solver_api();
   if (api.Create(&solver) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnCreate failed"};
+  if (api.Create(&solver2) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnCreate failed"};
   if (api.SetStream(solver, st) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
   dev_info.alloc(sizeof(int) * kMaxInfo);
   KS_CUDA(cudaMemsetAsync(dev_info.p, 0, sizeof(int) * kMaxInfo, st));
@@ -208,17 +210,18 @@ void Ctx::ensure_solver() {
 void Ctx::potrf(double* H, int n, int info_slot, cudaStream_t s) {
   ensure_solver();
   SolverApi& api = solver_api();
-  if (api.SetStream(solver, s) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
+  if (api.SetStream(solver2, s) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
   int lwork = 0;
-  if (api.DpotrfBufferSize(solver, CUBLAS_FILL_MODE_LOWER, n, H, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
+  if (api.DpotrfBufferSize(solver2, CUBLAS_FILL_MODE_LOWER, n, H, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
     throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrf_bufferSize failed"};
   if (lwork > solver_lwork) {
     KS_CUDA(cudaStreamSynchronize(st));
     KS_CUDA(cudaStreamSynchronize(st2));
+    KS_CUDA(cudaStreamSynchronize(st3));
     solver_work.alloc(sizeof(double) * static_cast<size_t>(lwork));
     solver_lwork = lwork;
   }
-  if (api.Dpotrf(solver, CUBLAS_FILL_MODE_LOWER, n, H, n, solver_work.as<double>(), solver_lwork,
+  if (api.Dpotrf(solver2, CUBLAS_FILL_MODE_LOWER, n, H, n, solver_work.as<double>(), solver_lwork,
                  dev_info.as<int>() + (info_slot % kMaxInfo)) != CUSOLVER_STATUS_SUCCESS)
     throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrf failed"};
   launches += 1;
@@ -247,6 +250,7 @@ void Ctx::check_infos(int used_slots) {
 void Ctx::check_async(const char* what) {
   cudaError_t e = cudaStreamSynchronize(st);
   if (e == cudaSuccess && st2) e = cudaStreamSynchronize(st2);
+  if (e == cudaSuccess && st3) e = cudaStreamSynchronize(st3);
   if (e != cudaSuccess) {
     std::string extra;
     if (e == cudaErrorLaunchFailure || e == cudaErrorIllegalInstruction) extra = " (kernel trapped: barrier wait budget exceeded or illegal instruction)";
@@ -443,13 +447,14 @@ __global__ void sumsq_f64_kernel(const double* p, int64_t n, double* out) {
 }
 
 // ------------------------------------------------------------------------------------ BlockLS fit
-// Two-stream software pipeline.  Per block j the work splits into a part that does NOT depend on the residual
-//   prep(j)  [stream st2]: shift estimate, slab S_j, G_j = S_j^T S_j, all-reduce, H_j = G_j - N d d^T + lambda I, Cholesky
+// Three-stream software pipeline.  Per block j the work splits into two parts that do NOT depend on the residual
+//   prep(j)   [stream st2]: shift estimate, slab S_j, G_j = S_j^T S_j, all-reduce
+//   factor(j) [stream st3]: H_j = G_j - N d d^T + lambda I, Cholesky (about 100 small, latency-bound cuSOLVER kernels)
 // and the residual-dependent chain
-//   main(j)  [stream st ]: Rr = tf32(R), C_j = S_j^T Rr, all-reduce, triangular solves, W_j += dW, R -= S_j dW.
-// prep(j+1) is enqueued before main(j), so the latency-bound Cholesky (about 100 small cuSOLVER kernels per block) and
-// the next block's featurization overlap with the tensor-core work of the current block; slabs / G / H are double
-// buffered and cross-stream dependencies are CUDA events.  No host synchronisation inside the loop.
+//   main(j)   [stream st ]: Rr = tf32(R), C_j = S_j^T Rr, all-reduce, triangular solves, W_j += dW, R -= S_j dW.
+// prep / factor run up to two blocks ahead of main (three slab / G / H buffers); cross-stream dependencies are CUDA events
+// and there is no host synchronisation inside the loop.  With the rows sharded over several GPUs the per-block tensor
+// work shrinks but the Cholesky does not: keeping it off both other chains is what keeps the strong scaling going.
 static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, int64_t nf_opt) {
   if (bs <= 0 || num_iter < 1) throw KsError{KS_ERR_INVALID, "blockSize must be > 0 and numIter >= 1"};
   if (Y.rows != src.n_rows) throw KsError{KS_ERR_INVALID, "features and labels have different row counts"};
@@ -462,11 +467,14 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   const int bmax = static_cast<int>(std::min<int64_t>(bs, D));
   const int64_t lds = round_up(bmax, 32);
   const int64_t kpad = round_up(k, 32);
-  cudaStream_t S1 = c.st, S2 = c.st2;
+  cudaStream_t S1 = c.st, S2 = c.st2, S3 = c.st3;
+  constexpr int NBUF = 3;
+  const auto host_t0 = std::chrono::steady_clock::now();
   c.spans.clear();
   const int64_t launches0 = c.launches;
   cudaEvent_t ev0 = c.get_event(), ev1 = c.get_event(), ev_init = c.get_event();
   KS_CUDA(cudaStreamSynchronize(S2));
+  KS_CUDA(cudaStreamSynchronize(S3));
   KS_CUDA(cudaEventRecord(ev0, S1));
 
   // ---- label mean (StandardScaler on labels, BlockLinearMapper.scala:215) + global row count
@@ -497,7 +505,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   c.launches += 1;
 
   // ---- residual R = Y - mean (fp32 master) and Rr = its tf32-rounded copy (the Gram kernel's B operand)
-  DevBuf r_f32, r_tf32, slab[2], gbuf[2], Hbuf[2], ssum[2], cm, rhs, rsum, bop, cbias, samp, fsum;
+  DevBuf r_f32, r_tf32, slab[NBUF], gbuf[NBUF], Hbuf[NBUF], ssum[NBUF], cm, rhs, rsum, bop, cbias, samp, fsum;
   r_f32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * kpad));
   r_tf32.alloc(r_f32.bytes);
   launch_init_residual(Y.d, Y.ld, model->intercept.as<double>(), r_f32.as<float>(), kpad, n_loc, k, S1);
@@ -507,7 +515,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   const int ldg = static_cast<int>(lds), ldc = static_cast<int>(kpad);
   const size_t g_elems = static_cast<size_t>(bmax) * ldg, c_elems = static_cast<size_t>(bmax) * ldc;
   const bool cache_factors = num_iter > 1;
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < NBUF; ++i) {
     slab[i].alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));
     gbuf[i].alloc(sizeof(float) * g_elems);
     ssum[i].alloc(sizeof(float) * lds);
@@ -539,8 +547,9 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   for (int it = 0; it < num_iter; ++it)
     for (int j = 0; j < nb; ++j) steps.push_back({it, j});
   const int T = static_cast<int>(steps.size());
-  std::vector<cudaEvent_t> ev_slab(T), ev_fact(T), ev_upd(T);
+  std::vector<cudaEvent_t> ev_slab(T), ev_fact(T), ev_upd(T), ev_g(T);
   for (int t = 0; t < T; ++t) {
+    ev_g[t] = c.get_event();
     ev_slab[t] = c.get_event();
     ev_fact[t] = c.get_event();
     ev_upd[t] = c.get_event();
@@ -555,10 +564,10 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
 
   // ---------------- prep(t): everything that does not depend on the residual, on stream S2
   auto prep = [&](int t) {
-    const int it = steps[t].it, j = steps[t].j, buf = t & 1;
+    const int it = steps[t].it, j = steps[t].j, buf = t % NBUF;
     int64_t c0;
     const int b = block_cols(j, &c0);
-    if (t >= 2) KS_CUDA(cudaStreamWaitEvent(S2, ev_upd[t - 2], 0));  // slab / G / H buffers of step t-2 are free
+    if (t >= NBUF) KS_CUDA(cudaStreamWaitEvent(S2, ev_upd[t - NBUF], 0));  // slab / G / H buffers of step t-NBUF are free
     c.span_begin(PH_FEATURIZE, S2);
     if (it == 0) {
       shifts[j] = std::make_unique<DevBuf>();
@@ -603,12 +612,15 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       c.allreduce_f32(gbuf[buf].as<float>(), g_elems, true);
       c.allreduce_f32(ssum[buf].as<float>(), static_cast<size_t>(b), true);
       c.span_end(S2);
-      c.span_begin(PH_SOLVE, S2);
+      KS_CUDA(cudaEventRecord(ev_g[t], S2));
+      // ---- factor(t) on S3
+      KS_CUDA(cudaStreamWaitEvent(S3, ev_g[t], 0));
+      c.span_begin(PH_SOLVE, S3);
       deltas[j] = std::make_unique<DevBuf>();
       deltas[j]->alloc(sizeof(double) * b);
       auto mean = std::make_unique<DevBuf>();
       mean->alloc(sizeof(double) * b);
-      launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), mean->as<double>(), b, S2);
+      launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), mean->as<double>(), b, S3);
       double* Hj;
       if (cache_factors) {
         factors[j] = std::make_unique<DevBuf>();
@@ -617,24 +629,26 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       } else {
         Hj = Hbuf[buf].as<double>();
       }
-      launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S2);
+      launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S3);
       c.launches += 2;
-      c.potrf(Hj, b, info_slot++, S2);
+      c.potrf(Hj, b, info_slot++, S3);
       auto W = std::make_unique<DevBuf>();
       W->alloc(sizeof(double) * static_cast<size_t>(b) * k);
-      KS_CUDA(cudaMemsetAsync(W->p, 0, W->bytes, S2));
+      KS_CUDA(cudaMemsetAsync(W->p, 0, W->bytes, S3));
       model->brows.push_back(b);
       model->W.push_back(std::move(W));
       model->mean.push_back(std::move(mean));
       flops += static_cast<double>(b) * b * b / 3.0;
-      c.span_end(S2);
+      c.span_end(S3);
+      KS_CUDA(cudaEventRecord(ev_fact[t], S3));
+    } else {
+      KS_CUDA(cudaEventRecord(ev_fact[t], S2));
     }
-    KS_CUDA(cudaEventRecord(ev_fact[t], S2));
   };
 
   // ---------------- main(t): the residual-dependent chain, on stream S1
   auto mainstep = [&](int t) {
-    const int it = steps[t].it, j = steps[t].j, buf = t & 1;
+    const int it = steps[t].it, j = steps[t].j, buf = t % NBUF;
     int64_t c0;
     const int b = block_cols(j, &c0);
     c.span_begin(PH_OTHER);
@@ -673,9 +687,9 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     KS_CUDA(cudaEventRecord(ev_upd[t], S1));
   };
 
-  prep(0);
+  for (int t = 0; t < std::min(T, NBUF - 1); ++t) prep(t);
   for (int t = 0; t < T; ++t) {
-    if (t + 1 < T) prep(t + 1);
+    if (t + NBUF - 1 < T) prep(t + NBUF - 1);
     mainstep(t);
   }
   KS_CUDA(cudaStreamWaitEvent(S1, ev_fact[T - 1], 0));
@@ -688,6 +702,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   c.event_pool.push_back(ev1);
   c.event_pool.push_back(ev_init);
   for (int t = 0; t < T; ++t) {
+    c.event_pool.push_back(ev_g[t]);
     c.event_pool.push_back(ev_slab[t]);
     c.event_pool.push_back(ev_fact[t]);
     c.event_pool.push_back(ev_upd[t]);
@@ -700,7 +715,8 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
      << ",\"world\":" << c.world << ",\"total_ms\":" << total_ms << ",\"featurize_ms\":" << ms[PH_FEATURIZE]
      << ",\"gram_ms\":" << ms[PH_GRAM] << ",\"allreduce_ms\":" << ms[PH_ALLREDUCE] << ",\"solve_ms\":" << ms[PH_SOLVE]
      << ",\"update_ms\":" << ms[PH_UPDATE] << ",\"other_ms\":" << ms[PH_OTHER] << ",\"local_flops\":" << flops
-     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"tf32x1\",\"streams\":2}";
+     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"tf32x1\",\"streams\":3,\"host_ms\":"
+     << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count() << "}";
   c.stats_json = js.str();
   return c.add(std::move(model));
 }
@@ -838,6 +854,7 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
     }
     if (const char* e = getenv("KS_GRAM_PAIR")) c->gram_pair = atoi(e) != 0;
     KS_CUDA(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
+    KS_CUDA(cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking));
     if (world_size > 1) {
       if (!nccl_id) throw KsError{KS_ERR_INVALID, "nccl_id required for world_size > 1"};
       ncclUniqueId id;
@@ -872,18 +889,21 @@ KS_API int32_t ks_ctx_destroy(int64_t ctx) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->st);
   if (c->st2) cudaStreamSynchronize(c->st2);
+  if (c->st3) cudaStreamSynchronize(c->st3);
   c->matrices.clear();
   c->rfs.clear();
   c->models.clear();
   c->tile_cache.clear();
   for (auto e : c->event_pool) cudaEventDestroy(e);
   if (c->solver) solver_api().Destroy(c->solver);
+  if (c->solver2) solver_api().Destroy(c->solver2);
   if (c->comm2 && c->comm2 != c->comm) nccl_api().CommDestroy(c->comm2);
   if (c->comm) nccl_api().CommDestroy(c->comm);
   c->solver_work.release();
   c->dev_info.release();
   cudaStreamDestroy(c->st);
   if (c->st2) cudaStreamDestroy(c->st2);
+  if (c->st3) cudaStreamDestroy(c->st3);
   c.reset();
   bool last;
   {

@@ -108,10 +108,12 @@ struct Ctx {
   int device = 0, rank = 0, world = 1;
   int num_sms = 148;
   cudaStream_t st = nullptr;   // main stream: residual-dependent chain (A^T R, triangular solves, update)
-  cudaStream_t st2 = nullptr;  // prep stream: featurize + Gram + Cholesky of the NEXT block (independent of the residual)
+  cudaStream_t st2 = nullptr;  // prep stream: featurize + Gram of the blocks AHEAD (independent of the residual)
+  cudaStream_t st3 = nullptr;  // factor stream: fp64 assembly + Cholesky of the blocks ahead
   ncclComm_t comm = nullptr;   // collectives issued on st
   ncclComm_t comm2 = nullptr;  // collectives issued on st2 (split of comm; falls back to comm)
-  cusolverDnHandle_t solver = nullptr;
+  cusolverDnHandle_t solver = nullptr;   // triangular solves (main stream)
+  cusolverDnHandle_t solver2 = nullptr;  // factorizations (factor stream): a handle's internal cuBLAS workspace is per stream
   DevBuf solver_work;
   int solver_lwork = 0;
   DevBuf dev_info;  // int[kMaxInfo]
