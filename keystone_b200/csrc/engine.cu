@@ -44,6 +44,27 @@ SolverApi& solver_api() {
       load_sym(api.lib, "cusolverDnDpotrf_bufferSize", api.DpotrfBufferSize, "libcusolver");
       load_sym(api.lib, "cusolverDnDpotrf", api.Dpotrf, "libcusolver");
       load_sym(api.lib, "cusolverDnDpotrs", api.Dpotrs, "libcusolver");
+      load_sym(api.lib, "cusolverDnDpotri_bufferSize", api.DpotriBufferSize, "libcusolver");
+      load_sym(api.lib, "cusolverDnDpotri", api.Dpotri, "libcusolver");
+    } catch (const KsError& e) {
+      fail = e.msg;
+    }
+  });
+  if (!fail.empty()) throw KsError{KS_ERR_SOLVER, fail};
+  return api;
+}
+BlasApi& blas_api() {
+  static BlasApi api;
+  static std::once_flag once;
+  static std::string fail;
+  std::call_once(once, [] {
+    try {
+      api.lib = open_first({"libcublas.so.12", "libcublas.so", "/usr/local/cuda/lib64/libcublas.so.12"});
+      if (!api.lib) throw KsError{KS_ERR_SOLVER, std::string("cannot load libcublas: ") + dlerror()};
+      load_sym(api.lib, "cublasCreate_v2", api.Create, "libcublas");
+      load_sym(api.lib, "cublasDestroy_v2", api.Destroy, "libcublas");
+      load_sym(api.lib, "cublasSetStream_v2", api.SetStream, "libcublas");
+      load_sym(api.lib, "cublasDsymm_v2", api.Dsymm, "libcublas");
     } catch (const KsError& e) {
       fail = e.msg;
     }
@@ -63,6 +84,7 @@ NcclApi& nccl_api() {
       load_sym(api.lib, "ncclCommInitRank", api.CommInitRank, "libnccl");
       load_sym(api.lib, "ncclCommDestroy", api.CommDestroy, "libnccl");
       load_sym(api.lib, "ncclAllReduce", api.AllReduce, "libnccl");
+      load_sym(api.lib, "ncclBroadcast", api.Broadcast, "libnccl");
       load_sym(api.lib, "ncclGetErrorString", api.GetErrorString, "libnccl");
       api.CommSplit = reinterpret_cast<decltype(api.CommSplit)>(dlsym(api.lib, "ncclCommSplit"));
     } catch (const KsError& e) {
@@ -170,7 +192,7 @@ cudaEvent_t Ctx::get_event() {
 }
 void Ctx::span_begin(int phase, cudaStream_t s) {
   if (!timing) return;
-  Span sp{phase, get_event(), get_event()};
+  Span sp{phase, get_event(), get_event(), s == st2 ? 2 : (s == st3 ? 3 : 1)};
   KS_CUDA(cudaEventRecord(sp.a, s ? s : st));
   spans.push_back(sp);
 }
@@ -180,14 +202,25 @@ void Ctx::span_end(cudaStream_t s) {
 }
 void Ctx::collect_spans(double out_ms[PH_COUNT]) {
   for (int i = 0; i < PH_COUNT; ++i) out_ms[i] = 0;
+  std::ostringstream tl;
+  tl << "[";
+  bool first = true;
   for (auto& s : spans) {
     float ms = 0;
     cudaEventSynchronize(s.b);
     cudaEventElapsedTime(&ms, s.a, s.b);
     out_ms[s.phase] += ms;
+    if (timeline_origin) {
+      float t0 = 0;
+      cudaEventElapsedTime(&t0, timeline_origin, s.a);
+      tl << (first ? "" : ",") << "[" << s.phase << "," << s.stream << "," << t0 << "," << (t0 + ms) << "]";
+      first = false;
+    }
     event_pool.push_back(s.a);
     event_pool.push_back(s.b);
   }
+  tl << "]";
+  timeline_json = timeline_origin ? tl.str() : "[]";
   spans.clear();
 }
 void Ctx::allreduce_f32(float* p, size_t n, bool prep) {
@@ -204,13 +237,17 @@ void Ctx::ensure_solver() {
   if (api.Create(&solver) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnCreate failed"};
   if (api.Create(&solver2) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnCreate failed"};
   if (api.SetStream(solver, st) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
+  solver_stream = st;
   dev_info.alloc(sizeof(int) * kMaxInfo);
   KS_CUDA(cudaMemsetAsync(dev_info.p, 0, sizeof(int) * kMaxInfo, st));
 }
 void Ctx::potrf(double* H, int n, int info_slot, cudaStream_t s) {
   ensure_solver();
   SolverApi& api = solver_api();
-  if (api.SetStream(solver2, s) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
+  if (s != solver2_stream) {
+    if (api.SetStream(solver2, s) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
+    solver2_stream = s;
+  }
   int lwork = 0;
   if (api.DpotrfBufferSize(solver2, CUBLAS_FILL_MODE_LOWER, n, H, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
     throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrf_bufferSize failed"};
@@ -229,10 +266,46 @@ void Ctx::potrf(double* H, int n, int info_slot, cudaStream_t s) {
 void Ctx::potrs(const double* H, int n, double* B, int nrhs, int info_slot, cudaStream_t s) {
   ensure_solver();
   if (nrhs == 0 || n == 0) return;
-  if (solver_api().SetStream(solver, s) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
+  if (s != solver_stream) {
+    if (solver_api().SetStream(solver, s) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
+    solver_stream = s;
+  }
   if (solver_api().Dpotrs(solver, CUBLAS_FILL_MODE_LOWER, n, nrhs, H, n, B, n, dev_info.as<int>() + (info_slot % kMaxInfo)) !=
       CUSOLVER_STATUS_SUCCESS)
     throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrs failed"};
+  launches += 1;
+}
+void Ctx::potri(double* H, int n, int info_slot, cudaStream_t s) {
+  ensure_solver();
+  SolverApi& api = solver_api();
+  if (s != solver2_stream) {
+    if (api.SetStream(solver2, s) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
+    solver2_stream = s;
+  }
+  int lwork = 0;
+  if (api.DpotriBufferSize(solver2, CUBLAS_FILL_MODE_LOWER, n, H, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
+    throw KsError{KS_ERR_SOLVER, "cusolverDnDpotri_bufferSize failed"};
+  if (lwork > solver_lwork) {
+    KS_CUDA(cudaStreamSynchronize(st));
+    KS_CUDA(cudaStreamSynchronize(st2));
+    KS_CUDA(cudaStreamSynchronize(st3));
+    solver_work.alloc(sizeof(double) * static_cast<size_t>(lwork));
+    solver_lwork = lwork;
+  }
+  if (api.Dpotri(solver2, CUBLAS_FILL_MODE_LOWER, n, H, n, solver_work.as<double>(), solver_lwork,
+                 dev_info.as<int>() + (info_slot % kMaxInfo)) != CUSOLVER_STATUS_SUCCESS)
+    throw KsError{KS_ERR_SOLVER, "cusolverDnDpotri failed"};
+  launches += 1;
+}
+void Ctx::symm_solve(const double* Hinv, int n, const double* B, int nrhs, double* out, cudaStream_t s) {
+  if (n == 0 || nrhs == 0) return;
+  BlasApi& api = blas_api();
+  if (!blas && api.Create(&blas) != CUBLAS_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cublasCreate failed"};
+  if (api.SetStream(blas, s) != CUBLAS_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cublasSetStream failed"};
+  const double one = 1.0, zero = 0.0;
+  if (api.Dsymm(blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, n, nrhs, &one, Hinv, n, B, n, &zero, out, n) !=
+      CUBLAS_STATUS_SUCCESS)
+    throw KsError{KS_ERR_SOLVER, "cublasDsymm failed"};
   launches += 1;
 }
 void Ctx::check_infos(int used_slots) {
@@ -251,6 +324,7 @@ void Ctx::check_async(const char* what) {
   cudaError_t e = cudaStreamSynchronize(st);
   if (e == cudaSuccess && st2) e = cudaStreamSynchronize(st2);
   if (e == cudaSuccess && st3) e = cudaStreamSynchronize(st3);
+  if (e == cudaSuccess && st4) e = cudaStreamSynchronize(st4);
   if (e != cudaSuccess) {
     std::string extra;
     if (e == cudaErrorLaunchFailure || e == cudaErrorIllegalInstruction) extra = " (kernel trapped: barrier wait budget exceeded or illegal instruction)";
@@ -340,7 +414,9 @@ void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* s
   k.p.flags = round_out ? 0 : KM_FLAG_NO_ROUND;
   k.epi = EPI_COS;
   k.pair = 0;
-  k.num_sms = c.num_sms;
+  // the projection kernel is persistent (one CTA per SM for its whole duration); on the look-ahead stream leave a few SMs
+  // free so that the critical chain's small kernels (NCCL all-reduce, triangular solves) can always be scheduled
+  k.num_sms = (st == c.st2) ? std::max(1, c.num_sms - c.reserve_sms) : c.num_sms;
   KS_CUDA(launch_kmajor(k, st));
   c.launches += 1;
 }
@@ -467,14 +543,14 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   const int bmax = static_cast<int>(std::min<int64_t>(bs, D));
   const int64_t lds = round_up(bmax, 32);
   const int64_t kpad = round_up(k, 32);
-  cudaStream_t S1 = c.st, S2 = c.st2, S3 = c.st3;
-  constexpr int NBUF = 3;
+  cudaStream_t S1 = c.st, S2 = c.st2, S3 = c.st3, S4 = c.st4;
   const auto host_t0 = std::chrono::steady_clock::now();
   c.spans.clear();
   const int64_t launches0 = c.launches;
   cudaEvent_t ev0 = c.get_event(), ev1 = c.get_event(), ev_init = c.get_event();
   KS_CUDA(cudaStreamSynchronize(S2));
   KS_CUDA(cudaStreamSynchronize(S3));
+  KS_CUDA(cudaStreamSynchronize(S4));
   KS_CUDA(cudaEventRecord(ev0, S1));
 
   // ---- label mean (StandardScaler on labels, BlockLinearMapper.scala:215) + global row count
@@ -505,7 +581,12 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   c.launches += 1;
 
   // ---- residual R = Y - mean (fp32 master) and Rr = its tf32-rounded copy (the Gram kernel's B operand)
-  DevBuf r_f32, r_tf32, slab[NBUF], gbuf[NBUF], Hbuf[NBUF], ssum[NBUF], cm, rhs, rsum, bop, cbias, samp, fsum;
+  // look-ahead depth of prep / factor over main: 2 blocks normally; with the owner-computes-inverse scheme the factor chain
+  // of a block is ~30 ms on its owner, so `world` of them must be in flight at once (N_loc shrinks with world, so do the slabs)
+  const bool use_inv = c.world >= c.inv_min_world;
+  const int NBUF = use_inv ? c.world + 2 : 3;
+  DevBuf r_f32, r_tf32, cm, rhs, dwb, rsum, bop, cbias, samp, fsum;
+  std::unique_ptr<DevBuf[]> slab(new DevBuf[NBUF]), gbuf(new DevBuf[NBUF]), Hbuf(new DevBuf[NBUF]), ssum(new DevBuf[NBUF]);
   r_f32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * kpad));
   r_tf32.alloc(r_f32.bytes);
   launch_init_residual(Y.d, Y.ld, model->intercept.as<double>(), r_f32.as<float>(), kpad, n_loc, k, S1);
@@ -523,6 +604,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   }
   cm.alloc(sizeof(float) * c_elems);
   rhs.alloc(sizeof(double) * static_cast<size_t>(bmax) * k);
+  dwb.alloc(rhs.bytes);
   rsum.alloc(sizeof(double) * kpad);
   bop.alloc(sizeof(float) * static_cast<size_t>(kpad) * lds);
   cbias.alloc(sizeof(float) * kpad);
@@ -547,9 +629,12 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   for (int it = 0; it < num_iter; ++it)
     for (int j = 0; j < nb; ++j) steps.push_back({it, j});
   const int T = static_cast<int>(steps.size());
-  std::vector<cudaEvent_t> ev_slab(T), ev_fact(T), ev_upd(T), ev_g(T);
+  std::vector<cudaEvent_t> ev_slab(T), ev_fact(T), ev_upd(T), ev_g(T), ev_inv(T), ev_solved(T);
+  const bool exclusive_solve = c.world >= c.exclusive_solve_min_world;
   for (int t = 0; t < T; ++t) {
+    ev_solved[t] = c.get_event();
     ev_g[t] = c.get_event();
+    ev_inv[t] = c.get_event();
     ev_slab[t] = c.get_event();
     ev_fact[t] = c.get_event();
     ev_upd[t] = c.get_event();
@@ -601,7 +686,16 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     if (!src.F) flops += 2.0 * static_cast<double>(n_loc) * src.d_in * b;
     c.span_end(S2);
     KS_CUDA(cudaEventRecord(ev_slab[t], S2));
+  };
+  // ---------------- prepB(t): Gram + factorization of block t (enqueued after main(t-1), see the loop below)
+  auto prepB = [&](int t) {
+    const int it = steps[t].it, j = steps[t].j, buf = t % NBUF;
+    int64_t c0;
+    const int b = block_cols(j, &c0);
     if (it == 0) {
+      // strong-scaling regime: start this block's Gram only once the critical chain has finished the previous block's
+      // triangular solves -- ~100 small latency-bound kernels that take 2x longer when they share the SMs with it
+      if (exclusive_solve && t >= 1) KS_CUDA(cudaStreamWaitEvent(S2, ev_solved[t - 1], 0));
       c.span_begin(PH_GRAM, S2);  // G part of the Gram
       KS_CUDA(cudaMemsetAsync(gbuf[buf].p, 0, gbuf[buf].bytes, S2));
       launch_gram_block(c, slab[buf].as<float>(), lds, n_loc, b, nullptr, 0, 0, gbuf[buf].as<float>(), ldg, nullptr, 0, true,
@@ -613,14 +707,11 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       c.allreduce_f32(ssum[buf].as<float>(), static_cast<size_t>(b), true);
       c.span_end(S2);
       KS_CUDA(cudaEventRecord(ev_g[t], S2));
-      // ---- factor(t) on S3
-      KS_CUDA(cudaStreamWaitEvent(S3, ev_g[t], 0));
-      c.span_begin(PH_SOLVE, S3);
+      // ---- factor(t)
       deltas[j] = std::make_unique<DevBuf>();
       deltas[j]->alloc(sizeof(double) * b);
       auto mean = std::make_unique<DevBuf>();
       mean->alloc(sizeof(double) * b);
-      launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), mean->as<double>(), b, S3);
       double* Hj;
       if (cache_factors) {
         factors[j] = std::make_unique<DevBuf>();
@@ -629,18 +720,49 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       } else {
         Hj = Hbuf[buf].as<double>();
       }
-      launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S3);
-      c.launches += 2;
-      c.potrf(Hj, b, info_slot++, S3);
       auto W = std::make_unique<DevBuf>();
       W->alloc(sizeof(double) * static_cast<size_t>(b) * k);
-      KS_CUDA(cudaMemsetAsync(W->p, 0, W->bytes, S3));
+      if (use_inv) {
+        // The latency-bound Cholesky + explicit inverse of block j run on ONE rank (j % world) on its factor stream S3; the
+        // inverse is broadcast on a separate stream S4 (a rank waiting for somebody else's inverse must not stall its own
+        // factor work).  The factor chains of `world` consecutive blocks thus proceed in parallel on different GPUs and the
+        // critical chain's solve becomes a single fp64 GEMM on every rank.
+        const int owner = j % c.world;
+        KS_CUDA(cudaStreamWaitEvent(S4, ev_g[t], 0));
+        launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), mean->as<double>(), b, S4);
+        KS_CUDA(cudaMemsetAsync(W->p, 0, W->bytes, S4));
+        if (c.rank == owner) {
+          KS_CUDA(cudaStreamWaitEvent(S3, ev_g[t], 0));
+          c.span_begin(PH_SOLVE, S3);
+          launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), nullptr, b, S3);
+          launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S3);
+          c.launches += 2;
+          c.potrf(Hj, b, info_slot++, S3);
+          c.potri(Hj, b, info_slot++, S3);
+          c.span_end(S3);
+          KS_CUDA(cudaEventRecord(ev_inv[t], S3));
+          KS_CUDA(cudaStreamWaitEvent(S4, ev_inv[t], 0));
+        }
+        c.span_begin(PH_ALLREDUCE, S4);
+        KS_NCCL(nccl_api().Broadcast(Hj, Hj, static_cast<size_t>(b) * b, ncclFloat64, owner, c.comm3, S4));
+        c.span_end(S4);
+        c.launches += 2;
+        KS_CUDA(cudaEventRecord(ev_fact[t], S4));
+      } else {
+        KS_CUDA(cudaStreamWaitEvent(S3, ev_g[t], 0));
+        c.span_begin(PH_SOLVE, S3);
+        launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), mean->as<double>(), b, S3);
+        launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S3);
+        c.launches += 2;
+        c.potrf(Hj, b, info_slot++, S3);
+        KS_CUDA(cudaMemsetAsync(W->p, 0, W->bytes, S3));
+        c.span_end(S3);
+        KS_CUDA(cudaEventRecord(ev_fact[t], S3));
+      }
       model->brows.push_back(b);
       model->W.push_back(std::move(W));
       model->mean.push_back(std::move(mean));
       flops += static_cast<double>(b) * b * b / 3.0;
-      c.span_end(S3);
-      KS_CUDA(cudaEventRecord(ev_fact[t], S3));
     } else {
       KS_CUDA(cudaEventRecord(ev_fact[t], S2));
     }
@@ -673,8 +795,16 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     launch_build_rhs(cm.as<float>(), ldc, deltas[j]->as<double>(), rsum.as<double>(), n_total_d, lam,
                      it > 0 ? model->W[j]->as<double>() : nullptr, rhs.as<double>(), b, k, S1);
     c.launches += 1;
-    c.potrs(Hj, b, rhs.as<double>(), k, info_slot++, S1);
-    launch_pack_update(rhs.as<double>(), model->W[j]->as<double>(), deltas[j]->as<double>(), bop.as<float>(), nullptr,
+    const double* dw_ptr;
+    if (use_inv) {
+      c.symm_solve(Hj, b, rhs.as<double>(), k, dwb.as<double>(), S1);
+      dw_ptr = dwb.as<double>();
+    } else {
+      c.potrs(Hj, b, rhs.as<double>(), k, info_slot++, S1);
+      dw_ptr = rhs.as<double>();
+    }
+    KS_CUDA(cudaEventRecord(ev_solved[t], S1));
+    launch_pack_update(dw_ptr, model->W[j]->as<double>(), deltas[j]->as<double>(), bop.as<float>(), nullptr,
                        static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), S1);
     c.launches += 1;
     flops += 2.0 * static_cast<double>(b) * b * k;
@@ -687,10 +817,14 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     KS_CUDA(cudaEventRecord(ev_upd[t], S1));
   };
 
+  // Enqueue order: a stream-wait on an event that has not been recorded yet counts as complete, so every wait must be
+  // enqueued after the corresponding record: prep(t) [featurize] after main(t - NBUF + 1), prepB(t) [Gram, factor] after main(t-1).
   for (int t = 0; t < std::min(T, NBUF - 1); ++t) prep(t);
+  prepB(0);
   for (int t = 0; t < T; ++t) {
-    if (t + NBUF - 1 < T) prep(t + NBUF - 1);
     mainstep(t);
+    if (t + 1 < T) prepB(t + 1);
+    if (t + NBUF - 1 < T) prep(t + NBUF - 1);
   }
   KS_CUDA(cudaStreamWaitEvent(S1, ev_fact[T - 1], 0));
   KS_CUDA(cudaEventRecord(ev1, S1));
@@ -703,19 +837,28 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   c.event_pool.push_back(ev_init);
   for (int t = 0; t < T; ++t) {
     c.event_pool.push_back(ev_g[t]);
+    c.event_pool.push_back(ev_inv[t]);
+    c.event_pool.push_back(ev_solved[t]);
     c.event_pool.push_back(ev_slab[t]);
     c.event_pool.push_back(ev_fact[t]);
     c.event_pool.push_back(ev_upd[t]);
   }
   double ms[PH_COUNT];
+  c.timeline_origin = getenv("KS_TIMELINE") ? ev0 : nullptr;
   c.collect_spans(ms);
+  c.timeline_origin = nullptr;
+  if (getenv("KS_TIMELINE")) {
+    FILE* f = fopen((std::string(getenv("KS_TIMELINE")) + "." + std::to_string(c.rank)).c_str(), "w");
+    if (f) { fputs(c.timeline_json.c_str(), f); fclose(f); }
+  }
   std::ostringstream js;
   js << "{\"solver\":\"blockls\",\"n_local\":" << n_loc << ",\"n_total\":" << static_cast<int64_t>(n_total_d) << ",\"d\":" << D
      << ",\"k\":" << k << ",\"block_size\":" << bs << ",\"num_blocks\":" << nb << ",\"num_iter\":" << num_iter
      << ",\"world\":" << c.world << ",\"total_ms\":" << total_ms << ",\"featurize_ms\":" << ms[PH_FEATURIZE]
      << ",\"gram_ms\":" << ms[PH_GRAM] << ",\"allreduce_ms\":" << ms[PH_ALLREDUCE] << ",\"solve_ms\":" << ms[PH_SOLVE]
      << ",\"update_ms\":" << ms[PH_UPDATE] << ",\"other_ms\":" << ms[PH_OTHER] << ",\"local_flops\":" << flops
-     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"tf32x1\",\"streams\":3,\"host_ms\":"
+     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"tf32x1\",\"streams\":3,\"solve\":\"" << (use_inv ? "inverse-owner" : "potrs")
+     << "\",\"host_ms\":"
      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count() << "}";
   c.stats_json = js.str();
   return c.add(std::move(model));
@@ -847,23 +990,34 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
     c->rank = rank;
     c->world = world_size;
     c->num_sms = prop.multiProcessorCount;
-    KS_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+    // stream priorities: the residual-dependent chain (st) is the critical path of the pipelined fit and mostly small
+    // kernels (NCCL, triangular solves); it must not queue behind the look-ahead tensor work of st2
+    int prio_least = 0, prio_greatest = 0;
+    KS_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    const int prio_mid = (prio_greatest < prio_least) ? prio_greatest + 1 : prio_greatest;
+    KS_CUDA(cudaStreamCreateWithPriority(&c->st, cudaStreamNonBlocking, prio_greatest));
     if (const char* e = getenv("KS_GRAM_CHUNK_ROWS")) {
       const long v = atol(e);
       if (v >= kGramStageRows) c->gram_chunk_rows = v;
     }
     if (const char* e = getenv("KS_GRAM_PAIR")) c->gram_pair = atoi(e) != 0;
-    KS_CUDA(cudaStreamCreateWithFlags(&c->st2, cudaStreamNonBlocking));
-    KS_CUDA(cudaStreamCreateWithFlags(&c->st3, cudaStreamNonBlocking));
+    if (const char* e = getenv("KS_RESERVE_SMS")) c->reserve_sms = std::max(0, std::min(140, atoi(e)));
+    if (const char* e = getenv("KS_INV_MIN_WORLD")) c->inv_min_world = std::max(1, atoi(e));
+    if (const char* e = getenv("KS_EXCL_SOLVE_MIN_WORLD")) c->exclusive_solve_min_world = std::max(1, atoi(e));
+    KS_CUDA(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, prio_least));
+    KS_CUDA(cudaStreamCreateWithPriority(&c->st3, cudaStreamNonBlocking, prio_mid));
+    KS_CUDA(cudaStreamCreateWithPriority(&c->st4, cudaStreamNonBlocking, prio_mid));
     if (world_size > 1) {
       if (!nccl_id) throw KsError{KS_ERR_INVALID, "nccl_id required for world_size > 1"};
       ncclUniqueId id;
       memcpy(&id, nccl_id, KS_NCCL_ID_BYTES);
       KS_NCCL(nccl_api().CommInitRank(&c->comm, world_size, id, rank));
       c->comm2 = c->comm;
-      if (nccl_api().CommSplit) {  // a second communicator so that collectives of the two streams never interleave
-        ncclComm_t c2 = nullptr;
+      c->comm3 = c->comm;
+      if (nccl_api().CommSplit) {  // one communicator per stream so that collectives of different streams never interleave
+        ncclComm_t c2 = nullptr, c3 = nullptr;
         if (nccl_api().CommSplit(c->comm, 0, rank, &c2, nullptr) == ncclSuccess && c2) c->comm2 = c2;
+        if (nccl_api().CommSplit(c->comm, 0, rank, &c3, nullptr) == ncclSuccess && c3) c->comm3 = c3;
       }
     }
     std::lock_guard<std::mutex> lk(g_mu);
@@ -890,6 +1044,7 @@ KS_API int32_t ks_ctx_destroy(int64_t ctx) {
   cudaStreamSynchronize(c->st);
   if (c->st2) cudaStreamSynchronize(c->st2);
   if (c->st3) cudaStreamSynchronize(c->st3);
+  if (c->st4) cudaStreamSynchronize(c->st4);
   c->matrices.clear();
   c->rfs.clear();
   c->models.clear();
@@ -897,6 +1052,8 @@ KS_API int32_t ks_ctx_destroy(int64_t ctx) {
   for (auto e : c->event_pool) cudaEventDestroy(e);
   if (c->solver) solver_api().Destroy(c->solver);
   if (c->solver2) solver_api().Destroy(c->solver2);
+  if (c->blas) blas_api().Destroy(c->blas);
+  if (c->comm3 && c->comm3 != c->comm) nccl_api().CommDestroy(c->comm3);
   if (c->comm2 && c->comm2 != c->comm) nccl_api().CommDestroy(c->comm2);
   if (c->comm) nccl_api().CommDestroy(c->comm);
   c->solver_work.release();
@@ -904,6 +1061,7 @@ KS_API int32_t ks_ctx_destroy(int64_t ctx) {
   cudaStreamDestroy(c->st);
   if (c->st2) cudaStreamDestroy(c->st2);
   if (c->st3) cudaStreamDestroy(c->st3);
+  if (c->st4) cudaStreamDestroy(c->st4);
   c.reset();
   bool last;
   {
@@ -929,6 +1087,9 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     if (n == "gram_chunk_rows" && value >= kGramStageRows) c.gram_chunk_rows = value;
     else if (n == "sample_rows" && value >= 1) c.sample_rows = value;
     else if (n == "gram_pair") c.gram_pair = value != 0;
+    else if (n == "reserve_sms" && value >= 0 && value < 148) c.reserve_sms = static_cast<int>(value);
+    else if (n == "inv_min_world" && value >= 1) c.inv_min_world = static_cast<int>(value);
+    else if (n == "exclusive_solve_min_world" && value >= 1) c.exclusive_solve_min_world = static_cast<int>(value);
     else if (n == "timing") c.timing = value != 0;
     else throw KsError{KS_ERR_INVALID, "unknown option or bad value: " + n};
   });

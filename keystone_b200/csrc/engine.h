@@ -89,7 +89,18 @@ struct SolverApi {
   cusolverStatus_t (*DpotrfBufferSize)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, int*) = nullptr;
   cusolverStatus_t (*Dpotrf)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, double*, int, int*) = nullptr;
   cusolverStatus_t (*Dpotrs)(cusolverDnHandle_t, cublasFillMode_t, int, int, const double*, int, double*, int, int*) = nullptr;
+  cusolverStatus_t (*DpotriBufferSize)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, int*) = nullptr;
+  cusolverStatus_t (*Dpotri)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, double*, int, int*) = nullptr;
 };
+struct BlasApi {  // cuBLAS, one plain library call: the fp64 symmetric product H^-1 * rhs
+  void* lib = nullptr;
+  cublasStatus_t (*Create)(cublasHandle_t*) = nullptr;
+  cublasStatus_t (*Destroy)(cublasHandle_t) = nullptr;
+  cublasStatus_t (*SetStream)(cublasHandle_t, cudaStream_t) = nullptr;
+  cublasStatus_t (*Dsymm)(cublasHandle_t, cublasSideMode_t, cublasFillMode_t, int, int, const double*, const double*, int,
+                          const double*, int, const double*, double*, int) = nullptr;
+};
+BlasApi& blas_api();
 struct NcclApi {
   void* lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -97,6 +108,7 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;  // optional (NCCL >= 2.18)
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 SolverApi& solver_api();  // throws KsError if libcusolver cannot be loaded
@@ -110,9 +122,18 @@ struct Ctx {
   cudaStream_t st = nullptr;   // main stream: residual-dependent chain (A^T R, triangular solves, update)
   cudaStream_t st2 = nullptr;  // prep stream: featurize + Gram of the blocks AHEAD (independent of the residual)
   cudaStream_t st3 = nullptr;  // factor stream: fp64 assembly + Cholesky of the blocks ahead
+  cudaStream_t st4 = nullptr;  // broadcast stream of the owner-computed inverses (so a broadcast never blocks a rank's own factor work)
   ncclComm_t comm = nullptr;   // collectives issued on st
   ncclComm_t comm2 = nullptr;  // collectives issued on st2 (split of comm; falls back to comm)
+  ncclComm_t comm3 = nullptr;  // broadcasts of the per-block inverse issued on st3
+  int inv_min_world = 1 << 30; // experimental: from this world size on, block j's Cholesky + explicit inverse run on rank
+                               // j % world only and are broadcast (off by default: cusolverDnDpotri is ~25 ms per 4096^2
+                               // block and its fp64 work slows the tensor kernels more than the shorter solve gains)
+  int exclusive_solve_min_world = 4;  // from this world size on, look-ahead tensor work is not launched while the critical
+                                      // chain runs its triangular solves (they take 12 ms contended vs 5.5 ms alone)
   cusolverDnHandle_t solver = nullptr;   // triangular solves (main stream)
+  cublasHandle_t blas = nullptr;         // H^-1 * rhs on the main stream
+  cudaStream_t solver_stream = nullptr, solver2_stream = nullptr;  // streams the handles are currently bound to
   cusolverDnHandle_t solver2 = nullptr;  // factorizations (factor stream): a handle's internal cuBLAS workspace is per stream
   DevBuf solver_work;
   int solver_lwork = 0;
@@ -122,6 +143,7 @@ struct Ctx {
   int64_t launches = 0;
   int64_t gram_chunk_rows = 4096;
   int gram_pair = 1;  // CTA-pair (cta_group::2) Gram kernel
+  int reserve_sms = 8; // SMs the persistent look-ahead kernel leaves to the critical chain
   int64_t sample_rows = 16384;
   int64_t next_id = 1;
   std::unordered_map<int64_t, std::unique_ptr<Matrix>> matrices;
@@ -129,7 +151,9 @@ struct Ctx {
   std::unordered_map<int64_t, std::unique_ptr<Model>> models;
   std::map<std::vector<int>, std::unique_ptr<DevBuf>> tile_cache;
   // phase timing of the current fit
-  struct Span { int phase; cudaEvent_t a, b; };
+  struct Span { int phase; cudaEvent_t a, b; int stream; };
+  cudaEvent_t timeline_origin = nullptr;  // when set, collect_spans also renders (phase, stream, start, end) per span
+  std::string timeline_json;
   std::vector<Span> spans;
   std::vector<cudaEvent_t> event_pool;
   bool timing = true;
@@ -148,6 +172,10 @@ struct Ctx {
   void ensure_solver();
   void potrf(double* H, int n, int info_slot, cudaStream_t s);
   void potrs(const double* H, int n, double* B, int nrhs, int info_slot, cudaStream_t s);
+  // H (Cholesky factor, lower) -> lower triangle of H^-1, in place (cusolverDnDpotri); latency-bound, runs on the factor stream
+  void potri(double* H, int n, int info_slot, cudaStream_t s);
+  // out (n x nrhs) = sym(Hinv, lower) * B   (cublasDsymm): the whole solve of the critical chain is ONE fp64 GEMM
+  void symm_solve(const double* Hinv, int n, const double* B, int nrhs, double* out, cudaStream_t s);
   void check_infos(int used_slots);
   void check_async(const char* what);
 };

@@ -12,8 +12,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, id_holder, ret):
+def _worker(rank, world, id_holder, ret, inv_min_world):
     sys.path.insert(0, ROOT)
+    os.environ["KS_INV_MIN_WORLD"] = str(inv_min_world)
     import keystone_b200 as ks
     from oracle import keystone_oracle as ko
     rng = np.random.default_rng(21)
@@ -41,14 +42,15 @@ def _worker(rank, world, id_holder, ret):
     ctx.close()
 
 
-def test_two_rank_fit_matches_oracle():
+@pytest.mark.parametrize("inv_min_world", [4, 2], ids=["potrs-on-every-rank", "owner-inverse-broadcast"])
+def test_two_rank_fit_matches_oracle(inv_min_world):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import keystone_b200 as ks
     mgr = mp.Manager()
     id_holder = mgr.dict(); ret = mgr.dict()
     id_holder["id"] = ks.Context.new_nccl_id()
-    mp.spawn(_worker, args=(2, id_holder, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, id_holder, ret, inv_min_world), nprocs=2, join=True)
     assert ret["rel"] < 5e-3, ret["rel"]
     assert ret["cost_rel"] < 2e-3 and ret["b_err"] < 1e-5
     assert np.array_equal(ret["W0"], ret["W1"])      # redundant solves are bit-identical across ranks
