@@ -156,6 +156,11 @@ KS_API int32_t ks_debug_gram(int64_t ctx, int64_t a, int64_t b, double* out_g, i
 /* Times `iters` launches of the Gram kernel alone (CUDA events on the launching stream); returns ms per launch. */
 KS_API int32_t ks_debug_time_gram(int64_t ctx, int64_t a, int64_t b, int32_t iters, double* out_ms);
 
+/* X = H^-1 B for a symmetric positive definite H (column-major n x n) and B (column-major n x k): Cholesky with cuSOLVER, then
+ * either the library's single-kernel multi-RHS solve (use_cusolver = 0, the product path) or cusolverDnDpotrs; best-of-3 ms. */
+KS_API int32_t ks_debug_chol_solve(int64_t ctx, const double* H_colmajor, int32_t n, const double* B_colmajor, int32_t k,
+                                   int32_t use_cusolver, double* X_out, double* out_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,7 @@ def _declare(L: C.CDLL) -> None:
     sig("ks_last_fit_stats_json", i64, C.c_char_p, i64)
     sig("ks_debug_gram", i64, i64, i64, C.c_void_p, i64, C.c_void_p, i64)
     sig("ks_debug_time_gram", i64, i64, i64, i32, p_f64)
+    sig("ks_debug_chol_solve", i64, C.c_void_p, i32, C.c_void_p, i32, i32, C.c_void_p, p_f64)
 
 
 def check(ctx: int, rc: int) -> None:

@@ -799,6 +799,10 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     if (use_inv) {
       c.symm_solve(Hj, b, rhs.as<double>(), k, dwb.as<double>(), S1);
       dw_ptr = dwb.as<double>();
+    } else if (c.custom_solve) {
+      KS_CUDA(launch_chol_solve(Hj, b, rhs.as<double>(), k, S1));
+      c.launches += 1;
+      dw_ptr = rhs.as<double>();
     } else {
       c.potrs(Hj, b, rhs.as<double>(), k, info_slot++, S1);
       dw_ptr = rhs.as<double>();
@@ -1001,6 +1005,7 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
       if (v >= kGramStageRows) c->gram_chunk_rows = v;
     }
     if (const char* e = getenv("KS_GRAM_PAIR")) c->gram_pair = atoi(e) != 0;
+    if (const char* e = getenv("KS_CUSTOM_SOLVE")) c->custom_solve = atoi(e) != 0;
     if (const char* e = getenv("KS_RESERVE_SMS")) c->reserve_sms = std::max(0, std::min(140, atoi(e)));
     if (const char* e = getenv("KS_INV_MIN_WORLD")) c->inv_min_world = std::max(1, atoi(e));
     if (const char* e = getenv("KS_EXCL_SOLVE_MIN_WORLD")) c->exclusive_solve_min_world = std::max(1, atoi(e));
@@ -1087,6 +1092,7 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     if (n == "gram_chunk_rows" && value >= kGramStageRows) c.gram_chunk_rows = value;
     else if (n == "sample_rows" && value >= 1) c.sample_rows = value;
     else if (n == "gram_pair") c.gram_pair = value != 0;
+    else if (n == "custom_solve") c.custom_solve = value != 0;
     else if (n == "reserve_sms" && value >= 0 && value < 148) c.reserve_sms = static_cast<int>(value);
     else if (n == "inv_min_world" && value >= 1) c.inv_min_world = static_cast<int>(value);
     else if (n == "exclusive_solve_min_world" && value >= 1) c.exclusive_solve_min_world = static_cast<int>(value);
@@ -1480,6 +1486,36 @@ KS_API int32_t ks_debug_time_gram(int64_t ctx, int64_t a, int64_t b, int32_t ite
     c.event_pool.push_back(e0);
     c.event_pool.push_back(e1);
     *out_ms = ms / std::max(iters, 1);
+  });
+}
+
+KS_API int32_t ks_debug_chol_solve(int64_t ctx, const double* H_colmajor, int32_t n, const double* B_colmajor, int32_t k,
+                                   int32_t use_cusolver, double* X_out, double* out_ms) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!H_colmajor || !B_colmajor || !X_out || n <= 0 || k <= 0) throw KsError{KS_ERR_INVALID, "bad arguments"};
+    DevBuf H, B;
+    H.alloc(sizeof(double) * static_cast<size_t>(n) * n);
+    B.alloc(sizeof(double) * static_cast<size_t>(n) * k);
+    KS_CUDA(cudaMemcpyAsync(H.p, H_colmajor, sizeof(double) * static_cast<size_t>(n) * n, cudaMemcpyHostToDevice, c.st));
+    c.potrf(H.as<double>(), n, 0, c.st);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+      KS_CUDA(cudaMemcpyAsync(B.p, B_colmajor, sizeof(double) * static_cast<size_t>(n) * k, cudaMemcpyHostToDevice, c.st));
+      cudaEvent_t e0 = c.get_event(), e1 = c.get_event();
+      KS_CUDA(cudaEventRecord(e0, c.st));
+      if (use_cusolver) c.potrs(H.as<double>(), n, B.as<double>(), k, 1, c.st);
+      else KS_CUDA(launch_chol_solve(H.as<double>(), n, B.as<double>(), k, c.st));
+      KS_CUDA(cudaEventRecord(e1, c.st));
+      c.check_async("debug_chol_solve");
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      best = std::min(best, ms);
+      c.event_pool.push_back(e0);
+      c.event_pool.push_back(e1);
+    }
+    c.check_infos(2);
+    KS_CUDA(cudaMemcpy(X_out, B.p, sizeof(double) * static_cast<size_t>(n) * k, cudaMemcpyDeviceToHost));
+    if (out_ms) *out_ms = best;
   });
 }
 

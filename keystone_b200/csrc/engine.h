@@ -129,8 +129,9 @@ struct Ctx {
   int inv_min_world = 1 << 30; // experimental: from this world size on, block j's Cholesky + explicit inverse run on rank
                                // j % world only and are broadcast (off by default: cusolverDnDpotri is ~25 ms per 4096^2
                                // block and its fp64 work slows the tensor kernels more than the shorter solve gains)
-  int exclusive_solve_min_world = 4;  // from this world size on, look-ahead tensor work is not launched while the critical
-                                      // chain runs its triangular solves (they take 12 ms contended vs 5.5 ms alone)
+  int exclusive_solve_min_world = 1 << 30;  // experimental: from this world size on the look-ahead Gram waits for the
+                                            // critical chain's triangular solves (4.4 ms alone, ~11 ms contended); measured
+                                            // neutral at 4 GPUs (332 vs 338 ms) because it serialises Gram and solve
   cusolverDnHandle_t solver = nullptr;   // triangular solves (main stream)
   cublasHandle_t blas = nullptr;         // H^-1 * rhs on the main stream
   cudaStream_t solver_stream = nullptr, solver2_stream = nullptr;  // streams the handles are currently bound to
@@ -144,6 +145,8 @@ struct Ctx {
   int64_t gram_chunk_rows = 4096;
   int gram_pair = 1;  // CTA-pair (cta_group::2) Gram kernel
   int reserve_sms = 8; // SMs the persistent look-ahead kernel leaves to the critical chain
+  int custom_solve = 0; // experimental: 1 = chol_solve_kernel (single launch; 10.8 ms at b=4096,k=1000 vs 4.4 ms for
+                        // cusolverDnDpotrs alone / ~11 ms when potrs shares the SMs), 0 = cusolverDnDpotrs
   int64_t sample_rows = 16384;
   int64_t next_id = 1;
   std::unordered_map<int64_t, std::unique_ptr<Matrix>> matrices;

@@ -48,6 +48,8 @@ int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols
 cudaError_t launch_gram(const GramLaunch& g, cudaStream_t st);
 cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st);
 unsigned int read_wait_timeout_flag();
+// B (n x k, column-major, ld = n) <- (L L^T)^-1 B with L the lower triangle of a column-major n x n matrix (solve_kernels.cu)
+cudaError_t launch_chol_solve(const double* L, int n, double* B, int k, cudaStream_t st);
 
 // ---- element-wise / reduction helpers (aux_kernels.cu) ----
 void launch_f64_to_f32_rows(const double* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int64_t cols,

@@ -265,3 +265,23 @@ def test_bwls_larger_problem_cosine_features(ctx):
     pred = model(feats).to_numpy()
     ref = F @ Wr + fb
     assert np.abs(pred - ref).max() < 2e-2
+
+
+@pytest.mark.parametrize("n,k", [(4096, 1000), (300, 37), (128, 8), (5, 3), (1000, 1)])
+def test_chol_solve_kernel(ctx, n, k):
+    """The single-kernel multi-RHS Cholesky solve (replaces cusolverDnDpotrs on the critical chain) vs numpy, and vs cuSOLVER."""
+    import ctypes as C
+    from keystone_b200._capi import lib, check
+    rng = np.random.default_rng(n + k)
+    A = rng.standard_normal((n + 50, n))
+    H = np.asfortranarray(A.T @ A + 0.5 * np.eye(n))
+    B = np.asfortranarray(rng.standard_normal((n, k)))
+    ref = np.linalg.solve(H, B)
+    out = {}
+    for use_cusolver in (0, 1):
+        X = np.empty((n, k), order="F"); ms = C.c_double(0)
+        check(ctx.handle, lib().ks_debug_chol_solve(ctx.handle, H.ctypes.data_as(C.c_void_p), n, B.ctypes.data_as(C.c_void_p), k,
+                                                   use_cusolver, X.ctypes.data_as(C.c_void_p), C.byref(ms)))
+        out[use_cusolver] = (X, ms.value)
+        assert np.abs(X - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()) * np.linalg.cond(H)
+    print(f"chol_solve n={n} k={k}: kernel {out[0][1]:.3f} ms, cusolver potrs {out[1][1]:.3f} ms")
