@@ -244,9 +244,13 @@ def main():
     sampler.start()
     l0 = ctx.launch_count()
     t0 = time.perf_counter()
+    step_wall = []
     for _ in range(args.steps):
+        ts = time.perf_counter()
         model = est.fit(feats, y_dev)
+        step_wall.append(1e3 * (time.perf_counter() - ts))
         stats.append(ctx.last_fit_stats())
+    t_loop = time.perf_counter() - t0
     barrier()
     t_resident = max_over_ranks((time.perf_counter() - t0) / args.steps)
     launches = (ctx.launch_count() - l0) // max(args.steps, 1)
@@ -326,6 +330,7 @@ def main():
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_resident,
            "device_ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "tf32", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
+           "step_wall_ms": step_wall, "loop_ms_rank0": 1e3 * t_loop,
            "alg_tflops": flops / t_resident / 1e12, "phase_ms": {k: stats[-1][k] for k in stats[-1] if k.endswith("_ms")},
            "roofline": roofline}
     if e2e:
