@@ -308,9 +308,13 @@ def main():
     n_loc = hi - lo
     gram_launch_flops = 2.0 * n_loc * args.block * (args.block + args.classes)          # full-GEMM convention, per launch
     achieved = gram_launch_flops / (gram_ms * 1e-3) / 1e12
-    traffic = None
+    # DRAM traffic of the dominant kernel from the committed ncu capture; only comparable when the capture was taken at this
+    # launch shape (the round-1 capture is the reduced N_loc = 131072 run, so it is reported beside the number, not as it)
+    traffic, traffic_ref = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "gram_ncu_summary.json"))).get("dram_bytes_per_launch")
+        traffic_ref = json.load(open(os.path.join(ROOT, "profiles", "gram_ncu_summary.json")))
+        if traffic_ref.get("n_rows") == n_loc:
+            traffic = traffic_ref.get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
     roofline = {"kernel": "gram2_tn_kernel (tcgen05 cta_group::2 kind::tf32, S^T [S | R])", "bound": "tensor", "achieved": achieved,
@@ -319,7 +323,7 @@ def main():
                         "triangle: executed flops are 0.65x); peak is the measured SUSTAINED bf16 figure (35 ms launches run "
                         "under the power cap), the tf32 MMA rate is half of it; kernel timed alone with CUDA events",
                 "executed_tflops": achieved * (104 * 256 * 512) / (args.block * (args.block + args.classes)) if args.block == 4096 and args.classes == 1000 else None,
-                "ms_per_launch": gram_ms}
+                "ms_per_launch": gram_ms, "traffic_reference_capture": traffic_ref}
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
