@@ -107,7 +107,8 @@ KS_API int32_t ks_blockls_fit(int64_t ctx, int64_t features, int64_t x_in, const
                        int32_t precision_mode, int64_t* out_model);
 /* BlockWeightedLeastSquaresEstimator(blockSize, numIter, lambda, mixtureWeight, numFeaturesOpt).fit
  * (K/nodes/learning/BlockWeightedLeastSquares.scala:36-84, trainWithL2 :102-321).  Rows need not be
- * class-sorted (groupByClasses :333-370 is applied on the device).  Single-rank in this version. */
+ * class-sorted within a rank (groupByClasses :333-370 is applied on the device).  With world_size > 1 the rows must be
+ * sharded BY CLASS: every class lives on exactly one rank (checked; KS_ERR_INVALID otherwise).  Collective across ranks. */
 KS_API int32_t ks_blockwls_fit(int64_t ctx, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, int64_t labels,
                         int32_t block_size, int32_t num_iter, double lambda, double mixture_weight,
                         int64_t num_features_or_0, int32_t precision_mode, int64_t* out_model);

@@ -12,7 +12,8 @@
 //   * residual update (:287-290) -> the same EPI_UPDATE GEMM as BlockLS
 // Features are shifted by an estimate m of the population mean before the (tf32) Gram; every quantity the reference
 // defines on raw features is recovered exactly in fp64 from (m, column sums, Gram of the shifted block).
-// Status: single rank (world_size == 1); class Grams of one block are kept resident (k * b * b * 4 bytes).
+// Multi-rank: rows are sharded BY CLASS (each class on exactly one rank, checked); population statistics and the solved
+// columns are all-reduced.  Class Grams of one block are kept resident (classes_on_rank * b * b * 4 bytes).
 #include "engine.h"
 
 #include <algorithm>
@@ -129,13 +130,16 @@ static unsigned grid1d(int64_t n, int threads = 256) {
 
 // ------------------------------------------------------------------------------------ fit
 int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, double w, int64_t nf_opt) {
-  if (c.world != 1) throw KsError{KS_ERR_INVALID, "ks_blockwls_fit: single-rank only in this version"};
   if (bs <= 0 || num_iter < 1) throw KsError{KS_ERR_INVALID, "blockSize must be > 0 and numIter >= 1"};
   if (Y.rows != src.n_rows) throw KsError{KS_ERR_INVALID, "features and labels have different row counts"};
+  // Multi-rank: every rank passes the rows of the classes it owns; each class must live on exactly one rank (the
+  // reference's one-class-per-partition precondition, :111-124, lifted to ranks).  N is this rank's row count, Ntot the
+  // global one; population statistics are all-reduced, per-class statistics and solves stay local, the solved columns are
+  // all-reduced into the full dW (the `collect` + `broadcast` of :276, :285).
   const int64_t N = Y.rows;
   const int k = static_cast<int>(Y.cols);
   const int64_t D = nf_opt > 0 ? nf_opt : src.D;
-  if (D > src.D || D <= 0 || N <= 0) throw KsError{KS_ERR_INVALID, "bad problem size"};
+  if (D > src.D || D <= 0 || N < 0) throw KsError{KS_ERR_INVALID, "bad problem size"};
   const int nb = static_cast<int>((D + bs - 1) / bs);
   const int bmax = static_cast<int>(std::min<int64_t>(bs, D));
   const int64_t lds = round_up(bmax, 32), kpad = round_up(k, 32);
@@ -155,6 +159,33 @@ int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double l
   KS_CUDA(cudaStreamSynchronize(st));
   std::vector<int64_t> count(k, 0);
   for (int64_t i = 0; i < N; ++i) count[cls[i]]++;
+  // global class sizes / ownership check / global row count
+  std::vector<double> gcount(k, 0.0);
+  double Ntot_d = static_cast<double>(N);
+  {
+    std::vector<double> h(2 * k + 1, 0.0);
+    for (int cc = 0; cc < k; ++cc) {
+      h[cc] = static_cast<double>(count[cc]);
+      h[k + cc] = count[cc] > 0 ? 1.0 : 0.0;
+    }
+    h[2 * k] = static_cast<double>(N);
+    if (c.world > 1) {
+      DevBuf tmp;
+      tmp.alloc(sizeof(double) * h.size());
+      KS_CUDA(cudaMemcpyAsync(tmp.p, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, st));
+      c.allreduce_f64(tmp.as<double>(), h.size());
+      KS_CUDA(cudaMemcpyAsync(h.data(), tmp.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, st));
+      KS_CUDA(cudaStreamSynchronize(st));
+    }
+    for (int cc = 0; cc < k; ++cc) {
+      gcount[cc] = h[cc];
+      if (h[k + cc] > 1.5)
+        throw KsError{KS_ERR_INVALID, "ks_blockwls_fit: class " + std::to_string(cc) + " has rows on more than one rank; every class "
+                                      "must be owned by exactly one rank (shard the rows by class)"};
+    }
+    Ntot_d = h[2 * k];
+  }
+  if (Ntot_d < 1) throw KsError{KS_ERR_INVALID, "no training rows"};
   bool contiguous = true;  // every class forms one run
   {
     std::vector<char> seen(k, 0);
@@ -230,17 +261,18 @@ int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double l
 
   // ---- jointLabelMean (:148-156), residual = labels - jointLabelMean (:167-169)
   std::vector<double> jlm(k, 0.0);
-  for (auto& r : ranges) jlm[r.cls] = 2 * w + (2 * (1.0 - w) * static_cast<double>(r.n) / static_cast<double>(N)) - 1;
+  for (int cc = 0; cc < k; ++cc)
+    if (gcount[cc] > 0) jlm[cc] = 2 * w + (2 * (1.0 - w) * gcount[cc] / Ntot_d) - 1;
   DevBuf jlm_d, R, Rr, slab, Gcls, Gpop, Ctmp, Cpop, xtr, shift, negm, psum, csum, rsum_all, rsum_cls, dp, dc, H, rhs, dW, bop, cbias,
       fsum, facc;
   jlm_d.alloc(sizeof(double) * k);
   KS_CUDA(cudaMemcpyAsync(jlm_d.p, jlm.data(), sizeof(double) * k, cudaMemcpyHostToDevice, st));
-  R.alloc(sizeof(float) * static_cast<size_t>(N * kpad));
+  R.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(N, 1) * kpad));
   Rr.alloc(R.bytes);
   bwls_init_residual_kernel<<<grid1d(N * kpad), 256, 0, st>>>(Yp->d, Yp->ld, jlm_d.as<double>(), R.as<float>(), kpad, N, k);
   c.launches += 1;
-  slab.alloc(sizeof(float) * static_cast<size_t>(N * lds));
-  Gcls.alloc(sizeof(float) * g_elems * ncls);
+  slab.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(N, 1) * lds));
+  Gcls.alloc(sizeof(float) * g_elems * std::max(ncls, 1));
   Gpop.alloc(sizeof(float) * g_elems);
   Ctmp.alloc(sizeof(float) * c_elems);
   Cpop.alloc(sizeof(float) * c_elems);
@@ -265,6 +297,7 @@ int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double l
     KS_CUDA(cudaMemsetAsync(fsum.p, 0, fsum.bytes, st));
     launch_colsum(sp->F->d, nullptr, sp->F->ld, N, static_cast<int>(sp->F->cols), fsum.as<double>(), st);
     c.launches += 1;
+    c.allreduce_f64(fsum.as<double>(), static_cast<size_t>(sp->F->cols));
   }
 
   auto model = std::make_unique<Model>();
@@ -290,7 +323,7 @@ int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double l
           // exact population mean of the block
           DevBuf cnt;
           cnt.alloc(sizeof(double));
-          const double nd = static_cast<double>(N);
+          const double nd = Ntot_d;
           KS_CUDA(cudaMemcpyAsync(cnt.p, &nd, sizeof(double), cudaMemcpyHostToDevice, st));
           launch_divide_by_count(fsum.as<double>() + c0, cnt.as<double>(), shifts[j]->as<float>(), nullptr, b, st);
           KS_CUDA(cudaStreamSynchronize(st));
@@ -304,7 +337,7 @@ int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double l
           cnt.alloc(sizeof(double));
           KS_CUDA(cudaMemsetAsync(s32.p, 0, s32.bytes, st));
           int64_t total = 0;
-          for (int sgi = 0; sgi < nseg; ++sgi) {
+          for (int sgi = 0; sgi < nseg && N > 0; ++sgi) {
             const int64_t r0 = std::min<int64_t>(N - 1, (N * sgi) / nseg);
             const int64_t nr = std::min<int64_t>(seg, N - r0);
             produce_slab(c, *sp, c0, b, sp->zeros.as<float>(), slab.as<float>() + r0 * lds, lds, r0, nr, false, s32.as<float>(), st);
@@ -313,6 +346,8 @@ int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double l
           launch_f32_to_f64_rows(s32.as<float>(), lds, psum.as<double>(), lds, 1, b, st);
           const double nd = static_cast<double>(total);
           KS_CUDA(cudaMemcpyAsync(cnt.p, &nd, sizeof(double), cudaMemcpyHostToDevice, st));
+          c.allreduce_f64(psum.as<double>(), static_cast<size_t>(b));
+          c.allreduce_f64(cnt.as<double>(), 1);
           launch_divide_by_count(psum.as<double>(), cnt.as<double>(), shifts[j]->as<float>(), nullptr, b, st);
           KS_CUDA(cudaStreamSynchronize(st));
           c.launches += 2;
@@ -342,6 +377,8 @@ int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double l
       }
       launch_colsum(slab.as<float>(), nullptr, lds, N, b, psum.as<double>(), st);
       c.launches += 2 + 2 * ncls;
+      c.allreduce_f64(psum.as<double>(), static_cast<size_t>(b));
+      c.allreduce_f64(rsum_all.as<double>(), static_cast<size_t>(k));
       KS_CUDA(cudaMemcpyAsync(h_rsum_all.data(), rsum_all.p, sizeof(double) * kpad, cudaMemcpyDeviceToHost, st));
       KS_CUDA(cudaMemcpyAsync(h_rsum_cls.data(), rsum_cls.p, sizeof(double) * static_cast<size_t>(ncls) * kpad, cudaMemcpyDeviceToHost, st));
 
@@ -361,20 +398,22 @@ int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double l
                                                                             rg.cls, b, k);
         c.launches += 2;
       }
+      c.allreduce_f32(Gpop.as<float>(), g_elems);   // population statistics over all ranks (treeReduce, :212-214)
+      c.allreduce_f32(Cpop.as<float>(), c_elems);
       KS_CUDA(cudaStreamSynchronize(st));  // host needs the residual sums below
 
       // ---------------- per class: joint second moments, fp64 Cholesky solve (:241-276)
-      bwls_means_kernel<<<(b + 255) / 256, 256, 0, st>>>(psum.as<double>(), static_cast<double>(N), dp.as<double>(), b);
+      bwls_means_kernel<<<(b + 255) / 256, 256, 0, st>>>(psum.as<double>(), Ntot_d, dp.as<double>(), b);
       KS_CUDA(cudaMemsetAsync(dW.p, 0, dW.bytes, st));
       for (int ci = 0; ci < ncls; ++ci) {
         const Range& rg = ranges[ci];
         const double nc = static_cast<double>(rg.n);
         bwls_means_kernel<<<(b + 255) / 256, 256, 0, st>>>(csum.as<double>() + static_cast<size_t>(ci) * lds, nc, dc.as<double>(), b);
         bwls_build_kernel<<<grid1d(static_cast<int64_t>(b) * b), 256, 0, st>>>(Gpop.as<float>(), Gcls.as<float>() + static_cast<size_t>(ci) * g_elems,
-                                                                          ldg, dp.as<double>(), dc.as<double>(), static_cast<double>(N),
+                                                                          ldg, dp.as<double>(), dc.as<double>(), Ntot_d,
                                                                           nc, w, lam, H.as<double>(), b);
         bwls_rhs_kernel<<<(b + 255) / 256, 256, 0, st>>>(Cpop.as<float>(), ldc, xtr.as<float>() + static_cast<size_t>(ci) * lds, m,
-                                                       dp.as<double>(), dc.as<double>(), static_cast<double>(N), nc,
+                                                       dp.as<double>(), dc.as<double>(), Ntot_d, nc,
                                                        h_rsum_all[rg.cls], h_rsum_cls[static_cast<size_t>(ci) * kpad + rg.cls], w, lam,
                                                        model->W[j]->as<double>() + static_cast<size_t>(rg.cls) * b, rhs.as<double>(),
                                                        it == 0 ? jms[j]->as<double>() + static_cast<size_t>(rg.cls) * b : nullptr, rg.cls, b);
@@ -384,6 +423,7 @@ int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double l
         copy_col_kernel<<<(b + 255) / 256, 256, 0, st>>>(rhs.as<double>(), dW.as<double>() + static_cast<size_t>(rg.cls) * b, b);
         c.launches += 1;
       }
+      c.allreduce_f64(dW.as<double>(), static_cast<size_t>(b) * k);  // every rank contributes the columns of its classes
       // ---------------- W_j += dW ; R -= F dW = S dW + 1 (m^T dW)   (:278-294)
       neg_f32_to_f64_kernel<<<(b + 255) / 256, 256, 0, st>>>(m, negm.as<double>(), b);
       launch_pack_update(dW.as<double>(), model->W[j]->as<double>(), negm.as<double>(), bop.as<float>(), nullptr,
@@ -400,6 +440,7 @@ int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double l
                                            static_cast<int>(model->brows[j]), k);
     c.launches += 1;
   }
+  c.allreduce_f64(facc.as<double>(), static_cast<size_t>(k));  // joint means exist only on the rank that owns the class
   final_b_finish_kernel<<<(k + 255) / 256, 256, 0, st>>>(jlm_d.as<double>(), facc.as<double>(), model->intercept.as<double>(), k);
   c.launches += 1;
   KS_CUDA(cudaEventRecord(ev1, st));
@@ -408,7 +449,8 @@ int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double l
   cudaEventElapsedTime(&total_ms, ev0, ev1);
   c.event_pool.push_back(ev0);
   c.event_pool.push_back(ev1);
-  c.stats_json = "{\"solver\":\"blockwls\",\"n_total\":" + std::to_string(N) + ",\"d\":" + std::to_string(D) + ",\"k\":" +
+  c.stats_json = "{\"solver\":\"blockwls\",\"world\":" + std::to_string(c.world) + ",\"n_local\":" + std::to_string(N) +
+                 ",\"n_total\":" + std::to_string(static_cast<int64_t>(Ntot_d)) + ",\"d\":" + std::to_string(D) + ",\"k\":" +
                  std::to_string(k) + ",\"classes_present\":" + std::to_string(ncls) + ",\"block_size\":" + std::to_string(bs) +
                  ",\"num_iter\":" + std::to_string(num_iter) + ",\"reshuffled\":" + (sorted_already ? "0" : "1") +
                  ",\"total_ms\":" + std::to_string(total_ms) + ",\"launches\":" + std::to_string(c.launches - launches0) + "}";

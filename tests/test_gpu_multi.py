@@ -54,3 +54,44 @@ def test_two_rank_fit_matches_oracle(inv_min_world):
     assert ret["rel"] < 5e-3, ret["rel"]
     assert ret["cost_rel"] < 2e-3 and ret["b_err"] < 1e-5
     assert np.array_equal(ret["W0"], ret["W1"])      # redundant solves are bit-identical across ranks
+
+
+def _bwls_worker(rank, world, id_holder, ret):
+    sys.path.insert(0, ROOT)
+    import keystone_b200 as ks
+    A = np.loadtxt(os.path.join(ROOT, "tests", "golden", "aMat.csv"), delimiter=",")
+    B = np.loadtxt(os.path.join(ROOT, "tests", "golden", "bMat.csv"), delimiter=",")
+    rows = np.r_[0:10] if rank == 0 else np.r_[10:15]            # classes {0, 1} on rank 0, class 2 on rank 1
+    ctx = ks.Context(device=rank, rank=rank, world_size=world, nccl_id=id_holder["id"])
+    model = ks.BlockWeightedLeastSquaresEstimator(4, 10, 0.1, 0.3).fit(ctx.matrix(A[rows]), ctx.matrix(B[rows]))
+    ret[f"W{rank}"] = np.concatenate(model.xs, 0)
+    ret[f"b{rank}"] = model.b_opt
+    # a class split over two ranks must be rejected on every rank
+    bad = np.r_[0:8] if rank == 0 else np.r_[8:15]
+    try:
+        ks.BlockWeightedLeastSquaresEstimator(4, 1, 0.1, 0.3).fit(ctx.matrix(A[bad]), ctx.matrix(B[bad]))
+        ret[f"rejected{rank}"] = False
+    except ks.KeystoneError:
+        ret[f"rejected{rank}"] = True
+    ctx.close()
+
+
+def test_two_rank_class_sharded_bwls_matches_oracle():
+    """BlockWeightedLeastSquares with the rows sharded by class over 2 ranks (the reference's one-class-per-partition layout,
+    T/nodes/learning/BlockWeightedLeastSquaresSuite.scala:67-68) equals the single-process fp64 oracle on the full fixture."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import keystone_b200 as ks
+    from oracle import keystone_oracle as ko
+    mgr = mp.Manager()
+    id_holder = mgr.dict(); ret = mgr.dict()
+    id_holder["id"] = ks.Context.new_nccl_id()
+    mp.spawn(_bwls_worker, args=(2, id_holder, ret), nprocs=2, join=True)
+    A = np.loadtxt(os.path.join(ROOT, "tests", "golden", "aMat.csv"), delimiter=",")
+    B = np.loadtxt(os.path.join(ROOT, "tests", "golden", "bMat.csv"), delimiter=",")
+    xs, fb = ko.bwls_fit(A, B, 4, 10, 0.1, 0.3)
+    Wr = np.concatenate(xs, 0)
+    assert np.linalg.norm(ret["W0"] - Wr) / np.linalg.norm(Wr) < 5e-3
+    assert np.abs(ret["b0"] - fb).max() < 5e-3
+    assert np.array_equal(ret["W0"], ret["W1"]) and np.array_equal(ret["b0"], ret["b1"])
+    assert ret["rejected0"] and ret["rejected1"]
