@@ -47,6 +47,8 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=2048, help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--precision", default=os.environ.get("KS_BENCH_PRECISION", "tf32"), choices=["tf32", "f16"],
+                    help="operand type of the three big GEMMs (fp32 accumulate, fp64 solve either way)")
     return ap.parse_args()
 
 
@@ -181,7 +183,8 @@ def main():
     config = {"workload": f"C3 CosineRandomFeatures({args.d_in}->{args.block})x{args.num_rf} + BlockLeastSquaresEstimator",
               "n_rows": args.n_rows, "d_in": args.d_in, "d": D, "k": args.classes, "block_size": args.block,
               "num_iter": args.num_iter, "lambda": args.lam, "parallelism": f"rows x{world}",
-              "l2": "inputs larger than L2 (X 1.76 GB, slab 16 GB per block)"}
+              "l2": "inputs larger than L2 (X 1.76 GB, slab 8-16 GB per block)",
+              "precision": f"{args.precision} operands, fp32 accumulate, fp64 solve"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -227,7 +230,7 @@ def main():
     Xp = torch.from_numpy(X).pin_memory()          # pinned host buffers for the e2e leg
     cp = torch.from_numpy(cls).pin_memory()
     rfs = [ks.CosineRandomFeatures(ctx, W, b) for W, b in params]
-    est = ks.BlockLeastSquaresEstimator(args.block, args.num_iter, args.lam)
+    est = ks.BlockLeastSquaresEstimator(args.block, args.num_iter, args.lam, precision=args.precision)
 
     def feats_of(x):
         return ks.Pipeline.gather(rfs).andThen(ks.VectorCombiner())(x)
@@ -265,8 +268,10 @@ def main():
     sa = ctx.synthetic_normal(hi - lo, args.block, 11, lo)
     sb = ctx.synthetic_normal(hi - lo, args.classes, 12, lo)
     ms = C.c_double(0)
+    ctx.set_option("precision", 1 if args.precision == "f16" else 0)   # the debug entry converts the operands to fp16 first
     check(ctx.handle, lib().ks_debug_time_gram(ctx.handle, sa.handle, sb.handle, 3, C.byref(ms)))
     check(ctx.handle, lib().ks_debug_time_gram(ctx.handle, sa.handle, sb.handle, 5, C.byref(ms)))
+    ctx.set_option("precision", 0)
     gram_ms = max_over_ranks(ms.value)
     del sa, sb
 
@@ -317,11 +322,13 @@ def main():
             traffic = traffic_ref.get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
-    roofline = {"kernel": "gram2_tn_kernel (tcgen05 cta_group::2 kind::tf32, S^T [S | R])", "bound": "tensor", "achieved": achieved,
+    kind = "kind::f16" if args.precision == "f16" else "kind::tf32"
+    roofline = {"kernel": f"gram2_tn_kernel (tcgen05 cta_group::2 {kind}, S^T [S | R])", "bound": "tensor", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "note": "algorithmic flops = 2*N_loc*b*(b+k) per launch (full-GEMM convention; the kernel skips the lower "
                         "triangle: executed flops are 0.65x); peak is the measured SUSTAINED bf16 figure (35 ms launches run "
-                        "under the power cap), the tf32 MMA rate is half of it; kernel timed alone with CUDA events",
+                        "under the power cap); the tf32 MMA rate is half of it, the fp16 rate equals it; kernel timed alone "
+                        "with CUDA events",
                 "executed_tflops": achieved * (104 * 256 * 512) / (args.block * (args.block + args.classes)) if args.block == 4096 and args.classes == 1000 else None,
                 "ms_per_launch": gram_ms, "traffic_reference_capture": traffic_ref}
 
@@ -333,7 +340,7 @@ def main():
     out = {"metric": "block-LS fit samples/sec (N=1M, D=64K, k=1K)", "value": args.n_rows / t_resident, "unit": "samples/s",
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_resident,
            "device_ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "tf32", "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
+           "dtype": args.precision, "data": "synthetic", "config": config, "clocks": clocks, "gpu_launches": int(launches),
            "step_wall_ms": step_wall, "loop_ms_rank0": 1e3 * t_loop,
            "alg_tflops": flops / t_resident / 1e12, "phase_ms": {k: stats[-1][k] for k in stats[-1] if k.endswith("_ms")},
            "roofline": roofline}

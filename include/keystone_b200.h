@@ -52,6 +52,9 @@ extern "C" {
 
 /* precision_mode of the fit/apply entry points */
 #define KS_PRECISION_TF32 0  /* operands rounded to tf32 (round-to-nearest), fp32 accumulate, fp64 solve */
+#define KS_PRECISION_F16 1   /* ks_blockls_fit on generated (cosine) features: fp16 operands (same 10-bit mantissa as tf32,
+                                residual / increments scaled by device-chosen powers of two), kind::f16 MMA at twice the
+                                tf32 rate, fp32 accumulate, fp64 solve; materialised feature matrices fall back to tf32 */
 
 #define KS_NCCL_ID_BYTES 128
 

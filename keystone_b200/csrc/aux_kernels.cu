@@ -3,6 +3,8 @@
 // K/utils/MatrixUtils.scala:137-146), residual initialisation, the fp64 assembly of the reduced
 // normal equations and operand packing.  All matrices are row-major fp32 with ld % 32 == 0
 // unless stated; fp64 matrices are column-major exactly as Breeze stores DenseMatrix[Double].
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 
 namespace ks {
@@ -314,20 +316,23 @@ void launch_build_system(const float* G, int ldg, const double* delta, double n_
 
 __global__ void build_rhs_kernel(const float* __restrict__ C, int ldc, const double* __restrict__ delta,
                                  const double* __restrict__ rsum, double n_total, double lam,
-                                 const double* __restrict__ Wold, double* __restrict__ rhs, int b, int k) {
+                                 const double* __restrict__ Wold, double* __restrict__ rhs, int b, int k,
+                                 const float* __restrict__ c_scale) {
   const int64_t total = static_cast<int64_t>(b) * k;
+  const double cs = c_scale ? static_cast<double>(__ldg(c_scale)) : 1.0;  // C was accumulated from a power-of-two scaled residual
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i / b), f = static_cast<int>(i - static_cast<int64_t>(c) * b);
-    double v = static_cast<double>(C[static_cast<int64_t>(f) * ldc + c]) - delta[f] * rsum[c];  // n * delta * (rsum / n)
+    double v = static_cast<double>(C[static_cast<int64_t>(f) * ldc + c]) * cs - delta[f] * rsum[c];  // n * delta * (rsum / n)
     if (Wold) v -= lam * Wold[i];
     rhs[i] = v;
   }
 }
 void launch_build_rhs(const float* C, int ldc, const double* delta, const double* rsum, double n_total, double lam,
-                      const double* Wold, double* rhs, int b, int k, cudaStream_t st) {
+                      const double* Wold, double* rhs, int b, int k, cudaStream_t st, const float* c_scale) {
   if (b == 0 || k == 0) return;
-  build_rhs_kernel<<<grid_for(static_cast<int64_t>(b) * k, 256), 256, 0, st>>>(C, ldc, delta, rsum, n_total, lam, Wold, rhs, b, k);
+  build_rhs_kernel<<<grid_for(static_cast<int64_t>(b) * k, 256), 256, 0, st>>>(C, ldc, delta, rsum, n_total, lam, Wold, rhs, b, k,
+                                                                               c_scale);
 }
 
 // one block per class column c: packs dW[:, c] into the K-major GEMM operand row c and reduces delta . dW[:, c]
@@ -457,6 +462,154 @@ void launch_sq_err(const float* Y, int64_t ldy, const float* L, int64_t ldl, int
                    cudaStream_t st) {
   if (rows == 0) return;
   sq_err_kernel<<<grid_for(rows * k, 256), 256, 0, st>>>(Y, ldy, L, ldl, rows, k, out);
+}
+
+// =====================================================================================
+// fp16 operand path (precision mode KS_PRECISION_F16): fp16 has the 10-bit mantissa of tf32 but a 5-bit exponent, so the
+// operands whose magnitude the data decides (residual, weight increments) are multiplied by a power of two chosen on the
+// device from their largest magnitude; the power of two is divided out again in fp32 / fp64 after the MMA.
+// =====================================================================================
+// maxbits: bit pattern of the largest |x| seen (non-negative floats order like unsigned integers); must be zeroed
+__global__ void max_abs_f32_kernel(const float* __restrict__ p, int64_t ld, int64_t rows, int cols, unsigned* __restrict__ maxbits) {
+  float m = 0.f;
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    m = fmaxf(m, fabsf(p[r * ld + c]));
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(maxbits, __float_as_uint(m));
+}
+__global__ void max_abs_f64_kernel(const double* __restrict__ p, int64_t n, unsigned* __restrict__ maxbits) {
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(static_cast<float>(p[i])));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(maxbits, __float_as_uint(m));
+}
+// scale[0] = 2^e with max * 2^e in [target / 2, target], scale[1] = 2^-e   (max == 0, inf or nan: 1, 1)
+__global__ void pow2_scale_kernel(const unsigned* __restrict__ maxbits, float target, float* __restrict__ scale) {
+  const float m = __uint_as_float(*maxbits);
+  float s = 1.f, inv = 1.f;
+  if (m > 0.f && m < 3.0e38f) {
+    int e = static_cast<int>(floorf(log2f(target / m)));
+    e = max(-100, min(100, e));
+    s = exp2f(static_cast<float>(e));
+    inv = exp2f(static_cast<float>(-e));
+    if (m * s > target) { s *= 0.5f; inv *= 2.f; }  // log2f rounding at an exact power of two
+  }
+  scale[0] = s;
+  scale[1] = inv;
+}
+void launch_max_abs_f32(const float* p, int64_t ld, int64_t rows, int cols, unsigned* maxbits, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return;
+  max_abs_f32_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(p, ld, rows, cols, maxbits);
+}
+void launch_max_abs_f64(const double* p, int64_t n, unsigned* maxbits, cudaStream_t st) {
+  if (n == 0) return;
+  max_abs_f64_kernel<<<grid_for(n, 256, 148 * 2), 256, 0, st>>>(p, n, maxbits);
+}
+void launch_pow2_scale(const unsigned* maxbits, float target, float* scale, cudaStream_t st) {
+  pow2_scale_kernel<<<1, 1, 0, st>>>(maxbits, target, scale);
+}
+
+__global__ void f32_to_f16_rows_kernel(const float* __restrict__ src, int64_t src_ld, __half* __restrict__ dst, int64_t dst_ld,
+                                       int64_t rows, int64_t cols) {
+  const int64_t total = rows * dst_ld;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / dst_ld, c = i - r * dst_ld;
+    dst[i] = __float2half_rn(c < cols ? src[r * src_ld + c] : 0.f);
+  }
+}
+void launch_f32_to_f16_rows(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int64_t cols, cudaStream_t st) {
+  if (rows == 0) return;
+  f32_to_f16_rows_kernel<<<grid_for(rows * dst_ld, 256), 256, 0, st>>>(src, src_ld, static_cast<__half*>(dst), dst_ld, rows, cols);
+}
+
+// fp16 twin of round_colsum_kernel: R16[:, :k] = fp16(R * scale[0]), columns >= k zero; sums as before (of R itself)
+__global__ void round_colsum16_kernel(const float* __restrict__ R, __half* __restrict__ R16, int64_t ld, int64_t rows, int k,
+                                      double* __restrict__ sums, int64_t rows_per_block, const float* __restrict__ scale) {
+  __shared__ double red[8][128];
+  const float sc = __ldg(scale);
+  const int c4 = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int64_t r_begin = blockIdx.y * rows_per_block;
+  const int64_t r_end = min(rows, r_begin + rows_per_block);
+  double a[4] = {0, 0, 0, 0};
+  if (c4 < ld) {
+    for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
+      const float4 v = *reinterpret_cast<const float4*>(R + r * ld + c4);
+      const float in[4] = {v.x, v.y, v.z, v.w};
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = c4 + j;
+        if (c < k) {
+          a[j] += in[j];
+          o[j] = in[j] * sc;
+        } else {
+          o[j] = 0.f;
+        }
+      }
+      const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<const unsigned*>(&h0);
+      pk.y = *reinterpret_cast<const unsigned*>(&h1);
+      *reinterpret_cast<uint2*>(R16 + r * ld + c4) = pk;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) red[threadIdx.y][threadIdx.x * 4 + j] = a[j];
+  __syncthreads();
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  if (t < 128) {
+    double s = 0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) s += red[y][t];
+    const int c = blockIdx.x * 128 + t;
+    if (c < k) atomicAdd(sums + c, s);
+  }
+}
+void launch_round_colsum16(const float* R, void* R16, int64_t ld, int64_t rows, int k, double* sums, const float* scale,
+                           cudaStream_t st) {
+  if (rows == 0) return;
+  const int64_t rpb = 1024;
+  dim3 grid(static_cast<unsigned>((ld + 127) / 128), static_cast<unsigned>((rows + rpb - 1) / rpb));
+  round_colsum16_kernel<<<grid, dim3(32, 8), 0, st>>>(R, static_cast<__half*>(R16), ld, rows, k, sums, rpb, scale);
+}
+
+// fp16 twin of pack_update_kernel: bop16[c][f] = fp16(dW[f][c] * scale[0]); Wmodel and cbias exactly as the tf32 version
+__global__ void pack_update16_kernel(const double* __restrict__ dW, double* __restrict__ Wmodel,
+                                     const double* __restrict__ delta, __half* __restrict__ bop, int ldb,
+                                     float* __restrict__ cbias, int b, int k, const float* __restrict__ scale) {
+  const int c = blockIdx.x;
+  const double sc = static_cast<double>(__ldg(scale));
+  __shared__ double red[256];
+  double acc = 0;
+  for (int f = threadIdx.x; f < ldb; f += blockDim.x) {
+    float h = 0.f;
+    if (c < k && f < b) {
+      const double w = dW[static_cast<int64_t>(c) * b + f];
+      if (Wmodel) Wmodel[static_cast<int64_t>(c) * b + f] += w;
+      if (delta) acc += delta[f] * w;
+      h = static_cast<float>(w * sc);
+    }
+    bop[static_cast<int64_t>(c) * ldb + f] = __float2half_rn(h);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && cbias) cbias[c] = static_cast<float>(red[0]);
+}
+void launch_pack_update16(const double* dW, double* Wmodel, const double* delta, void* bop16, int ldb, float* cbias, int b, int k,
+                          int kpad, const float* scale, cudaStream_t st) {
+  if (kpad == 0) return;
+  pack_update16_kernel<<<kpad, 256, 0, st>>>(dW, Wmodel, delta, static_cast<__half*>(bop16), ldb, cbias, b, k, scale);
 }
 
 }  // namespace ks

@@ -231,6 +231,10 @@ void Ctx::allreduce_f64(double* p, size_t n, bool prep) {
   if (world <= 1 || n == 0) return;
   KS_NCCL(nccl_api().AllReduce(p, p, n, ncclFloat64, ncclSum, prep ? comm2 : comm, prep ? st2 : st));
 }
+void Ctx::allreduce_max_u32(unsigned* p, size_t n) {
+  if (world <= 1 || n == 0) return;
+  KS_NCCL(nccl_api().AllReduce(p, p, n, ncclUint32, ncclMax, comm, st));
+}
 void Ctx::ensure_solver() {
   if (solver) return;
   SolverApi& api = solver_api();
@@ -382,6 +386,14 @@ void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, i
   c.launches += 1;
 }
 
+static void tmap16_or_throw(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                            int swizzle) {
+  const int r = make_tmap_any(m, base, rows, cols, ld, box_cols, box_rows, 2, swizzle);
+  if (r != 0)
+    throw KsError{KS_ERR_CUDA, "cuTensorMapEncodeTiled (fp16) failed (" + std::to_string(r) + ") rows=" + std::to_string(rows) +
+                                   " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld)};
+}
+
 static void tmap_or_throw(CUtensorMap* m, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
                           bool atom32 = false) {
   const int r = make_tmap_2d(m, base, rows, cols, ld, box_rows, atom32);
@@ -390,12 +402,13 @@ static void tmap_or_throw(CUtensorMap* m, const float* base, int64_t rows, int64
                                    " cols=" + std::to_string(cols) + " ld=" + std::to_string(ld)};
 }
 
-void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, float* slab, int64_t lds,
-                  int64_t row_begin, int64_t rows, bool round_out, float* colsum, cudaStream_t st) {
+void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, void* slab_v, int64_t lds,
+                  int64_t row_begin, int64_t rows, bool round_out, float* colsum, cudaStream_t st, bool out16) {
   if (rows <= 0 || cols <= 0) return;
   if (!st) st = c.st;
+  float* slab = static_cast<float*>(slab_v);
   if (src.F) {
-    if (!round_out) throw KsError{KS_ERR_INVALID, "unrounded slab only for generated features"};
+    if (!round_out || out16) throw KsError{KS_ERR_INVALID, "unrounded / fp16 slabs only for generated features"};
     launch_center_round(src.F->d + row_begin * src.F->ld, src.F->ld, static_cast<int>(c0), shift, slab, colsum, lds, rows,
                         static_cast<int>(cols), st);
     c.launches += 1;
@@ -404,7 +417,9 @@ void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* s
   KmLaunch k;
   tmap_or_throw(&k.tmA, src.xop.as<float>() + row_begin * src.X->ld, rows, src.d_in, src.X->ld, 128);
   tmap_or_throw(&k.tmB, src.Wall + c0 * src.ldw, cols, src.d_in, src.ldw, 256);
-  tmap_or_throw(&k.tmOut, slab, rows, cols, lds, 32);
+  if (out16) tmap16_or_throw(&k.tmOut, slab_v, rows, cols, lds, 32, 32, TMAP_NONE);
+  else tmap_or_throw(&k.tmOut, slab, rows, cols, lds, 32);
+  k.out16 = out16 ? 1 : 0;
   k.p.vec0 = src.ball + c0;
   k.p.vec1 = shift;
   k.p.colsum = colsum;
@@ -449,22 +464,31 @@ const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, b
   return p;
 }
 
-void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* R, int64_t ldr, int kcols,
-                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c, cudaStream_t st) {
+void launch_gram_block(Ctx& c, const void* slab, int64_t lds, int64_t rows, int b, const void* R, int64_t ldr, int kcols,
+                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c, cudaStream_t st, bool f16) {
   if (rows <= 0 || b <= 0 || (!with_g && !with_c)) return;
   if (!st) st = c.st;
   GramLaunch g;
   int nt = 0;
-  g.pair = c.gram_pair;
+  g.pair = f16 ? 1 : c.gram_pair;
+  g.f16 = f16 ? 1 : 0;
   g.tiles = gram_tiles(c, b, kcols, with_g, with_c, g.pair != 0, &nt);
   g.num_tiles = nt;
-  tmap_or_throw(&g.tmA, slab, rows, b, lds, kGramStageRows, true);
-  g.tmB0 = g.tmA;
-  if (with_c) tmap_or_throw(&g.tmB1, R, rows, kcols, ldr, kGramStageRows, true);
-  else g.tmB1 = g.tmA;
+  const int stage_rows = f16 ? 64 : kGramStageRows;
+  if (f16) {  // MN-major fp16 operands: 64-column (128 B) x 64-row boxes, plain 128 B swizzle
+    tmap16_or_throw(&g.tmA, slab, rows, b, lds, 64, stage_rows, TMAP_SW128);
+    g.tmB0 = g.tmA;
+    if (with_c) tmap16_or_throw(&g.tmB1, R, rows, kcols, ldr, 64, stage_rows, TMAP_SW128);
+    else g.tmB1 = g.tmA;
+  } else {
+    tmap_or_throw(&g.tmA, static_cast<const float*>(slab), rows, b, lds, kGramStageRows, true);
+    g.tmB0 = g.tmA;
+    if (with_c) tmap_or_throw(&g.tmB1, static_cast<const float*>(R), rows, kcols, ldr, kGramStageRows, true);
+    else g.tmB1 = g.tmA;
+  }
   g.rows = static_cast<int>(rows);
   int64_t chunk = c.gram_chunk_rows;
-  chunk = std::max<int64_t>(kGramStageRows, chunk / kGramStageRows * kGramStageRows);
+  chunk = std::max<int64_t>(stage_rows, chunk / stage_rows * stage_rows);
   g.chunk_rows = static_cast<int>(chunk);
   if (with_g) tmap_or_throw(&g.tmOut0, G, b, b, ldg, 32);
   if (with_c) tmap_or_throw(&g.tmOut1, C, b, kcols, ldc, 32);
@@ -476,14 +500,22 @@ void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int
   c.launches += 1;
 }
 
-void launch_update(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* bop, int64_t ldb, int k,
-                   float* out, int64_t ldo, const float* cbias, int epi, bool reduce, cudaStream_t st) {
+void launch_update(Ctx& c, const void* slab, int64_t lds, int64_t rows, int b, const void* bop, int64_t ldb, int k,
+                   float* out, int64_t ldo, const float* cbias, int epi, bool reduce, cudaStream_t st, bool f16,
+                   const float* acc_scale_ptr) {
   if (rows <= 0 || k <= 0 || b <= 0) return;
   if (!st) st = c.st;
   KmLaunch u;
-  u.pair = c.gram_pair;
-  tmap_or_throw(&u.tmA, slab, rows, b, lds, 128);
-  tmap_or_throw(&u.tmB, bop, k, b, ldb, u.pair ? 128 : 256);
+  u.pair = f16 ? 1 : c.gram_pair;
+  u.f16 = f16 ? 1 : 0;
+  u.p.acc_scale_ptr = acc_scale_ptr;
+  if (f16) {  // K-major fp16 operands: 64 K-elements (128 B) x 128 rows per box
+    tmap16_or_throw(&u.tmA, slab, rows, b, lds, 64, 128, TMAP_SW128);
+    tmap16_or_throw(&u.tmB, bop, k, b, ldb, 64, 128, TMAP_SW128);
+  } else {
+    tmap_or_throw(&u.tmA, static_cast<const float*>(slab), rows, b, lds, 128);
+    tmap_or_throw(&u.tmB, static_cast<const float*>(bop), k, b, ldb, u.pair ? 128 : 256);
+  }
   tmap_or_throw(&u.tmOut, out, rows, k, ldo, 32);  // k valid columns: the store never touches columns >= k
   u.p.vec0 = cbias;
   u.p.vec1 = nullptr;
@@ -531,7 +563,8 @@ __global__ void sumsq_f64_kernel(const double* p, int64_t n, double* out) {
 // prep / factor run up to two blocks ahead of main (three slab / G / H buffers); cross-stream dependencies are CUDA events
 // and there is no host synchronisation inside the loop.  With the rows sharded over several GPUs the per-block tensor
 // work shrinks but the Cholesky does not: keeping it off both other chains is what keeps the strong scaling going.
-static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, int64_t nf_opt) {
+static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, int64_t nf_opt,
+                           int precision = KS_PRECISION_TF32) {
   if (bs <= 0 || num_iter < 1) throw KsError{KS_ERR_INVALID, "blockSize must be > 0 and numIter >= 1"};
   if (Y.rows != src.n_rows) throw KsError{KS_ERR_INVALID, "features and labels have different row counts"};
   const int64_t n_loc = Y.rows;
@@ -585,19 +618,37 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   // of a block is ~30 ms on its owner, so `world` of them must be in flight at once (N_loc shrinks with world, so do the slabs)
   const bool use_inv = c.world >= c.inv_min_world;
   const int NBUF = use_inv ? c.world + 2 : 3;
-  DevBuf r_f32, r_tf32, cm, rhs, dwb, rsum, bop, cbias, samp, fsum;
+  // fp16 operand mode (KS_PRECISION_F16): the slab, the residual operand and the increment operand are fp16 and the three
+  // big GEMMs run as kind::f16 -- same 10-bit mantissa as tf32 at twice the MMA rate and half the slab bytes.  Only for
+  // generated cosine features (|value| <= 2: no range problem); the residual and the increments are scaled by device-chosen
+  // powers of two.  Materialised feature matrices have arbitrary scale and keep the tf32 path.
+  const bool f16 = precision == KS_PRECISION_F16 && !src.F;
+  const size_t es = f16 ? 2 : 4;  // bytes per slab / operand element
+  DevBuf r_f32, r_tf32, cm, rhs, dwb, rsum, bop, cbias, samp, fsum, scales;
   std::unique_ptr<DevBuf[]> slab(new DevBuf[NBUF]), gbuf(new DevBuf[NBUF]), Hbuf(new DevBuf[NBUF]), ssum(new DevBuf[NBUF]);
   r_f32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * kpad));
-  r_tf32.alloc(r_f32.bytes);
+  r_tf32.alloc(f16 ? r_f32.bytes / 2 : r_f32.bytes);
   launch_init_residual(Y.d, Y.ld, model->intercept.as<double>(), r_f32.as<float>(), kpad, n_loc, k, S1);
   c.launches += 1;
+  // scales: [0] max|R0| bits, [1] max|dW| bits (per block), then float pairs {2^e, 2^-e}: [2,3] residual, [4,5] increment
+  scales.alloc(sizeof(float) * 8);
+  unsigned* maxbits = scales.as<unsigned>();
+  const float* rscale = scales.as<float>() + 2;
+  float* dwscale = scales.as<float>() + 4;
+  if (f16) {
+    KS_CUDA(cudaMemsetAsync(scales.p, 0, scales.bytes, S1));
+    launch_max_abs_f32(r_f32.as<float>(), kpad, n_loc, k, maxbits, S1);
+    c.allreduce_max_u32(maxbits, 1);  // every rank must scale its rows of R alike: C is summed over the ranks
+    launch_pow2_scale(maxbits, 4096.f, scales.as<float>() + 2, S1);  // 16x headroom below fp16's 65504 for later residuals
+    c.launches += 2;
+  }
   c.span_end();
 
   const int ldg = static_cast<int>(lds), ldc = static_cast<int>(kpad);
   const size_t g_elems = static_cast<size_t>(bmax) * ldg, c_elems = static_cast<size_t>(bmax) * ldc;
   const bool cache_factors = num_iter > 1;
   for (int i = 0; i < NBUF; ++i) {
-    slab[i].alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));
+    slab[i].alloc(es * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));
     gbuf[i].alloc(sizeof(float) * g_elems);
     ssum[i].alloc(sizeof(float) * lds);
     if (!cache_factors) Hbuf[i].alloc(sizeof(double) * static_cast<size_t>(bmax) * bmax);
@@ -606,7 +657,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   rhs.alloc(sizeof(double) * static_cast<size_t>(bmax) * k);
   dwb.alloc(rhs.bytes);
   rsum.alloc(sizeof(double) * kpad);
-  bop.alloc(sizeof(float) * static_cast<size_t>(kpad) * lds);
+  bop.alloc(es * static_cast<size_t>(kpad) * lds);
   cbias.alloc(sizeof(float) * kpad);
   samp.alloc(sizeof(double) * (bmax + 1));  // sample column sums + sample row count (generated features)
   std::vector<std::unique_ptr<DevBuf>> factors(nb), deltas(nb), shifts(nb);
@@ -668,8 +719,8 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
         const int64_t ns = std::min<int64_t>(n_loc, c.sample_rows);
         KS_CUDA(cudaMemsetAsync(samp.p, 0, samp.bytes, S2));
         KS_CUDA(cudaMemsetAsync(ssum[buf].p, 0, ssum[buf].bytes, S2));
-        produce_slab(c, src, c0, b, src.zeros.as<float>(), slab[buf].as<float>(), lds, 0, ns, /*round_out=*/false,
-                     ssum[buf].as<float>(), S2);
+        produce_slab(c, src, c0, b, src.zeros.as<float>(), slab[buf].p, lds, 0, ns, /*round_out=*/false,
+                     ssum[buf].as<float>(), S2, f16);
         launch_f32_to_f64_rows(ssum[buf].as<float>(), lds, samp.as<double>(), bmax, 1, b, S2);  // 1 x b "matrix"
         c.launches += 1;
         set_f64_kernel<<<1, 1, 0, S2>>>(samp.as<double>() + bmax, static_cast<double>(ns));
@@ -681,8 +732,8 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       }
     }
     KS_CUDA(cudaMemsetAsync(ssum[buf].p, 0, ssum[buf].bytes, S2));
-    produce_slab(c, src, c0, b, shifts[j]->as<float>(), slab[buf].as<float>(), lds, 0, n_loc, true,
-                 it == 0 ? ssum[buf].as<float>() : nullptr, S2);
+    produce_slab(c, src, c0, b, shifts[j]->as<float>(), slab[buf].p, lds, 0, n_loc, true,
+                 it == 0 ? ssum[buf].as<float>() : nullptr, S2, f16);
     if (!src.F) flops += 2.0 * static_cast<double>(n_loc) * src.d_in * b;
     c.span_end(S2);
     KS_CUDA(cudaEventRecord(ev_slab[t], S2));
@@ -698,8 +749,8 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       if (exclusive_solve && t >= 1) KS_CUDA(cudaStreamWaitEvent(S2, ev_solved[t - 1], 0));
       c.span_begin(PH_GRAM, S2);  // G part of the Gram
       KS_CUDA(cudaMemsetAsync(gbuf[buf].p, 0, gbuf[buf].bytes, S2));
-      launch_gram_block(c, slab[buf].as<float>(), lds, n_loc, b, nullptr, 0, 0, gbuf[buf].as<float>(), ldg, nullptr, 0, true,
-                        false, S2);
+      launch_gram_block(c, slab[buf].p, lds, n_loc, b, nullptr, 0, 0, gbuf[buf].as<float>(), ldg, nullptr, 0, true,
+                        false, S2, f16);
       flops += 2.0 * n_loc * static_cast<double>(b) * b;
       c.span_end(S2);
       c.span_begin(PH_ALLREDUCE, S2);
@@ -776,13 +827,14 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     c.span_begin(PH_OTHER);
     KS_CUDA(cudaMemsetAsync(cm.p, 0, sizeof(float) * c_elems, S1));
     KS_CUDA(cudaMemsetAsync(rsum.p, 0, rsum.bytes, S1));
-    launch_round_colsum(r_f32.as<float>(), r_tf32.as<float>(), kpad, n_loc, k, rsum.as<double>(), S1);
+    if (f16) launch_round_colsum16(r_f32.as<float>(), r_tf32.p, kpad, n_loc, k, rsum.as<double>(), rscale, S1);
+    else launch_round_colsum(r_f32.as<float>(), r_tf32.as<float>(), kpad, n_loc, k, rsum.as<double>(), S1);
     c.launches += 1;
     c.span_end();
     KS_CUDA(cudaStreamWaitEvent(S1, ev_slab[t], 0));
     c.span_begin(PH_UPDATE);  // A^T R part of the Gram (accounted with the residual chain)
-    launch_gram_block(c, slab[buf].as<float>(), lds, n_loc, b, r_tf32.as<float>(), kpad, k, nullptr, 0, cm.as<float>(), ldc,
-                      false, true, S1);
+    launch_gram_block(c, slab[buf].p, lds, n_loc, b, r_tf32.p, kpad, k, nullptr, 0, cm.as<float>(), ldc,
+                      false, true, S1, f16);
     flops += 2.0 * n_loc * static_cast<double>(b) * k;
     c.span_end();
     c.span_begin(PH_ALLREDUCE);
@@ -793,7 +845,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     c.span_begin(PH_SOLVE);
     double* Hj = cache_factors ? factors[j]->as<double>() : Hbuf[buf].as<double>();
     launch_build_rhs(cm.as<float>(), ldc, deltas[j]->as<double>(), rsum.as<double>(), n_total_d, lam,
-                     it > 0 ? model->W[j]->as<double>() : nullptr, rhs.as<double>(), b, k, S1);
+                     it > 0 ? model->W[j]->as<double>() : nullptr, rhs.as<double>(), b, k, S1, f16 ? rscale + 1 : nullptr);
     c.launches += 1;
     const double* dw_ptr;
     if (use_inv) {
@@ -808,14 +860,23 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       dw_ptr = rhs.as<double>();
     }
     KS_CUDA(cudaEventRecord(ev_solved[t], S1));
-    launch_pack_update(dw_ptr, model->W[j]->as<double>(), deltas[j]->as<double>(), bop.as<float>(), nullptr,
-                       static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), S1);
+    if (f16) {
+      KS_CUDA(cudaMemsetAsync(maxbits + 1, 0, sizeof(unsigned), S1));
+      launch_max_abs_f64(dw_ptr, static_cast<int64_t>(b) * k, maxbits + 1, S1);
+      launch_pow2_scale(maxbits + 1, 8192.f, dwscale, S1);
+      launch_pack_update16(dw_ptr, model->W[j]->as<double>(), deltas[j]->as<double>(), bop.p, static_cast<int>(lds),
+                           cbias.as<float>(), b, k, static_cast<int>(kpad), dwscale, S1);
+      c.launches += 2;
+    } else {
+      launch_pack_update(dw_ptr, model->W[j]->as<double>(), deltas[j]->as<double>(), bop.as<float>(), nullptr,
+                         static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), S1);
+    }
     c.launches += 1;
     flops += 2.0 * static_cast<double>(b) * b * k;
     c.span_end();
     c.span_begin(PH_UPDATE);
-    launch_update(c, slab[buf].as<float>(), lds, n_loc, b, bop.as<float>(), lds, k, r_f32.as<float>(), kpad, cbias.as<float>(),
-                  EPI_UPDATE, /*reduce=*/true, S1);
+    launch_update(c, slab[buf].p, lds, n_loc, b, bop.p, lds, k, r_f32.as<float>(), kpad, cbias.as<float>(),
+                  EPI_UPDATE, /*reduce=*/true, S1, f16, f16 ? dwscale + 1 : nullptr);
     flops += 2.0 * n_loc * static_cast<double>(b) * k;
     c.span_end();
     KS_CUDA(cudaEventRecord(ev_upd[t], S1));
@@ -861,7 +922,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
      << ",\"world\":" << c.world << ",\"total_ms\":" << total_ms << ",\"featurize_ms\":" << ms[PH_FEATURIZE]
      << ",\"gram_ms\":" << ms[PH_GRAM] << ",\"allreduce_ms\":" << ms[PH_ALLREDUCE] << ",\"solve_ms\":" << ms[PH_SOLVE]
      << ",\"update_ms\":" << ms[PH_UPDATE] << ",\"other_ms\":" << ms[PH_OTHER] << ",\"local_flops\":" << flops
-     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"tf32x1\",\"streams\":3,\"solve\":\"" << (use_inv ? "inverse-owner" : "potrs")
+     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"" << (f16 ? "f16" : "tf32x1") << "\",\"streams\":3,\"solve\":\"" << (use_inv ? "inverse-owner" : "potrs")
      << "\",\"host_ms\":"
      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count() << "}";
   c.stats_json = js.str();
@@ -1005,6 +1066,7 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
       if (v >= kGramStageRows) c->gram_chunk_rows = v;
     }
     if (const char* e = getenv("KS_GRAM_PAIR")) c->gram_pair = atoi(e) != 0;
+    if (const char* e = getenv("KS_PRECISION")) c->precision = (atoi(e) == 1 || !strcmp(e, "f16")) ? KS_PRECISION_F16 : KS_PRECISION_TF32;
     if (const char* e = getenv("KS_CUSTOM_SOLVE")) c->custom_solve = atoi(e) != 0;
     if (const char* e = getenv("KS_RESERVE_SMS")) c->reserve_sms = std::max(0, std::min(140, atoi(e)));
     if (const char* e = getenv("KS_INV_MIN_WORLD")) c->inv_min_world = std::max(1, atoi(e));
@@ -1092,6 +1154,7 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     if (n == "gram_chunk_rows" && value >= kGramStageRows) c.gram_chunk_rows = value;
     else if (n == "sample_rows" && value >= 1) c.sample_rows = value;
     else if (n == "gram_pair") c.gram_pair = value != 0;
+    else if (n == "precision" && (value == KS_PRECISION_TF32 || value == KS_PRECISION_F16)) c.precision = static_cast<int>(value);
     else if (n == "custom_solve") c.custom_solve = value != 0;
     else if (n == "reserve_sms" && value >= 0 && value < 148) c.reserve_sms = static_cast<int>(value);
     else if (n == "inv_min_world" && value >= 1) c.inv_min_world = static_cast<int>(value);
@@ -1263,10 +1326,12 @@ KS_API int32_t ks_blockls_fit(int64_t ctx, int64_t features, int64_t x_in, const
                        int64_t* out_model) {
   return guard(ctx, [&](Ctx& c) {
     if (!out_model) throw KsError{KS_ERR_INVALID, "null out_model"};
-    if (precision_mode != KS_PRECISION_TF32) throw KsError{KS_ERR_INVALID, "unsupported precision_mode"};
+    if (precision_mode != KS_PRECISION_TF32 && precision_mode != KS_PRECISION_F16)
+      throw KsError{KS_ERR_INVALID, "unsupported precision_mode"};
     FeatSrc src;
     make_feat_src(c, features, x_in, rfs, n_rfs, src);
-    *out_model = fit_blockls(c, src, c.matrix(labels), block_size, num_iter, lambda, num_features_or_0);
+    const int prec = c.precision == KS_PRECISION_F16 ? KS_PRECISION_F16 : precision_mode;  // the context option overrides
+    *out_model = fit_blockls(c, src, c.matrix(labels), block_size, num_iter, lambda, num_features_or_0, prec);
   });
 }
 
@@ -1275,7 +1340,8 @@ KS_API int32_t ks_blockwls_fit(int64_t ctx, int64_t features, int64_t x_in, cons
                         int32_t precision_mode, int64_t* out_model) {
   return guard(ctx, [&](Ctx& c) {
     if (!out_model) throw KsError{KS_ERR_INVALID, "null out_model"};
-    if (precision_mode != KS_PRECISION_TF32) throw KsError{KS_ERR_INVALID, "unsupported precision_mode"};
+    if (precision_mode != KS_PRECISION_TF32)
+      throw KsError{KS_ERR_INVALID, "unsupported precision_mode (the weighted solver computes in tf32 only)"};
     FeatSrc src;
     make_feat_src(c, features, x_in, rfs, n_rfs, src);
     *out_model = fit_bwls(c, src, c.matrix(labels), block_size, num_iter, lambda, mixture_weight, num_features_or_0);
@@ -1435,23 +1501,43 @@ KS_API int32_t ks_last_fit_stats_json(int64_t ctx, char* buf, int64_t buflen) {
 }
 
 // ---------------------------------------------------------------- debug / micro-benchmarks
-static void debug_gram_run(Ctx& c, Matrix& A, Matrix& B, DevBuf& gc, int* ldg, int* ldc) {
+// With the context option precision = KS_PRECISION_F16 the operands are first converted to fp16 and the kind::f16 kernel runs.
+struct DebugGramOps {
+  DevBuf a16, b16;
+  const void* A = nullptr;
+  const void* B = nullptr;
+  bool f16 = false;
+};
+static void debug_gram_run(Ctx& c, Matrix& A, Matrix& B, DevBuf& gc, int* ldg, int* ldc, DebugGramOps& ops) {
   if (A.rows != B.rows) throw KsError{KS_ERR_INVALID, "row mismatch"};
+  ops.f16 = c.precision == KS_PRECISION_F16;
+  ops.A = A.d;
+  ops.B = B.d;
+  if (ops.f16) {
+    ops.a16.alloc(2 * static_cast<size_t>(std::max<int64_t>(A.rows, 1) * A.ld));
+    ops.b16.alloc(2 * static_cast<size_t>(std::max<int64_t>(B.rows, 1) * B.ld));
+    launch_f32_to_f16_rows(A.d, A.ld, ops.a16.p, A.ld, A.rows, A.cols, c.st);
+    launch_f32_to_f16_rows(B.d, B.ld, ops.b16.p, B.ld, B.rows, B.cols, c.st);
+    ops.A = ops.a16.p;
+    ops.B = ops.b16.p;
+  }
   const int b = static_cast<int>(A.cols), kc = static_cast<int>(B.cols);
   *ldg = static_cast<int>(round_up(b, 32));
   *ldc = static_cast<int>(round_up(kc, 32));
   const size_t ge = static_cast<size_t>(b) * *ldg, ce = static_cast<size_t>(b) * *ldc;
   gc.alloc(sizeof(float) * (ge + ce));
   KS_CUDA(cudaMemsetAsync(gc.p, 0, gc.bytes, c.st));
-  launch_gram_block(c, A.d, A.ld, A.rows, b, B.d, B.ld, kc, gc.as<float>(), *ldg, gc.as<float>() + ge, *ldc, true, true);
+  launch_gram_block(c, ops.A, A.ld, A.rows, b, ops.B, B.ld, kc, gc.as<float>(), *ldg, gc.as<float>() + ge, *ldc, true, true,
+                    nullptr, ops.f16);
 }
 KS_API int32_t ks_debug_gram(int64_t ctx, int64_t a, int64_t b, double* out_g, int64_t ld_g, double* out_c, int64_t ld_c) {
   return guard(ctx, [&](Ctx& c) {
     Matrix& A = c.matrix(a);
     Matrix& B = c.matrix(b);
     DevBuf gc;
+    DebugGramOps ops;
     int ldg, ldc;
-    debug_gram_run(c, A, B, gc, &ldg, &ldc);
+    debug_gram_run(c, A, B, gc, &ldg, &ldc, ops);
     c.check_async("debug_gram");
     const int m = static_cast<int>(A.cols), kc = static_cast<int>(B.cols);
     std::vector<float> h(gc.bytes / sizeof(float));
@@ -1471,14 +1557,15 @@ KS_API int32_t ks_debug_time_gram(int64_t ctx, int64_t a, int64_t b, int32_t ite
     Matrix& A = c.matrix(a);
     Matrix& B = c.matrix(b);
     DevBuf gc;
+    DebugGramOps ops;
     int ldg, ldc;
-    debug_gram_run(c, A, B, gc, &ldg, &ldc);  // warm-up + allocation
+    debug_gram_run(c, A, B, gc, &ldg, &ldc, ops);  // warm-up + allocation
     const size_t ge = static_cast<size_t>(A.cols) * ldg;
     cudaEvent_t e0 = c.get_event(), e1 = c.get_event();
     KS_CUDA(cudaEventRecord(e0, c.st));
     for (int i = 0; i < iters; ++i)
-      launch_gram_block(c, A.d, A.ld, A.rows, static_cast<int>(A.cols), B.d, B.ld, static_cast<int>(B.cols), gc.as<float>(), ldg,
-                        gc.as<float>() + ge, ldc, true, true);
+      launch_gram_block(c, ops.A, A.ld, A.rows, static_cast<int>(A.cols), ops.B, B.ld, static_cast<int>(B.cols), gc.as<float>(),
+                        ldg, gc.as<float>() + ge, ldc, true, true, nullptr, ops.f16);
     KS_CUDA(cudaEventRecord(e1, c.st));
     c.check_async("debug_time_gram");
     float ms = 0;

@@ -144,6 +144,8 @@ struct Ctx {
   int64_t launches = 0;
   int64_t gram_chunk_rows = 4096;
   int gram_pair = 1;  // CTA-pair (cta_group::2) Gram kernel
+  int precision = 0;  // KS_PRECISION_TF32 (0) or KS_PRECISION_F16 (1: fp16 slab / residual / increment operands, kind::f16;
+                      // BlockLeastSquares on generated (cosine) features only, everything else stays tf32)
   int reserve_sms = 8; // SMs the persistent look-ahead kernel leaves to the critical chain
   int custom_solve = 0; // experimental: 1 = chol_solve_kernel (single launch; 10.8 ms at b=4096,k=1000 vs 4.4 ms for
                         // cusolverDnDpotrs alone / ~11 ms when potrs shares the SMs), 0 = cusolverDnDpotrs
@@ -172,6 +174,7 @@ struct Ctx {
   void collect_spans(double out_ms[PH_COUNT]);
   void allreduce_f32(float* p, size_t n, bool prep = false);
   void allreduce_f64(double* p, size_t n, bool prep = false);
+  void allreduce_max_u32(unsigned* p, size_t n);
   void ensure_solver();
   void potrf(double* H, int n, int info_slot, cudaStream_t s);
   void potrs(const double* H, int n, double* B, int nrhs, int info_slot, cudaStream_t s);
@@ -198,14 +201,20 @@ struct FeatSrc {
 void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out);
 // slab[rows x lds] = round_tf32(features[row_begin : row_begin+rows, c0 : c0+cols] - shift)   (shift may be the zero vector)
 // colsum (optional, fp32[cols], must be zeroed): receives the column sums of the stored slab
-void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, float* slab, int64_t lds,
-                  int64_t row_begin, int64_t rows, bool round_out = true, float* colsum = nullptr, cudaStream_t st = nullptr);
+// out16: the slab is fp16 (lds in fp16 elements), generated features only
+void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, void* slab, int64_t lds,
+                  int64_t row_begin, int64_t rows, bool round_out = true, float* colsum = nullptr, cudaStream_t st = nullptr,
+                  bool out16 = false);
 const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, bool pair, int* num_tiles);
-void launch_gram_block(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* R, int64_t ldr, int kcols,
-                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c, cudaStream_t st = nullptr);
+// f16: slab and R are fp16 matrices (leading dimensions in elements); G / C stay fp32
+void launch_gram_block(Ctx& c, const void* slab, int64_t lds, int64_t rows, int b, const void* R, int64_t ldr, int kcols,
+                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c, cudaStream_t st = nullptr,
+                       bool f16 = false);
 // out[rows x k] (+)= (epi == EPI_UPDATE ? -1 : +1) * slab[rows x b] * bop[k x b]^T + cbias   (reduce: add into out)
-void launch_update(Ctx& c, const float* slab, int64_t lds, int64_t rows, int b, const float* bop, int64_t ldb, int k,
-                   float* out, int64_t ldo, const float* cbias, int epi, bool reduce, cudaStream_t st = nullptr);
+// f16: slab and bop are fp16; the product is multiplied by *acc_scale_ptr (device scalar, may be null) before the epilogue
+void launch_update(Ctx& c, const void* slab, int64_t lds, int64_t rows, int b, const void* bop, int64_t ldb, int k,
+                   float* out, int64_t ldo, const float* cbias, int epi, bool reduce, cudaStream_t st = nullptr,
+                   bool f16 = false, const float* acc_scale_ptr = nullptr);
 
 int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, double w, int64_t nf_opt);
 

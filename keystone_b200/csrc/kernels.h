@@ -26,12 +26,15 @@ struct GramLaunch {
   int chunk_rows;  // split of the contraction across CTAs (multiple of kGramStageRows)
   int n_valid0, n_valid1;  // valid output columns per target (whole 32-column chunks beyond are skipped)
   int pair;                // 1: CTA-pair kernel (tiles are 256 x 512), 0: single-CTA kernel (tiles are 128 x 256)
+  int f16 = 0;             // 1: operands are fp16 (kind::f16, CTA-pair kernel, 64-row stages), 0: tf32
 };
 enum { KM_FLAG_NO_ROUND = 1, KM_FLAG_REDUCE = 2 };
 struct KmParams {
   const float* vec0;  // EPI_COS: bias;  EPI_UPDATE / EPI_APPLY: per-column constant
   const float* vec1;  // EPI_COS: shift
   float* colsum;      // EPI_COS: if non-null, colsum[n] += sum over valid rows of the stored values (fp32 atomics)
+  float acc_scale = 1.f;    // the accumulator is multiplied by this before the epilogue (undoes power-of-two operand scaling)
+  const float* acc_scale_ptr = nullptr;  // optional device scalar multiplied into acc_scale (scale chosen on the device)
   int M, N, K;
   int flags;  // KM_FLAG_NO_ROUND: EPI_COS keeps fp32;  KM_FLAG_REDUCE: add into the output instead of overwriting it
 };
@@ -42,9 +45,14 @@ struct KmLaunch {
   int epi;
   int num_sms;
   int pair;  // 1: CTA-pair kernel (EPI_UPDATE / EPI_APPLY; tmB box is {32, 128}), 0: single-CTA persistent kernel
+  int f16 = 0;   // 1: fp16 operands (EPI_UPDATE / EPI_APPLY on CTA pairs; boxes are {64, 128} fp16)
+  int out16 = 0; // 1: EPI_COS writes the slab as fp16 (tmOut: {32, 32} fp16 boxes, no swizzle)
 };
 
 int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool atom32 = false);
+enum { TMAP_SW128 = 0, TMAP_SW128_ATOM32 = 1, TMAP_NONE = 2 };
+int make_tmap_any(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                  int elem_bytes, int swizzle);
 cudaError_t launch_gram(const GramLaunch& g, cudaStream_t st);
 cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st);
 unsigned int read_wait_timeout_flag();
@@ -77,7 +85,7 @@ void launch_build_system(const float* G, int ldg, const double* delta, double n_
                          cudaStream_t st);
 // RHS (fp64 column-major b x k, ld = b) = C[:, :k] - n * delta * rbar^T - lam * Wold
 void launch_build_rhs(const float* C, int ldc, const double* delta, const double* rsum, double n_total, double lam,
-                      const double* Wold, double* rhs, int b, int k, cudaStream_t st);
+                      const double* Wold, double* rhs, int b, int k, cudaStream_t st, const float* c_scale = nullptr);
 // Wmodel += dW;  Bop_hi/lo [kpad x ldb] = split(dW^T);  cbias[c] = sum_f delta[f] dW[f][c]
 void launch_pack_update(const double* dW, double* Wmodel, const double* delta, float* bop_hi, float* bop_lo, int ldb,
                         float* cbias, int b, int k, int kpad, cudaStream_t st);
@@ -92,5 +100,14 @@ void launch_normal_f32(float* dst, int64_t ld, int64_t rows, int cols, uint64_t 
                        float stddev, cudaStream_t st);
 void launch_w_to_operand(const double* W_colmajor, int64_t n_out, int64_t n_in, float* dst, int64_t ld, cudaStream_t st);
 void launch_f64_to_f32_vec(const double* src, float* dst, int64_t n, cudaStream_t st);
+// ---- fp16 operand path: device-chosen power-of-two scales (scale[0] = 2^e, scale[1] = 2^-e) and fp16 operand packers
+void launch_max_abs_f32(const float* p, int64_t ld, int64_t rows, int cols, unsigned* maxbits, cudaStream_t st);
+void launch_max_abs_f64(const double* p, int64_t n, unsigned* maxbits, cudaStream_t st);
+void launch_pow2_scale(const unsigned* maxbits, float target, float* scale, cudaStream_t st);
+void launch_f32_to_f16_rows(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int64_t cols, cudaStream_t st);
+void launch_round_colsum16(const float* R, void* R16, int64_t ld, int64_t rows, int k, double* sums, const float* scale,
+                           cudaStream_t st);
+void launch_pack_update16(const double* dW, double* Wmodel, const double* delta, void* bop16, int ldb, float* cbias, int b, int k,
+                          int kpad, const float* scale, cudaStream_t st);
 
 }  // namespace ks

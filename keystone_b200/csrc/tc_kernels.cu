@@ -169,24 +169,34 @@ gram_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // traffic per MMA drops from 12 KB (1-CTA 128 x 256) to 8 KB and the L2 -> SM traffic halves; the 1-CTA kernel
 // saturates shared-memory bandwidth at ~2/3 of the tensor peak (profiles/README.md).
 // =====================================================================================
-template <int SR, int STAGES>
+// F16 = true: fp16 operands (kind::f16, K = 16 per MMA, 64-element = 128 B boxes, plain 128 B swizzle, 64-row stages);
+// F16 = false: tf32 (fp32 containers, K = 8, 32-element boxes, SWIZZLE_128B_BASE32B, 32-row stages).  Same bytes per stage.
+template <bool F16, int STAGES>
 struct Gram2Cfg {
   static constexpr int PM = 256, PN = 512;          // pair tile
-  static constexpr int A_BYTES = 128 * SR * 4;      // this CTA's 128 columns of A
-  static constexpr int BH_BYTES = 128 * SR * 4;     // this CTA's half (128 columns) of one N=256 B tile
+  static constexpr int SR = F16 ? 64 : 32;          // rows (K) per stage
+  static constexpr int ES = F16 ? 2 : 4;            // operand element size
+  static constexpr int CW = 128 / ES;               // columns per TMA box (128 B)
+  static constexpr int NBOX = 128 / CW;             // boxes per 128 operand columns
+  static constexpr int KI = F16 ? 16 : 8;           // K per MMA instruction
+  static constexpr int A_BYTES = 128 * SR * ES;     // this CTA's 128 columns of A
+  static constexpr int BH_BYTES = 128 * SR * ES;    // this CTA's half (128 columns) of one N=256 B tile
   static constexpr int STAGE_BYTES = A_BYTES + 2 * BH_BYTES;
   static constexpr int BOX_BYTES = SR * 128;
+  static constexpr int KSTEP_BYTES = KI * 128;      // start-address advance per MMA
+  static constexpr int SBO = F16 ? 1024 : 512;      // distance between the K groups inside one MMA
   static constexpr int STAGING_BYTES = 4 * 4096;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;
 };
 
-template <int SR, int STAGES>
+template <bool F16, int STAGES>
 __global__ void __launch_bounds__(kGramThreads, 1)
 gram2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                 const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmOut0,
                 const __grid_constant__ CUtensorMap tmOut1, const GramTile* __restrict__ tiles, int num_tiles, int rows,
                 int chunk_rows, int n_valid0, int n_valid1) {
-  using Cfg = Gram2Cfg<SR, STAGES>;
+  using Cfg = Gram2Cfg<F16, STAGES>;
+  constexpr int SR = Cfg::SR;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
@@ -243,18 +253,19 @@ gram2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         uint8_t* sB = sA + Cfg::A_BYTES;
         const int r = row0 + ks * SR;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tma_load_2d_pair(sA + i * Cfg::BOX_BYTES, &tmA, &full_bar[s], m0 + 32 * i, r);
+        for (int i = 0; i < Cfg::NBOX; ++i) tma_load_2d_pair(sA + i * Cfg::BOX_BYTES, &tmA, &full_bar[s], m0 + Cfg::CW * i, r);
 #pragma unroll
         for (int h = 0; h < 2; ++h)
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < Cfg::NBOX; ++i)
             tma_load_2d_pair(sB + h * Cfg::BH_BYTES + i * Cfg::BOX_BYTES, tmB, &full_bar[s],
-                             n0 + h * 256 + static_cast<int>(rank) * 128 + 32 * i, r);
+                             n0 + h * 256 + static_cast<int>(rank) * 128 + Cfg::CW * i, r);
       }
     }
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {
-      constexpr uint32_t idesc = make_idesc_tf32(256, 256, 1, 1);
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(256, 256, 1, 1) : make_idesc_tf32(256, 256, 1, 1);
+      constexpr uint32_t layout = F16 ? kLayoutSw128 : kLayoutSw128Base32;
       for (int ks = 0; ks < ksteps; ++ks) {
         const int s = ks % STAGES;
         const uint32_t ph = (ks / STAGES) & 1;
@@ -263,12 +274,13 @@ gram2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t sA = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t sB = sA + Cfg::A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < SR / 8; ++kk) {
-          const uint64_t ad = make_smem_desc(sA + kk * 1024, Cfg::BOX_BYTES, 512, kLayoutSw128Base32);
+        for (int kk = 0; kk < SR / Cfg::KI; ++kk) {
+          // MN-major: 128 B-wide MN chunks are BOX_BYTES apart (LBO); K groups inside one MMA are SBO apart
+          const uint64_t ad = make_smem_desc(sA + kk * Cfg::KSTEP_BYTES, Cfg::BOX_BYTES, Cfg::SBO, layout);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const uint64_t bd = make_smem_desc(sB + h * Cfg::BH_BYTES + kk * 1024, Cfg::BOX_BYTES, 512, kLayoutSw128Base32);
-            umma_tf32_pair(tmem_base + h * 256, ad, bd, idesc, (ks | kk) != 0);
+            const uint64_t bd = make_smem_desc(sB + h * Cfg::BH_BYTES + kk * Cfg::KSTEP_BYTES, Cfg::BOX_BYTES, Cfg::SBO, layout);
+            umma_pair<F16>(tmem_base + h * 256, ad, bd, idesc, (ks | kk) != 0);
           }
         }
         umma_commit_pair(&empty_bar[s]);
@@ -316,12 +328,13 @@ gram2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // =====================================================================================
 static constexpr int kKmThreads = 320;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-9: epilogue (2 per TMEM lane quarter)
 
-template <int BN, int STAGES>
+template <bool F16, int BN, int STAGES>
 struct KmCfg {
   static constexpr int BM = 128;
-  static constexpr int BK = 32;  // 32 fp32 = 128 B = one swizzle row
-  static constexpr int A_BYTES = BM * BK * 4;
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int BK = F16 ? 64 : 32;  // K elements per stage: 128 B = one swizzle row
+  static constexpr int ES = F16 ? 2 : 4;
+  static constexpr int A_BYTES = BM * BK * ES;
+  static constexpr int B_BYTES = BN * BK * ES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = 8 * 4096;  // one 32 x 32 fp32 chunk per epilogue warp
   static constexpr int VEC_BYTES = 8 * 256 * 4;   // per-warp bias / shift vectors
@@ -341,11 +354,31 @@ __device__ __forceinline__ float cos_reduced(float x) {
   return __cosf(r);
 }
 
-template <int EPI, int BN, int STAGES>
+// fp16 flavour of the staging: thread `lane` owns row `lane` of a 32 x 32 chunk, stored as 64 B rows without swizzle
+// (the matching tensor map is {32, 32} fp16, SWIZZLE_NONE).
+__device__ __forceinline__ void stage_row_f16(uint8_t* buf, int lane, const float (&o)[32]) {
+  uint4* row = reinterpret_cast<uint4*>(buf + lane * 64);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    __half2 h0 = __floats2half2_rn(o[8 * c + 0], o[8 * c + 1]);
+    __half2 h1 = __floats2half2_rn(o[8 * c + 2], o[8 * c + 3]);
+    __half2 h2 = __floats2half2_rn(o[8 * c + 4], o[8 * c + 5]);
+    __half2 h3 = __floats2half2_rn(o[8 * c + 6], o[8 * c + 7]);
+    uint4 v;
+    v.x = *reinterpret_cast<uint32_t*>(&h0);
+    v.y = *reinterpret_cast<uint32_t*>(&h1);
+    v.z = *reinterpret_cast<uint32_t*>(&h2);
+    v.w = *reinterpret_cast<uint32_t*>(&h3);
+    row[c] = v;
+  }
+}
+
+// F16: fp16 operands (kind::f16); OUT16 (EPI_COS only): the slab is written as fp16 (tmOut: {32, 32} fp16 boxes, no swizzle).
+template <int EPI, bool F16, bool OUT16, int BN, int STAGES>
 __global__ void __launch_bounds__(kKmThreads, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmOut, KmParams p) {
-  using Cfg = KmCfg<BN, STAGES>;
+  using Cfg = KmCfg<F16, BN, STAGES>;
   static_assert(BN == 256, "epilogue column split assumes BN == 256");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -410,7 +443,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc_tf32(Cfg::BM, BN, 0, 0);
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(Cfg::BM, BN, 0, 0) : make_idesc_tf32(Cfg::BM, BN, 0, 0);
       uint32_t it = 0, tl = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
         const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
@@ -425,11 +458,12 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           const uint32_t sA = smem_u32(smem + s * Cfg::STAGE_BYTES);
           const uint32_t sB = sA + Cfg::A_BYTES;
 #pragma unroll
-          for (int kk = 0; kk < Cfg::BK / 8; ++kk) {
-            // K-major, 128B swizzle: 8-row groups are 1024 B apart (SBO); K advances 32 B inside the swizzle row
+          for (int kk = 0; kk < 4; ++kk) {
+            // K-major, 128B swizzle: 8-row groups are 1024 B apart (SBO); K advances 32 B (8 tf32 / 16 fp16) per MMA
             const uint64_t ad = make_smem_desc_sw128(sA + kk * 32, 16, 1024);
             const uint64_t bd = make_smem_desc_sw128(sB + kk * 32, 16, 1024);
-            umma_tf32(d_tmem, ad, bd, idesc, (ks | kk) != 0);
+            if (F16) umma_f16(d_tmem, ad, bd, idesc, (ks | kk) != 0);
+            else umma_tf32(d_tmem, ad, bd, idesc, (ks | kk) != 0);
           }
           umma_commit(&empty_bar[s]);
         }
@@ -444,6 +478,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     float* v0s = vec_smem + ew * 256;  // this warp's 128 vec0 values
     float* v1s = v0s + 128;            // and 128 vec1 values
     uint8_t* buf = staging + ew * 4096;
+    const float ascale = p.acc_scale_ptr ? __ldg(p.acc_scale_ptr) * p.acc_scale : p.acc_scale;
     uint32_t tl = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
       const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
@@ -470,15 +505,16 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (EPI == EPI_COS) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float val = cos_reduced(__uint_as_float(v[i]) + v0s[c0 + i]) - v1s[c0 + i];
-            o[i] = (p.flags & KM_FLAG_NO_ROUND) ? val : round_tf32(val);
+            const float val = cos_reduced(__uint_as_float(v[i]) * ascale + v0s[c0 + i]) - v1s[c0 + i];
+            // the value summed into colsum must be exactly the stored one: fp16 round trip / tf32 rounding
+            o[i] = OUT16 ? __half2float(__float2half_rn(val)) : ((p.flags & KM_FLAG_NO_ROUND) ? val : round_tf32(val));
           }
         } else if (EPI == EPI_UPDATE) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] - __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] - __uint_as_float(v[i]) * ascale;
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] + __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] + __uint_as_float(v[i]) * ascale;
         }
         if (EPI == EPI_COS && p.colsum != nullptr && m0 + q * 32 + lane >= p.M) {
 #pragma unroll
@@ -486,7 +522,8 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         if (lane == 0) bulk_wait_read0();  // the previous chunk's store has finished reading the staging buffer
         __syncwarp();
-        stage_row_sw128(buf, lane, o);
+        if (OUT16) stage_row_f16(buf, lane, o);
+        else stage_row_sw128(buf, lane, o);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -496,11 +533,16 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         if (EPI == EPI_COS && p.colsum != nullptr) {
           // column sums of the chunk straight from the staged copy: lane c adds column c over the 32 rows
-          // (row r keeps 16 B chunk j at (j ^ (r & 7)): 32 lanes read 32 distinct words of one 128 B row, no conflicts)
           float cs = 0.f;
+          if (OUT16) {
 #pragma unroll
-          for (int r = 0; r < 32; ++r)
-            cs += *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+            for (int r = 0; r < 32; ++r) cs += __half2float(*reinterpret_cast<const __half*>(buf + r * 64 + lane * 2));
+          } else {
+            // (row r keeps 16 B chunk j at (j ^ (r & 7)): 32 lanes read 32 distinct words of one 128 B row, no conflicts)
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              cs += *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+          }
           const int n = n0 + c0 + lane;
           if (n < p.N) atomicAdd(p.colsum + n, cs);
         }
@@ -525,22 +567,24 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // operand reads per MMA.  All 512 TMEM columns hold the accumulator, so the epilogue is not overlapped with the next
 // tile's main loop; with K = 4096 it is ~5 % of the tile time.
 // =====================================================================================
-template <int STAGES>
+template <bool F16, int STAGES>
 struct Km2Cfg {
-  static constexpr int PM = 256, PN = 512, BK = 32;
-  static constexpr int A_BYTES = 128 * BK * 4;
-  static constexpr int BH_BYTES = 128 * BK * 4;
+  static constexpr int PM = 256, PN = 512;
+  static constexpr int BK = F16 ? 64 : 32;  // K elements per stage (one 128 B swizzle row)
+  static constexpr int ES = F16 ? 2 : 4;
+  static constexpr int A_BYTES = 128 * BK * ES;
+  static constexpr int BH_BYTES = 128 * BK * ES;
   static constexpr int STAGE_BYTES = A_BYTES + 2 * BH_BYTES;
   static constexpr int STAGING_BYTES = 4 * 4096;
   static constexpr int VEC_BYTES = 4 * 512 * 4;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + VEC_BYTES + 1024 + 256;
 };
 
-template <int EPI, int STAGES>
+template <int EPI, bool F16, int STAGES>
 __global__ void __launch_bounds__(kGramThreads, 1)
 gemm2_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmOut, KmParams p) {
-  using Cfg = Km2Cfg<STAGES>;
+  using Cfg = Km2Cfg<F16, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
@@ -599,7 +643,7 @@ gemm2_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp == 1) {
     if (rank == 0 && elect_one()) {
-      constexpr uint32_t idesc = make_idesc_tf32(256, 256, 0, 0);
+      constexpr uint32_t idesc = F16 ? make_idesc_f16(256, 256, 0, 0) : make_idesc_tf32(256, 256, 0, 0);
       for (int ks = 0; ks < ksteps; ++ks) {
         const int s = ks % STAGES;
         const uint32_t ph = (ks / STAGES) & 1;
@@ -608,12 +652,12 @@ gemm2_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t sA = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint32_t sB = sA + Cfg::A_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < Cfg::BK / 8; ++kk) {
+        for (int kk = 0; kk < 4; ++kk) {  // 4 MMAs per 128 B of K (8 tf32 or 16 fp16 elements = 32 B each)
           const uint64_t ad = make_smem_desc_sw128(sA + kk * 32, 16, 1024);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const uint64_t bd = make_smem_desc_sw128(sB + h * Cfg::BH_BYTES + kk * 32, 16, 1024);
-            umma_tf32_pair(tmem_base + h * 256, ad, bd, idesc, (ks | kk) != 0);
+            umma_pair<F16>(tmem_base + h * 256, ad, bd, idesc, (ks | kk) != 0);
           }
         }
         umma_commit_pair(&empty_bar[s]);
@@ -624,6 +668,7 @@ gemm2_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;
     float* v0s = vec_smem + (warp - 2) * 512;
     uint8_t* buf = staging + (warp - 2) * 4096;
+    const float ascale = p.acc_scale_ptr ? __ldg(p.acc_scale_ptr) * p.acc_scale : p.acc_scale;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const int n = n0 + j * 32 + lane;
@@ -641,10 +686,10 @@ gemm2_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       float o[32];
       if (EPI == EPI_UPDATE) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] - __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] - __uint_as_float(v[i]) * ascale;
       } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] + __uint_as_float(v[i]);
+        for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] + __uint_as_float(v[i]) * ascale;
       }
       if (lane == 0) bulk_wait_read0();
       __syncwarp();
@@ -691,14 +736,23 @@ static PFN_encodeTiled get_encode_fn() {
 // 2D fp32 row-major matrix [rows x cols], leading dimension ld (floats); box = {32 floats, box_rows}, 128B swizzle
 // (atom32: the 32 B-atom flavour required by MN-major tf32 MMA operands).
 int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool atom32) {
+  return make_tmap_any(out, base, rows, cols, ld, 32, box_rows, 4, atom32 ? TMAP_SW128_ATOM32 : TMAP_SW128);
+}
+
+// General form: elem_bytes 4 (fp32 / tf32) or 2 (fp16); ld in elements; box {box_cols, box_rows}.
+int make_tmap_any(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                  int elem_bytes, int swizzle) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) return -1;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 4};
-  cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * static_cast<cuuint64_t>(elem_bytes)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+  const CUtensorMapSwizzle sw = swizzle == TMAP_SW128_ATOM32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                : swizzle == TMAP_SW128      ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                             : CU_TENSOR_MAP_SWIZZLE_NONE;
+  CUresult r = fn(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : -static_cast<int>(r) - 1000;
 }
@@ -721,10 +775,11 @@ static cudaError_t launch_gram_t(const GramLaunch& g, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int SR, int STAGES>
+template <bool F16, int STAGES>
 static cudaError_t launch_gram2_t(const GramLaunch& g, cudaStream_t st) {
-  using Cfg = Gram2Cfg<SR, STAGES>;
-  auto kern = gram2_tn_kernel<SR, STAGES>;
+  using Cfg = Gram2Cfg<F16, STAGES>;
+  if (g.chunk_rows % Cfg::SR != 0) return cudaErrorInvalidValue;
+  auto kern = gram2_tn_kernel<F16, STAGES>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -751,15 +806,16 @@ static cudaError_t launch_gram2_t(const GramLaunch& g, cudaStream_t st) {
 }
 
 cudaError_t launch_gram(const GramLaunch& g, cudaStream_t st) {
+  if (g.f16) return launch_gram2_t<true, 4>(g, st);
   if (g.chunk_rows % kGramStageRows != 0) return cudaErrorInvalidValue;
-  if (g.pair) return launch_gram2_t<kGramStageRows, 4>(g, st);
+  if (g.pair) return launch_gram2_t<false, 4>(g, st);
   return launch_gram_t<256, kGramStageRows, 4>(g, st);
 }
 
-template <int EPI, int BN, int STAGES>
+template <int EPI, bool F16, bool OUT16, int BN, int STAGES>
 static cudaError_t launch_km_t(const KmLaunch& k, cudaStream_t st) {
-  using Cfg = KmCfg<BN, STAGES>;
-  auto kern = gemm_kmajor_kernel<EPI, BN, STAGES>;
+  using Cfg = KmCfg<F16, BN, STAGES>;
+  auto kern = gemm_kmajor_kernel<EPI, F16, OUT16, BN, STAGES>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -775,10 +831,10 @@ static cudaError_t launch_km_t(const KmLaunch& k, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-template <int EPI, int STAGES>
+template <int EPI, bool F16, int STAGES>
 static cudaError_t launch_km2_t(const KmLaunch& k, cudaStream_t st) {
-  using Cfg = Km2Cfg<STAGES>;
-  auto kern = gemm2_kmajor_kernel<EPI, STAGES>;
+  using Cfg = Km2Cfg<F16, STAGES>;
+  auto kern = gemm2_kmajor_kernel<EPI, F16, STAGES>;
   static bool attr_done = false;
   if (!attr_done) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -805,12 +861,15 @@ static cudaError_t launch_km2_t(const KmLaunch& k, cudaStream_t st) {
 }
 
 cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st) {
-  if (k.pair && k.epi == EPI_UPDATE) return launch_km2_t<EPI_UPDATE, 4>(k, st);
-  if (k.pair && k.epi == EPI_APPLY) return launch_km2_t<EPI_APPLY, 4>(k, st);
+  if (k.f16 && k.epi == EPI_UPDATE) return launch_km2_t<EPI_UPDATE, true, 4>(k, st);
+  if (k.f16 && k.epi == EPI_APPLY) return launch_km2_t<EPI_APPLY, true, 4>(k, st);
+  if (k.out16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, false, true, 256, 3>(k, st);
+  if (k.pair && k.epi == EPI_UPDATE) return launch_km2_t<EPI_UPDATE, false, 4>(k, st);
+  if (k.pair && k.epi == EPI_APPLY) return launch_km2_t<EPI_APPLY, false, 4>(k, st);
   switch (k.epi) {
-    case EPI_COS: return launch_km_t<EPI_COS, 256, 3>(k, st);
-    case EPI_UPDATE: return launch_km_t<EPI_UPDATE, 256, 3>(k, st);
-    case EPI_APPLY: return launch_km_t<EPI_APPLY, 256, 3>(k, st);
+    case EPI_COS: return launch_km_t<EPI_COS, false, false, 256, 3>(k, st);
+    case EPI_UPDATE: return launch_km_t<EPI_UPDATE, false, false, 256, 3>(k, st);
+    case EPI_APPLY: return launch_km_t<EPI_APPLY, false, false, 256, 3>(k, st);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -243,8 +243,13 @@ class LinearMapper(BlockLinearMapper):
 
 class BlockLeastSquaresEstimator(LabelEstimator, WeightedNode):
     def __init__(self, block_size: int, num_iter: int, lam: float = 0.0, num_features_opt: Optional[int] = None,
-                 ctx: Optional[Context] = None):
+                 ctx: Optional[Context] = None, precision: str = "tf32"):
+        """precision: "tf32" (default) or "f16" -- fp16 operands for the three big GEMMs when the features are generated
+        cosine features (KS_PRECISION_F16 in include/keystone_b200.h); same mantissa, twice the tensor-core rate."""
         self.block_size, self.num_iter, self.lam, self.num_features_opt, self.ctx = block_size, num_iter, lam, num_features_opt, ctx
+        if precision not in ("tf32", "f16"):
+            raise ValueError("precision must be 'tf32' or 'f16'")
+        self.precision = precision
         self.weight = 3 * num_iter + 1  # BlockLinearMapper.scala:204
 
     def fit(self, data, labels) -> BlockLinearMapper:
@@ -254,7 +259,9 @@ class BlockLeastSquaresEstimator(LabelEstimator, WeightedNode):
         f, x, rfs, n = feature_source_args(ds)
         h = C.c_int64(0)
         check(ctx.handle, lib().ks_blockls_fit(ctx.handle, f, x, rfs, n, lb.handle, self.block_size, self.num_iter, self.lam,
-                                                self.num_features_opt or 0, _capi.KS_PRECISION_TF32, C.byref(h)))
+                                                self.num_features_opt or 0,
+                                                _capi.KS_PRECISION_F16 if self.precision == "f16" else _capi.KS_PRECISION_TF32,
+                                                C.byref(h)))
         return BlockLinearMapper(ctx, h.value)
 
     def cost(self, n: int, d: int, k: int, sparsity: float, num_machines: int, cpu_weight: float, mem_weight: float,

@@ -162,6 +162,92 @@ def test_blockls_fit_cosine_features_regenerated(ctx):
     W2, R2 = np.concatenate(m2.xs, 0), np.concatenate(xs2, 0)
     assert np.linalg.norm(W2 - R2) / np.linalg.norm(R2) < W_TOL
 
+# ------------------------------------------------------------------------------------ fp16 operand mode (KS_PRECISION_F16)
+@pytest.fixture()
+def ctx16(ctx):
+    ctx.set_option("precision", 1)
+    yield ctx
+    ctx.set_option("precision", 0)
+
+
+@pytest.mark.parametrize("n,m,kc", [(777, 200, 70), (64, 64, 64), (5000, 640, 257), (130, 1030, 5)])
+def test_gram_f16_exact_on_small_integers(ctx16, n, m, kc):
+    """Small integers are exact in fp16 and their sums exact in fp32: the kind::f16 Gram kernel must be bit-exact,
+    which pins its MN-major fp16 descriptors (SWIZZLE_128B, LBO = box, SBO = 1024, 2048 B per K = 16 step)."""
+    rng = np.random.default_rng(n)
+    A = rng.integers(-3, 4, (n, m)).astype(np.float64); B = rng.integers(-3, 4, (n, kc)).astype(np.float64)
+    G, Cm = _debug_gram(ctx16, A, B)
+    assert np.array_equal(G, A.T @ A), np.abs(G - A.T @ A).max()
+    assert np.array_equal(Cm, A.T @ B), np.abs(Cm - A.T @ B).max()
+
+
+def test_gram_f16_rounding(ctx16):
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((3000, 300)).astype(np.float16); B = rng.standard_normal((3000, 40)).astype(np.float16)
+    G, Cm = _debug_gram(ctx16, A.astype(np.float64), B.astype(np.float64))
+    A64, B64 = A.astype(np.float64), B.astype(np.float64)
+    assert np.abs(G - A64.T @ A64).max() < 5e-5 * (np.abs(A64).T @ np.abs(A64)).max() + 1e-5
+    assert np.abs(Cm - A64.T @ B64).max() < 5e-5 * (np.abs(A64).T @ np.abs(B64)).max() + 1e-5
+
+
+def _cosine_problem(ctx, seed, n, d_in, n_out, k, n_maps):
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((n, d_in))
+    cls = rng.integers(0, k, n)
+    params = [ko.cosine_random_features_params(d_in, n_out, 0.17, rng) for _ in range(n_maps)]
+    x = ctx.matrix(X.astype(np.float32))
+    rfs = [ks.CosineRandomFeatures(ctx, W, b) for W, b in params]
+    feats = ks.Pipeline.gather(rfs).andThen(ks.VectorCombiner())(x)
+    Xd = X.astype(np.float32).astype(np.float64)
+    F = np.concatenate([ko.cosine_random_features(Xd, W, b) for W, b in params], 1)
+    return feats, F, cls
+
+
+@pytest.mark.parametrize("bs,iters", [(256, 1), (200, 2)])
+def test_blockls_fit_f16_matches_oracle(ctx, bs, iters):
+    """Same problem and the same tolerance as the tf32 test above, with the fp16 operand path selected per fit."""
+    n, k = 4000, 10
+    feats, F, cls = _cosine_problem(ctx, 4, n, 44, 256, k, 3)
+    y = ctx.labels_from_classes(cls, k)
+    Y = ko.class_label_indicators(cls, k)
+    model = ks.BlockLeastSquaresEstimator(bs, iters, 2.0, precision="f16").fit(feats, y)
+    assert ctx.last_fit_stats()["mma"] == "f16"
+    xs, b0, mus = ko.block_ls_fit(F, Y, bs, iters, 2.0)
+    Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
+    rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
+    assert rel < W_TOL, rel
+    assert np.abs(np.concatenate(model.feature_means) - np.concatenate(mus)).max() < 1e-4
+    pred = model(feats).to_numpy()
+    ref = ko.block_linear_apply(F, xs, bs, b0, mus)
+    assert np.abs(pred - ref).max() < 5e-3
+
+
+def test_blockls_fit_f16_label_scale_invariance(ctx):
+    """fp16 has a 5-bit exponent: the residual and increment operands carry device-chosen power-of-two scales, so labels of
+    magnitude 1e-6 or 1e+5 (far outside fp16's comfortable range) must give the same relative accuracy."""
+    n, k = 3000, 4
+    feats, F, cls = _cosine_problem(ctx, 9, n, 30, 256, k, 2)
+    rng = np.random.default_rng(10)
+    Y0 = rng.standard_normal((n, k))
+    for scale in (1e-6, 1.0, 1e5):
+        Y = Y0 * scale
+        model = ks.BlockLeastSquaresEstimator(256, 1, 1.0, precision="f16").fit(feats, ctx.matrix(Y))
+        xs, b0, mus = ko.block_ls_fit(F, Y.astype(np.float32).astype(np.float64), 256, 1, 1.0)
+        Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
+        rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
+        assert rel < W_TOL, (scale, rel)
+
+
+def test_blockls_f16_falls_back_to_tf32_for_materialized_features(ctx):
+    rng = np.random.default_rng(12)
+    F = rng.standard_normal((1500, 300)) * 1e4     # far outside fp16's range once squared: must not be computed in fp16
+    Y = rng.standard_normal((1500, 3))
+    model = ks.BlockLeastSquaresEstimator(128, 1, 1.0, precision="f16").fit(ctx.matrix(F), ctx.matrix(Y))
+    assert ctx.last_fit_stats()["mma"] == "tf32x1"
+    xs, _, _ = ko.block_ls_fit(F.astype(np.float32).astype(np.float64), Y, 128, 1, 1.0)
+    Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
+    assert np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr) < W_TOL
+
 
 def test_linear_map_estimator_known_answer(ctx):
     """T/nodes/learning/LinearMapperSuite.scala:13-36 through the GPU path."""
