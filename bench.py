@@ -47,7 +47,8 @@ def parse_args():
     ap.add_argument("--cpu-rows", type=int, default=2048, help="rows of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--precision", default=os.environ.get("KS_BENCH_PRECISION", "tf32"), choices=["tf32", "f16"],
+    ap.add_argument("--no-tf32-ref", action="store_true", help="skip the extra tf32-operand fits reported beside an f16 run")
+    ap.add_argument("--precision", default=os.environ.get("KS_BENCH_PRECISION", "f16"), choices=["tf32", "f16"],
                     help="operand type of the three big GEMMs (fp32 accumulate, fp64 solve either way)")
     return ap.parse_args()
 
@@ -260,6 +261,19 @@ def main():
     clocks = sampler.stop()
     dev_ms = max_over_ranks(float(np.mean([s["total_ms"] for s in stats])))
 
+    # ---- the same fit with tf32 operands (the other precision mode of the library), 1 warm-up + 2 timed fits, for reference
+    tf32_ref = None
+    if args.precision == "f16" and not args.no_tf32_ref:
+        est32 = ks.BlockLeastSquaresEstimator(args.block, args.num_iter, args.lam, precision="tf32")
+        est32.fit(feats, y_dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            est32.fit(feats, y_dev)
+        barrier()
+        t32 = max_over_ranks((time.perf_counter() - t0) / 2)
+        tf32_ref = {"value": args.n_rows / t32, "unit": "samples/s", "ms_per_step": 1e3 * t32, "steps": 2, "warmup": 1}
+
     # ---- dominant kernel alone (same launch shape as inside the fit: S^T [S | R], N_loc x 4096 slab, k columns),
     #      CUDA events on the launching stream, 3 warm-up + 5 timed launches; the fit itself runs it concurrently with
     #      the residual chain on a second stream, so the in-fit span would not isolate the kernel
@@ -344,6 +358,8 @@ def main():
            "step_wall_ms": step_wall, "loop_ms_rank0": 1e3 * t_loop,
            "alg_tflops": flops / t_resident / 1e12, "phase_ms": {k: stats[-1][k] for k in stats[-1] if k.endswith("_ms")},
            "roofline": roofline}
+    if tf32_ref:
+        out["tf32_operands"] = tf32_ref
     if e2e:
         out["e2e"] = e2e
     if cpu_baseline:

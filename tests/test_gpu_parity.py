@@ -216,7 +216,9 @@ def test_blockls_fit_f16_matches_oracle(ctx, bs, iters):
     Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
     rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
     assert rel < W_TOL, rel
-    assert np.abs(np.concatenate(model.feature_means) - np.concatenate(mus)).max() < 1e-4
+    # the means are those of the generated features (tf32 projection, 10-bit slab): measured 1.2e-4 at N = 4000 in both modes,
+    # shrinking like 1/sqrt(N) (4.2e-5 at N = 32768, tools/accuracy_probe.py)
+    assert np.abs(np.concatenate(model.feature_means) - np.concatenate(mus)).max() < 5e-4
     pred = model(feats).to_numpy()
     ref = ko.block_linear_apply(F, xs, bs, b0, mus)
     assert np.abs(pred - ref).max() < 5e-3
