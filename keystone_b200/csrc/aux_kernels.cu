@@ -516,17 +516,20 @@ void launch_pow2_scale(const unsigned* maxbits, float target, float* scale, cuda
 }
 
 __global__ void f32_to_f16_rows_kernel(const float* __restrict__ src, int64_t src_ld, __half* __restrict__ dst, int64_t dst_ld,
-                                       int64_t rows, int64_t cols) {
+                                       int64_t rows, int64_t cols, const float* __restrict__ scale) {
   const int64_t total = rows * dst_ld;
+  const float sc = scale ? __ldg(scale) : 1.f;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t r = i / dst_ld, c = i - r * dst_ld;
-    dst[i] = __float2half_rn(c < cols ? src[r * src_ld + c] : 0.f);
+    dst[i] = __float2half_rn(c < cols ? src[r * src_ld + c] * sc : 0.f);
   }
 }
-void launch_f32_to_f16_rows(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int64_t cols, cudaStream_t st) {
+void launch_f32_to_f16_rows(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int64_t cols, cudaStream_t st,
+                            const float* scale) {
   if (rows == 0) return;
-  f32_to_f16_rows_kernel<<<grid_for(rows * dst_ld, 256), 256, 0, st>>>(src, src_ld, static_cast<__half*>(dst), dst_ld, rows, cols);
+  f32_to_f16_rows_kernel<<<grid_for(rows * dst_ld, 256), 256, 0, st>>>(src, src_ld, static_cast<__half*>(dst), dst_ld, rows, cols,
+                                                                       scale);
 }
 
 // fp16 twin of round_colsum_kernel: R16[:, :k] = fp16(R * scale[0]), columns >= k zero; sums as before (of R itself)

@@ -337,7 +337,9 @@ void Ctx::check_async(const char* what) {
 }
 
 // ------------------------------------------------------------------------------------ feature source
-void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out) {
+__global__ void combine_scales_kernel(const float* a, const float* b, float* out) { out[0] = a[1] * b[1]; }
+
+void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out, bool want_f16) {
   if (features != 0) {
     if (x_in != 0 || n_rfs != 0) throw KsError{KS_ERR_INVALID, "pass either features or (x_in, rfs), not both"};
     out.F = &c.matrix(features);
@@ -384,6 +386,26 @@ void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, i
   launch_center_round(out.X->d, out.X->ld, 0, out.zeros.as<float>(), out.xop.as<float>(), nullptr, out.X->ld, out.n_rows,
                       static_cast<int>(out.X->cols), c.st);
   c.launches += 1;
+  if (want_f16 && c.proj_f16) {
+    // fp16 copies of X and W for the kind::f16 projection.  Each carries its own power-of-two scale (largest magnitude
+    // mapped into [2048, 4096]), so the input units do not matter; the product of the two inverse scales is applied to the
+    // fp32 accumulator in the epilogue.  Same 10-bit mantissa as the tf32 operands above.
+    out.pscale.alloc(sizeof(float) * 8);  // [0] 1/(sx*sw)  [1] maxbits x  [2] maxbits w  [4,5] x {s, 1/s}  [6,7] w {s, 1/s}
+    KS_CUDA(cudaMemsetAsync(out.pscale.p, 0, out.pscale.bytes, c.st));
+    float* ps = out.pscale.as<float>();
+    unsigned* mb = out.pscale.as<unsigned>();
+    launch_max_abs_f32(out.X->d, out.X->ld, out.n_rows, static_cast<int>(out.X->cols), mb + 1, c.st);
+    launch_max_abs_f32(out.Wall, out.ldw, total, static_cast<int>(out.d_in), mb + 2, c.st);
+    launch_pow2_scale(mb + 1, 4096.f, ps + 4, c.st);
+    launch_pow2_scale(mb + 2, 4096.f, ps + 6, c.st);
+    combine_scales_kernel<<<1, 1, 0, c.st>>>(ps + 4, ps + 6, ps);
+    out.xop16.alloc(2 * static_cast<size_t>(std::max<int64_t>(out.n_rows, 1) * out.X->ld));
+    out.w16.alloc(2 * static_cast<size_t>(total * out.ldw));
+    launch_f32_to_f16_rows(out.X->d, out.X->ld, out.xop16.p, out.X->ld, out.n_rows, out.X->cols, c.st, ps + 4);
+    launch_f32_to_f16_rows(out.Wall, out.ldw, out.w16.p, out.ldw, total, out.d_in, c.st, ps + 6);
+    c.launches += 7;
+    out.proj16 = true;
+  }
 }
 
 static void tmap16_or_throw(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
@@ -415,8 +437,16 @@ void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* s
     return;
   }
   KmLaunch k;
-  tmap_or_throw(&k.tmA, src.xop.as<float>() + row_begin * src.X->ld, rows, src.d_in, src.X->ld, 128);
-  tmap_or_throw(&k.tmB, src.Wall + c0 * src.ldw, cols, src.d_in, src.ldw, 256);
+  if (out16 && src.proj16) {  // fp16 operands: 64 K-elements (128 B) per box row
+    tmap16_or_throw(&k.tmA, static_cast<const uint16_t*>(src.xop16.p) + row_begin * src.X->ld, rows, src.d_in, src.X->ld, 64, 128,
+                    TMAP_SW128);
+    tmap16_or_throw(&k.tmB, static_cast<const uint16_t*>(src.w16.p) + c0 * src.ldw, cols, src.d_in, src.ldw, 64, 256, TMAP_SW128);
+    k.f16 = 1;
+    k.p.acc_scale_ptr = src.pscale.as<float>();
+  } else {
+    tmap_or_throw(&k.tmA, src.xop.as<float>() + row_begin * src.X->ld, rows, src.d_in, src.X->ld, 128);
+    tmap_or_throw(&k.tmB, src.Wall + c0 * src.ldw, cols, src.d_in, src.ldw, 256);
+  }
   if (out16) tmap16_or_throw(&k.tmOut, slab_v, rows, cols, lds, 32, 32, TMAP_NONE);
   else tmap_or_throw(&k.tmOut, slab, rows, cols, lds, 32);
   k.out16 = out16 ? 1 : 0;
@@ -472,6 +502,7 @@ void launch_gram_block(Ctx& c, const void* slab, int64_t lds, int64_t rows, int 
   int nt = 0;
   g.pair = f16 ? 1 : c.gram_pair;
   g.f16 = f16 ? 1 : 0;
+  g.epi_multi = c.epi_multi;
   g.tiles = gram_tiles(c, b, kcols, with_g, with_c, g.pair != 0, &nt);
   g.num_tiles = nt;
   const int stage_rows = f16 ? 64 : kGramStageRows;
@@ -523,7 +554,7 @@ void launch_update(Ctx& c, const void* slab, int64_t lds, int64_t rows, int b, c
   u.p.M = static_cast<int>(rows);
   u.p.N = k;
   u.p.K = b;
-  u.p.flags = reduce ? KM_FLAG_REDUCE : 0;
+  u.p.flags = (reduce ? KM_FLAG_REDUCE : 0) | ((u.pair && c.epi_multi) ? KM_FLAG_EPI_MULTI : 0);
   u.epi = epi;
   u.num_sms = c.num_sms;
   KS_CUDA(launch_kmajor(u, st));
@@ -1066,6 +1097,8 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
       if (v >= kGramStageRows) c->gram_chunk_rows = v;
     }
     if (const char* e = getenv("KS_GRAM_PAIR")) c->gram_pair = atoi(e) != 0;
+    if (const char* e = getenv("KS_EPI_MULTI")) c->epi_multi = atoi(e) != 0;
+    if (const char* e = getenv("KS_PROJ_F16")) c->proj_f16 = atoi(e) != 0;
     if (const char* e = getenv("KS_PRECISION")) c->precision = (atoi(e) == 1 || !strcmp(e, "f16")) ? KS_PRECISION_F16 : KS_PRECISION_TF32;
     if (const char* e = getenv("KS_CUSTOM_SOLVE")) c->custom_solve = atoi(e) != 0;
     if (const char* e = getenv("KS_RESERVE_SMS")) c->reserve_sms = std::max(0, std::min(140, atoi(e)));
@@ -1154,6 +1187,8 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     if (n == "gram_chunk_rows" && value >= kGramStageRows) c.gram_chunk_rows = value;
     else if (n == "sample_rows" && value >= 1) c.sample_rows = value;
     else if (n == "gram_pair") c.gram_pair = value != 0;
+    else if (n == "epi_multi") c.epi_multi = value != 0;
+    else if (n == "proj_f16") c.proj_f16 = value != 0;
     else if (n == "precision" && (value == KS_PRECISION_TF32 || value == KS_PRECISION_F16)) c.precision = static_cast<int>(value);
     else if (n == "custom_solve") c.custom_solve = value != 0;
     else if (n == "reserve_sms" && value >= 0 && value < 148) c.reserve_sms = static_cast<int>(value);
@@ -1329,7 +1364,7 @@ KS_API int32_t ks_blockls_fit(int64_t ctx, int64_t features, int64_t x_in, const
     if (precision_mode != KS_PRECISION_TF32 && precision_mode != KS_PRECISION_F16)
       throw KsError{KS_ERR_INVALID, "unsupported precision_mode"};
     FeatSrc src;
-    make_feat_src(c, features, x_in, rfs, n_rfs, src);
+    make_feat_src(c, features, x_in, rfs, n_rfs, src, precision_mode == KS_PRECISION_F16 || c.precision == KS_PRECISION_F16);
     const int prec = c.precision == KS_PRECISION_F16 ? KS_PRECISION_F16 : precision_mode;  // the context option overrides
     *out_model = fit_blockls(c, src, c.matrix(labels), block_size, num_iter, lambda, num_features_or_0, prec);
   });

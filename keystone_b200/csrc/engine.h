@@ -144,6 +144,8 @@ struct Ctx {
   int64_t launches = 0;
   int64_t gram_chunk_rows = 4096;
   int gram_pair = 1;  // CTA-pair (cta_group::2) Gram kernel
+  int epi_multi = 1;  // CTA-pair kernels: 8 rotating epilogue staging buffers per warp (0: one buffer, store-and-wait)
+  int proj_f16 = 1;   // fp16 mode: the projection GEMM X W^T runs with fp16 operands too (0: tf32 operands, fp16 slab)
   int precision = 0;  // KS_PRECISION_TF32 (0) or KS_PRECISION_F16 (1: fp16 slab / residual / increment operands, kind::f16;
                       // BlockLeastSquares on generated (cosine) features only, everything else stays tf32)
   int reserve_sms = 8; // SMs the persistent look-ahead kernel leaves to the critical chain
@@ -191,6 +193,10 @@ struct FeatSrc {
   Matrix* F = nullptr;
   Matrix* X = nullptr;
   DevBuf xop;   // tf32-rounded copy of X (GEMM operand)
+  // fp16 operand mode: X and the projection weights as fp16, each multiplied by a device-chosen power of two;
+  // pscale[0] = 1 / (x scale * w scale) is applied to the accumulator before the cosine
+  DevBuf xop16, w16, pscale;
+  bool proj16 = false;
   DevBuf wcat, bcat;
   float* Wall = nullptr;
   float* ball = nullptr;
@@ -198,7 +204,8 @@ struct FeatSrc {
   int64_t D = 0, n_rows = 0;
   DevBuf zeros;  // max(D-block, d_in) zero floats
 };
-void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out);
+void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out,
+                   bool want_f16 = false);
 // slab[rows x lds] = round_tf32(features[row_begin : row_begin+rows, c0 : c0+cols] - shift)   (shift may be the zero vector)
 // colsum (optional, fp32[cols], must be zeroed): receives the column sums of the stored slab
 // out16: the slab is fp16 (lds in fp16 elements), generated features only

@@ -26,9 +26,10 @@ struct GramLaunch {
   int chunk_rows;  // split of the contraction across CTAs (multiple of kGramStageRows)
   int n_valid0, n_valid1;  // valid output columns per target (whole 32-column chunks beyond are skipped)
   int pair;                // 1: CTA-pair kernel (tiles are 256 x 512), 0: single-CTA kernel (tiles are 128 x 256)
+  int epi_multi = 1;       // CTA-pair kernel: rotate the epilogue through 8 staging buffers per warp (idle stage memory)
   int f16 = 0;             // 1: operands are fp16 (kind::f16, CTA-pair kernel, 64-row stages), 0: tf32
 };
-enum { KM_FLAG_NO_ROUND = 1, KM_FLAG_REDUCE = 2 };
+enum { KM_FLAG_NO_ROUND = 1, KM_FLAG_REDUCE = 2, KM_FLAG_EPI_MULTI = 4 };
 struct KmParams {
   const float* vec0;  // EPI_COS: bias;  EPI_UPDATE / EPI_APPLY: per-column constant
   const float* vec1;  // EPI_COS: shift
@@ -104,7 +105,8 @@ void launch_f64_to_f32_vec(const double* src, float* dst, int64_t n, cudaStream_
 void launch_max_abs_f32(const float* p, int64_t ld, int64_t rows, int cols, unsigned* maxbits, cudaStream_t st);
 void launch_max_abs_f64(const double* p, int64_t n, unsigned* maxbits, cudaStream_t st);
 void launch_pow2_scale(const unsigned* maxbits, float target, float* scale, cudaStream_t st);
-void launch_f32_to_f16_rows(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int64_t cols, cudaStream_t st);
+void launch_f32_to_f16_rows(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int64_t cols, cudaStream_t st,
+                            const float* scale = nullptr);  // optional device scalar multiplied in before the conversion
 void launch_round_colsum16(const float* R, void* R16, int64_t ld, int64_t rows, int k, double* sums, const float* scale,
                            cudaStream_t st);
 void launch_pack_update16(const double* dW, double* Wmodel, const double* delta, void* bop16, int ldb, float* cbias, int b, int k,

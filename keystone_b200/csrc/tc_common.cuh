@@ -102,6 +102,8 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// at most 7 of this thread's bulk groups may still be reading their shared-memory source (8 rotating staging buffers)
+__device__ __forceinline__ void bulk_wait_read7() { asm volatile("cp.async.bulk.wait_group.read 7;" ::: "memory"); }
 
 // Epilogue staging: thread `lane` owns row `lane` of a 32 x 32 fp32 chunk (128 B per row) and writes it into a
 // 4 KB, 1024 B-aligned shared buffer in the 128 B-swizzled order a {32, 32} SWIZZLE_128B tensor map expects

@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kGramThreads, 1)
 gram2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                 const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmOut0,
                 const __grid_constant__ CUtensorMap tmOut1, const GramTile* __restrict__ tiles, int num_tiles, int rows,
-                int chunk_rows, int n_valid0, int n_valid1) {
+                int chunk_rows, int n_valid0, int n_valid1, int epi_multi) {
   using Cfg = Gram2Cfg<F16, STAGES>;
   constexpr int SR = Cfg::SR;
   extern __shared__ uint8_t smem_raw[];
@@ -290,9 +290,13 @@ gram2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else {
     const int q = warp & 3;
     const int n_valid = tile.which ? n_valid1 : n_valid0;
-    uint8_t* buf = staging + (warp - 2) * 4096;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    // Once the accumulator is complete nobody reads or writes the operand stages of either CTA any more (every TMA load
+    // has landed and every MMA has retired), so the epilogue rotates through 8 staging buffers per warp carved out of the
+    // stage memory: 8 reduce-adds in flight per warp instead of one store-and-wait round trip per 32-column chunk.
+    uint8_t* buf0 = epi_multi ? smem + (warp - 2) * 32768 : staging + (warp - 2) * 4096;
+    static_assert(STAGES * Cfg::STAGE_BYTES >= 4 * 32768, "stage memory too small for the rotating epilogue buffers");
 #pragma unroll 1
     for (int c0 = 0; c0 < Cfg::PN; c0 += 32) {
       if (n0 + c0 >= n_valid) break;  // warp-uniform
@@ -302,7 +306,11 @@ gram2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       float o[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
-      if (lane == 0) bulk_wait_read0();
+      uint8_t* buf = epi_multi ? buf0 + ((c0 >> 5) & 7) * 4096 : buf0;
+      if (lane == 0) {
+        if (epi_multi) bulk_wait_read7();
+        else bulk_wait_read0();
+      }
       __syncwarp();
       stage_row_sw128(buf, lane, o);
       fence_proxy_async();
@@ -667,7 +675,9 @@ gemm2_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else {
     const int q = warp & 3;
     float* v0s = vec_smem + (warp - 2) * 512;
-    uint8_t* buf = staging + (warp - 2) * 4096;
+    const bool epi_multi = (p.flags & KM_FLAG_EPI_MULTI) != 0;  // rotating staging buffers in the idle stage memory (see gram2)
+    uint8_t* buf0 = epi_multi ? smem + (warp - 2) * 32768 : staging + (warp - 2) * 4096;
+    static_assert(STAGES * Cfg::STAGE_BYTES >= 4 * 32768, "stage memory too small for the rotating epilogue buffers");
     const float ascale = p.acc_scale_ptr ? __ldg(p.acc_scale_ptr) * p.acc_scale : p.acc_scale;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
@@ -691,7 +701,11 @@ gemm2_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] + __uint_as_float(v[i]) * ascale;
       }
-      if (lane == 0) bulk_wait_read0();
+      uint8_t* buf = epi_multi ? buf0 + ((c0 >> 5) & 7) * 4096 : buf0;
+      if (lane == 0) {
+        if (epi_multi) bulk_wait_read7();
+        else bulk_wait_read0();
+      }
       __syncwarp();
       stage_row_sw128(buf, lane, o);
       fence_proxy_async();
@@ -802,7 +816,7 @@ static cudaError_t launch_gram2_t(const GramLaunch& g, cudaStream_t st) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, g.tmA, g.tmB0, g.tmB1, g.tmOut0, g.tmOut1, g.tiles, g.num_tiles, g.rows, g.chunk_rows,
-                            g.n_valid0, g.n_valid1);
+                            g.n_valid0, g.n_valid1, g.epi_multi);
 }
 
 cudaError_t launch_gram(const GramLaunch& g, cudaStream_t st) {
@@ -863,6 +877,7 @@ static cudaError_t launch_km2_t(const KmLaunch& k, cudaStream_t st) {
 cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st) {
   if (k.f16 && k.epi == EPI_UPDATE) return launch_km2_t<EPI_UPDATE, true, 4>(k, st);
   if (k.f16 && k.epi == EPI_APPLY) return launch_km2_t<EPI_APPLY, true, 4>(k, st);
+  if (k.out16 && k.f16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, true, true, 256, 3>(k, st);
   if (k.out16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, false, true, 256, 3>(k, st);
   if (k.pair && k.epi == EPI_UPDATE) return launch_km2_t<EPI_UPDATE, false, 4>(k, st);
   if (k.pair && k.epi == EPI_APPLY) return launch_km2_t<EPI_APPLY, false, 4>(k, st);

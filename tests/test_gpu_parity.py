@@ -240,6 +240,29 @@ def test_blockls_fit_f16_label_scale_invariance(ctx):
         assert rel < W_TOL, (scale, rel)
 
 
+def test_blockls_fit_f16_input_scale_invariance(ctx):
+    """The fp16 projection operands (X and the random-feature weights) carry their own power-of-two scales: inputs in units
+    of 1e4 with weights in units of 1e-4 (products unchanged) must fit exactly like the O(1) problem."""
+    rng = np.random.default_rng(21)
+    n, d_in, n_out, k = 3000, 30, 256, 4
+    X = rng.standard_normal((n, d_in))
+    cls = rng.integers(0, k, n)
+    W, b = ko.cosine_random_features_params(d_in, n_out, 0.2, rng)
+    Y = ko.class_label_indicators(cls, k)
+    for sx in (1.0, 1e4, 1e-4):
+        Xs = (X * sx).astype(np.float32)
+        Ws = W / sx
+        rf = ks.CosineRandomFeatures(ctx, Ws, b)
+        feats = rf(ctx.matrix(Xs))
+        model = ks.BlockLeastSquaresEstimator(n_out, 1, 1.0, precision="f16").fit(feats, ctx.labels_from_classes(cls, k))
+        assert ctx.last_fit_stats()["mma"] == "f16"
+        F = ko.cosine_random_features(Xs.astype(np.float64), Ws.astype(np.float32).astype(np.float64), b)
+        xs, _, _ = ko.block_ls_fit(F, Y, n_out, 1, 1.0)
+        Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
+        rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
+        assert rel < W_TOL, (sx, rel)
+
+
 def test_blockls_f16_falls_back_to_tf32_for_materialized_features(ctx):
     rng = np.random.default_rng(12)
     F = rng.standard_normal((1500, 300)) * 1e4     # far outside fp16's range once squared: must not be computed in fp16

@@ -24,8 +24,8 @@ def main(n=262144, b=4096, k=1000, precs=(0, 1), chunks=(2048, 4096, 8192, 16384
 
 
 if __name__ == "__main__":
-    # no arguments: the sweep;  <rows> <tf32|f16> <chunk_rows>: one configuration (the ncu target: warm-up launches, then 5)
+    # no arguments: the sweep;  <rows> <tf32|f16> <chunk_rows[,chunk_rows...]>: one precision (the ncu target: warm-up launches, then 5)
     if len(sys.argv) == 4:
-        main(n=int(sys.argv[1]), precs=(1 if sys.argv[2] == "f16" else 0,), chunks=(int(sys.argv[3]),))
+        main(n=int(sys.argv[1]), precs=(1 if sys.argv[2] == "f16" else 0,), chunks=tuple(int(v) for v in sys.argv[3].split(",")))
     else:
         main()
