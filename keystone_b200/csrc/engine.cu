@@ -518,7 +518,12 @@ void launch_gram_block(Ctx& c, const void* slab, int64_t lds, int64_t rows, int 
     else g.tmB1 = g.tmA;
   }
   g.rows = static_cast<int>(rows);
+  // Rows of the contraction per CTA (pair).  Every chunk ends in a reduce-add of its 256 x 512 partial tile, so long
+  // chunks mean less reduce traffic and fewer, longer CTAs next to the critical chain's kernels; short chunks keep enough
+  // CTAs per launch to balance 74 CTA pairs when the rows are sharded.  Measured in the config-3 fit (tools/ab_fit.py,
+  // fp16 operands, N = 1M): 4096 -> 660 ms, 8192 -> 655 ms, 16384 -> 639 ms, 32768 -> 650 ms.
   int64_t chunk = c.gram_chunk_rows;
+  if (chunk <= 0) chunk = !f16 ? 4096 : rows >= 400000 ? 16384 : rows >= 200000 ? 8192 : 4096;
   chunk = std::max<int64_t>(stage_rows, chunk / stage_rows * stage_rows);
   g.chunk_rows = static_cast<int>(chunk);
   if (with_g) tmap_or_throw(&g.tmOut0, G, b, b, ldg, 32);
@@ -1184,7 +1189,7 @@ KS_API int32_t ks_ctx_synchronize(int64_t ctx) {
 KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
   return guard(ctx, [&](Ctx& c) {
     const std::string n = name ? name : "";
-    if (n == "gram_chunk_rows" && value >= kGramStageRows) c.gram_chunk_rows = value;
+    if (n == "gram_chunk_rows" && (value == 0 || value >= kGramStageRows)) c.gram_chunk_rows = value;
     else if (n == "sample_rows" && value >= 1) c.sample_rows = value;
     else if (n == "gram_pair") c.gram_pair = value != 0;
     else if (n == "epi_multi") c.epi_multi = value != 0;

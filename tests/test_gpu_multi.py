@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, id_holder, ret, inv_min_world):
+def _worker(rank, world, id_holder, ret, inv_min_world, precision):
     sys.path.insert(0, ROOT)
     os.environ["KS_INV_MIN_WORLD"] = str(inv_min_world)
     import keystone_b200 as ks
@@ -21,13 +21,15 @@ def _worker(rank, world, id_holder, ret, inv_min_world):
     n, d_in, n_out, k = 6001, 40, 256, 6
     X = rng.standard_normal((n, d_in)).astype(np.float32)
     cls = rng.integers(0, k, n)
-    params = [ko.cosine_random_features_params(d_in, n_out, 0.2, rng) for _ in range(2)]
+    X[: n // 2] *= 4.0   # the two ranks see inputs of different magnitude: their fp16 operand scales differ
+    params = [ko.cosine_random_features_params(d_in, n_out, 0.2 / 2, rng) for _ in range(2)]
     lo, hi = ks.shard_range(n, rank, world)
     ctx = ks.Context(device=rank, rank=rank, world_size=world, nccl_id=id_holder["id"])
     x = ctx.matrix(X[lo:hi]); y = ctx.labels_from_classes(cls[lo:hi], k)
     rfs = [ks.CosineRandomFeatures(ctx, W, b) for W, b in params]
     feats = ks.Pipeline.gather(rfs).andThen(ks.VectorCombiner())(x)
-    model = ks.BlockLeastSquaresEstimator(n_out, 2, 0.5).fit(feats, y)
+    model = ks.BlockLeastSquaresEstimator(n_out, 2, 0.5, precision=precision).fit(feats, y)
+    assert ctx.last_fit_stats()["mma"] == ("f16" if precision == "f16" else "tf32x1")
     W = np.concatenate(model.xs, 0)
     cost = model.compute_cost(feats, y, 0.5)
     if rank == 0:
@@ -42,15 +44,16 @@ def _worker(rank, world, id_holder, ret, inv_min_world):
     ctx.close()
 
 
-@pytest.mark.parametrize("inv_min_world", [4, 2], ids=["potrs-on-every-rank", "owner-inverse-broadcast"])
-def test_two_rank_fit_matches_oracle(inv_min_world):
+@pytest.mark.parametrize("inv_min_world,precision", [(4, "tf32"), (2, "tf32"), (4, "f16")],
+                         ids=["potrs-on-every-rank", "owner-inverse-broadcast", "fp16-operands"])
+def test_two_rank_fit_matches_oracle(inv_min_world, precision):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import keystone_b200 as ks
     mgr = mp.Manager()
     id_holder = mgr.dict(); ret = mgr.dict()
     id_holder["id"] = ks.Context.new_nccl_id()
-    mp.spawn(_worker, args=(2, id_holder, ret, inv_min_world), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, id_holder, ret, inv_min_world, precision), nprocs=2, join=True)
     assert ret["rel"] < 5e-3, ret["rel"]
     assert ret["cost_rel"] < 2e-3 and ret["b_err"] < 1e-5
     assert np.array_equal(ret["W0"], ret["W1"])      # redundant solves are bit-identical across ranks
