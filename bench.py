@@ -175,6 +175,9 @@ def cpu_info():
 
 # ----------------------------------------------------------------------------------------- main
 def main():
+    # keep stdout to the one JSON line: NCCL prints a version banner there when NCCL_DEBUG is VERSION (or unset on some builds)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -514,8 +514,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float val = cos_reduced(__uint_as_float(v[i]) * ascale + v0s[c0 + i]) - v1s[c0 + i];
-            // the value summed into colsum must be exactly the stored one: fp16 round trip / tf32 rounding
-            o[i] = OUT16 ? __half2float(__float2half_rn(val)) : ((p.flags & KM_FLAG_NO_ROUND) ? val : round_tf32(val));
+            // the value summed into colsum must be exactly the stored one: tf32 rounding here; the fp16 slab is rounded once,
+            // by the packed conversion of the staging step, and its column sums are taken from the staged halfs
+            o[i] = OUT16 ? val : ((p.flags & KM_FLAG_NO_ROUND) ? val : round_tf32(val));
           }
         } else if (EPI == EPI_UPDATE) {
 #pragma unroll
@@ -528,7 +529,14 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = 0.f;  // rows past the end must not pollute the column sums
         }
-        if (lane == 0) bulk_wait_read0();  // the previous chunk's store has finished reading the staging buffer
+        // an fp16 chunk is 2 KB: the 4 KB staging buffer holds two, so one store may still be reading while the next chunk
+        // is staged (4 chunks per tile: the halves alternate consistently from tile to tile)
+        uint8_t* const sbuf = buf;
+        uint8_t* buf = OUT16 ? sbuf + ((c0 >> 5) & 1) * 2048 : sbuf;
+        if (lane == 0) {  // the store that last used this staging slot has finished reading it
+          if (OUT16) bulk_wait_read1();
+          else bulk_wait_read0();
+        }
         __syncwarp();
         if (OUT16) stage_row_f16(buf, lane, o);
         else stage_row_sw128(buf, lane, o);

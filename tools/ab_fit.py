@@ -23,8 +23,10 @@ def main():
         rfs = [ks.CosineRandomFeatures.create(ctx, d_in, n_out, 0.0555, rng) for _ in range(nrf)]
         feats = ks.Pipeline.gather(rfs).andThen(ks.VectorCombiner())(x)
         est = ks.BlockLeastSquaresEstimator(n_out, 1, 1.0, precision="f16")
-        configs = [(1, 1, 4096), (0, 1, 4096), (0, 0, 4096), (1, 0, 4096), (0, 1, 8192), (0, 1, 16384), (1, 1, 16384), (0, 0, 16384),
-                   (0, 1, 32768)]
+        # (epi_multi, proj_f16, gram_chunk_rows) -- chunk 0 = the engine's own choice
+        configs = [(1, 1, 0), (1, 0, 0), (0, 1, 0), (1, 1, 4096)]
+        if len(sys.argv) > 2:
+            configs = [tuple(int(v) for v in c.split(",")) for c in sys.argv[2:]]
         for rep in range(2):
             for epi, proj, chunk in configs:
                 ctx.set_option("epi_multi", epi)
