@@ -76,12 +76,12 @@ JFN(jlong, cosineRfCreate)(JNIEnv* env, jobject, jlong ctx, jdoubleArray W, jdou
 }
 
 JFN(jlong, blockLsFit)(JNIEnv* env, jobject, jlong ctx, jlong features, jlong xIn, jlongArray rfs, jlong labels, jint blockSize,
-                       jint numIter, jdouble lambda, jlong numFeaturesOr0) {
+                       jint numIter, jdouble lambda, jlong numFeaturesOr0, jint precisionMode) {
   int64_t h = 0;
   jsize n = rfs ? env->GetArrayLength(rfs) : 0;
   jlong* r = n ? env->GetLongArrayElements(rfs, nullptr) : nullptr;
   int32_t rc = ks_blockls_fit(ctx, features, xIn, reinterpret_cast<const int64_t*>(r), n, labels, blockSize, numIter, lambda,
-                              numFeaturesOr0, KS_PRECISION_TF32, &h);
+                              numFeaturesOr0, precisionMode, &h);
   if (r) env->ReleaseLongArrayElements(rfs, r, JNI_ABORT);
   check(env, ctx, rc);
   return h;

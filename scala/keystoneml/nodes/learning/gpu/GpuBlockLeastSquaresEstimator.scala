@@ -17,7 +17,8 @@ import org.apache.spark.rdd.RDD
  * which is what this reference implementation shows.
  * Not compiled in the build image (no JVM).
  */
-class GpuBlockLeastSquaresEstimator(blockSize: Int, numIter: Int, lambda: Double = 0.0, numFeaturesOpt: Option[Int] = None)
+class GpuBlockLeastSquaresEstimator(blockSize: Int, numIter: Int, lambda: Double = 0.0, numFeaturesOpt: Option[Int] = None,
+    precisionMode: Int = 0)
   extends LabelEstimator[DenseVector[Double], DenseVector[Double], DenseVector[Double]] with WeightedNode {
 
   override val weight = (3 * numIter) + 1
@@ -38,7 +39,8 @@ class GpuBlockLeastSquaresEstimator(blockSize: Int, numIter: Int, lambda: Double
     try {
       val f = lib.matrixFromHost(ctx, flatten(feats), feats.length, feats(0).length)
       val y = lib.matrixFromHost(ctx, flatten(labels), labels.length, labels(0).length)
-      val m = lib.blockLsFit(ctx, f, 0L, null, y, blockSize, numIter, lambda, numFeaturesOpt.map(_.toLong).getOrElse(0L))
+      val m = lib.blockLsFit(ctx, f, 0L, null, y, blockSize, numIter, lambda, numFeaturesOpt.map(_.toLong).getOrElse(0L),
+        precisionMode)
       val nb = lib.modelNumBlocks(ctx, m)
       val k = labels(0).length
       val xs = (0 until nb).map { j =>

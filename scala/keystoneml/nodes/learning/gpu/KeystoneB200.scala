@@ -16,8 +16,9 @@ class KeystoneB200 extends Serializable {
   @native def matrixToHost(ctx: Long, m: Long): Array[Double]
   @native def matrixDestroy(ctx: Long, m: Long): Unit
   @native def cosineRfCreate(ctx: Long, w: Array[Double], b: Array[Double], nOut: Long, nIn: Long): Long
+  /** precisionMode: 0 = tf32 operands (KS_PRECISION_TF32), 1 = fp16 operands for generated cosine features (KS_PRECISION_F16). */
   @native def blockLsFit(ctx: Long, features: Long, xIn: Long, rfs: Array[Long], labels: Long,
-      blockSize: Int, numIter: Int, lambda: Double, numFeaturesOr0: Long): Long
+      blockSize: Int, numIter: Int, lambda: Double, numFeaturesOr0: Long, precisionMode: Int): Long
   @native def blockWlsFit(ctx: Long, features: Long, xIn: Long, rfs: Array[Long], labels: Long,
       blockSize: Int, numIter: Int, lambda: Double, mixtureWeight: Double, numFeaturesOr0: Long): Long
   @native def modelNumBlocks(ctx: Long, model: Long): Int
