@@ -152,7 +152,9 @@ def cpu_baseline_record(args, X, cls, params, nb, D):
     t_cpu, t_solve = cpu_reference_fit(args, X, cls, params, args.cpu_rows)
     per_row = (t_cpu - t_solve) / args.cpu_rows
     full = args.n_rows / (per_row * args.n_rows + t_solve)
-    return {"value": args.cpu_rows / t_cpu, "unit": "samples/s", "cores": cores, "cpu": cpu_model, "kind": "port",
+    # `value` is the metric at the benchmark's N: the per-row cost measured on the sample scaled to N rows plus the measured
+    # N-independent solves once (the sample alone would charge those 16 solves to 2048 rows and understate the CPU 2.6x)
+    return {"value": full, "unit": "samples/s", "sample_value": args.cpu_rows / t_cpu, "cores": cores, "cpu": cpu_model, "kind": "port",
             "sample": f"first {args.cpu_rows} rows, all {nb} blocks (D={D}, k={args.classes}); numpy/OpenBLAS fp64 oracle, "
                       f"{t_cpu:.1f} s of which {t_solve:.1f} s are the N-independent {args.block}^2 solves; the Spark/Breeze "
                       f"reference itself needs a JVM (absent)",
@@ -196,10 +198,10 @@ def main():
         X, cls, params = make_workload(args, 0, args.cpu_rows)
         recs = [cpu_baseline_record(args, X, cls, params, nb, D) for _ in range(max(1, args.steps))]
         secs = float(np.mean([r["seconds"] for r in recs]))
-        sps = args.cpu_rows / secs
+        sps = float(np.mean([r["value"] for r in recs]))
         rec = dict(recs[-1]); rec["value"] = sps
         print(json.dumps({"impl": "reference", "metric": "block-LS fit samples/sec (N=1M, D=64K, k=1K)", "value": sps,
-                          "unit": "samples/s", "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs,
+                          "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                           "config": config, "cpu_baseline": rec,
                           "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
