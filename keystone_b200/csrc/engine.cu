@@ -85,6 +85,8 @@ NcclApi& nccl_api() {
       load_sym(api.lib, "ncclCommDestroy", api.CommDestroy, "libnccl");
       load_sym(api.lib, "ncclAllReduce", api.AllReduce, "libnccl");
       load_sym(api.lib, "ncclBroadcast", api.Broadcast, "libnccl");
+      load_sym(api.lib, "ncclGroupStart", api.GroupStart, "libnccl");
+      load_sym(api.lib, "ncclGroupEnd", api.GroupEnd, "libnccl");
       load_sym(api.lib, "ncclGetErrorString", api.GetErrorString, "libnccl");
       api.CommSplit = reinterpret_cast<decltype(api.CommSplit)>(dlsym(api.lib, "ncclCommSplit"));
     } catch (const KsError& e) {
@@ -653,6 +655,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   // look-ahead depth of prep / factor over main: 2 blocks normally; with the owner-computes-inverse scheme the factor chain
   // of a block is ~30 ms on its owner, so `world` of them must be in flight at once (N_loc shrinks with world, so do the slabs)
   const bool use_inv = c.world >= c.inv_min_world;
+  const bool shard_solve = !use_inv && !c.custom_solve && c.world > 1 && c.shard_solve && k >= c.world;
   const int NBUF = use_inv ? c.world + 2 : 3;
   // fp16 operand mode (KS_PRECISION_F16): the slab, the residual operand and the increment operand are fp16 and the three
   // big GEMMs run as kind::f16 -- same 10-bit mantissa as tf32 at twice the MMA rate and half the slab bytes.  Only for
@@ -891,6 +894,21 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       KS_CUDA(launch_chol_solve(Hj, b, rhs.as<double>(), k, S1));
       c.launches += 1;
       dw_ptr = rhs.as<double>();
+    } else if (shard_solve) {
+      // Column-sharded solve: the right-hand sides are independent, so rank r solves columns [k r / world, k (r+1) / world)
+      // in place (column-major: a contiguous slice) and one grouped broadcast per rank hands every slice to everybody.
+      // All ranks end up with the same bytes, so the model stays bit-identical across ranks.
+      auto col0 = [&](int r) { return static_cast<int64_t>(k) * r / c.world; };
+      const int64_t m0 = col0(c.rank), m1 = col0(c.rank + 1);
+      c.potrs(Hj, b, rhs.as<double>() + m0 * b, static_cast<int>(m1 - m0), info_slot++, S1);
+      KS_NCCL(nccl_api().GroupStart());
+      for (int r = 0; r < c.world; ++r) {
+        double* slice = rhs.as<double>() + col0(r) * b;
+        KS_NCCL(nccl_api().Broadcast(slice, slice, static_cast<size_t>(col0(r + 1) - col0(r)) * b, ncclFloat64, r, c.comm, S1));
+      }
+      KS_NCCL(nccl_api().GroupEnd());
+      c.launches += 1;
+      dw_ptr = rhs.as<double>();
     } else {
       c.potrs(Hj, b, rhs.as<double>(), k, info_slot++, S1);
       dw_ptr = rhs.as<double>();
@@ -958,7 +976,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
      << ",\"world\":" << c.world << ",\"total_ms\":" << total_ms << ",\"featurize_ms\":" << ms[PH_FEATURIZE]
      << ",\"gram_ms\":" << ms[PH_GRAM] << ",\"allreduce_ms\":" << ms[PH_ALLREDUCE] << ",\"solve_ms\":" << ms[PH_SOLVE]
      << ",\"update_ms\":" << ms[PH_UPDATE] << ",\"other_ms\":" << ms[PH_OTHER] << ",\"local_flops\":" << flops
-     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"" << (f16 ? "f16" : "tf32x1") << "\",\"streams\":3,\"solve\":\"" << (use_inv ? "inverse-owner" : "potrs")
+     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"" << (f16 ? "f16" : "tf32x1") << "\",\"streams\":3,\"solve\":\"" << (use_inv ? "inverse-owner" : shard_solve ? "potrs-column-sharded" : "potrs")
      << "\",\"host_ms\":"
      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count() << "}";
   c.stats_json = js.str();
@@ -1103,6 +1121,7 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
     }
     if (const char* e = getenv("KS_GRAM_PAIR")) c->gram_pair = atoi(e) != 0;
     if (const char* e = getenv("KS_EPI_MULTI")) c->epi_multi = atoi(e) != 0;
+    if (const char* e = getenv("KS_SHARD_SOLVE")) c->shard_solve = atoi(e) != 0;
     if (const char* e = getenv("KS_PROJ_F16")) c->proj_f16 = atoi(e) != 0;
     if (const char* e = getenv("KS_PRECISION")) c->precision = (atoi(e) == 1 || !strcmp(e, "f16")) ? KS_PRECISION_F16 : KS_PRECISION_TF32;
     if (const char* e = getenv("KS_CUSTOM_SOLVE")) c->custom_solve = atoi(e) != 0;
@@ -1193,6 +1212,7 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     else if (n == "sample_rows" && value >= 1) c.sample_rows = value;
     else if (n == "gram_pair") c.gram_pair = value != 0;
     else if (n == "epi_multi") c.epi_multi = value != 0;
+    else if (n == "shard_solve") c.shard_solve = value != 0;
     else if (n == "proj_f16") c.proj_f16 = value != 0;
     else if (n == "precision" && (value == KS_PRECISION_TF32 || value == KS_PRECISION_F16)) c.precision = static_cast<int>(value);
     else if (n == "custom_solve") c.custom_solve = value != 0;

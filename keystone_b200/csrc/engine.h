@@ -109,6 +109,8 @@ struct NcclApi {
   ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*) = nullptr;  // optional (NCCL >= 2.18)
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 SolverApi& solver_api();  // throws KsError if libcusolver cannot be loaded
@@ -129,6 +131,9 @@ struct Ctx {
   int inv_min_world = 1 << 30; // experimental: from this world size on, block j's Cholesky + explicit inverse run on rank
                                // j % world only and are broadcast (off by default: cusolverDnDpotri is ~25 ms per 4096^2
                                // block and its fp64 work slows the tensor kernels more than the shorter solve gains)
+  int shard_solve = 1;  // world > 1: every rank runs the triangular solves for its k / world right-hand sides only and the
+                        // columns of dW are gathered (grouped ncclBroadcast, 32 MB at b = 4096, k = 1000) -- the solve is the
+                        // serial term of the strong-scaling curve and its cost is proportional to the number of columns
   int exclusive_solve_min_world = 1 << 30;  // experimental: from this world size on the look-ahead Gram waits for the
                                             // critical chain's triangular solves (4.4 ms alone, ~11 ms contended); measured
                                             // neutral at 4 GPUs (332 vs 338 ms) because it serialises Gram and solve
