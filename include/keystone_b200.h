@@ -55,6 +55,9 @@ extern "C" {
 #define KS_PRECISION_F16 1   /* ks_blockls_fit on generated (cosine) features: fp16 operands (same 10-bit mantissa as tf32,
                                 residual / increments scaled by device-chosen powers of two), kind::f16 MMA at twice the
                                 tf32 rate, fp32 accumulate, fp64 solve; materialised feature matrices fall back to tf32 */
+#define KS_PRECISION_F16X2 2 /* EXPERIMENTAL (not yet validated on hardware): every fp16 operand carried as hi + lo (21 significant
+                                bits), products keep hi*hi + hi*lo + lo*hi on the same kernels; ~3x the fp16 tensor work;
+                                ks_blockls_fit on generated features only (others fall back to tf32) */
 
 #define KS_NCCL_ID_BYTES 128
 

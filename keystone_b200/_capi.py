@@ -17,6 +17,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "keystone_b200.h")
 KS_NCCL_ID_BYTES = 128
 KS_PRECISION_TF32 = 0
 KS_PRECISION_F16 = 1
+KS_PRECISION_F16X2 = 2  # experimental
 
 
 class KeystoneError(RuntimeError):

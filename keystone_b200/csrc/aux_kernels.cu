@@ -297,21 +297,24 @@ void launch_delta_mean(const float* ssum, const float* shift, double n_total, do
 }
 
 // ------------------------------------------------------------------ reduced system assembly (fp64)
+// cross (optional, split-operand mode): full b x b matrix S_hi^T S_lo; the Gram of S = S_hi + S_lo is then
+// S_hi^T S_hi + cross + cross^T (the lo x lo term, ~2^-22 of the diagonal, is dropped)
 __global__ void build_system_kernel(const float* __restrict__ G, int ldg, const double* __restrict__ delta, double n_total,
-                                    double lam, double* __restrict__ H, int b) {
+                                    double lam, double* __restrict__ H, int b, const float* __restrict__ cross) {
   const int64_t total = static_cast<int64_t>(b) * b;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i / b), r = static_cast<int>(i - static_cast<int64_t>(c) * b);
     const int lo = min(r, c), hi = max(r, c);
-    const double g = static_cast<double>(G[static_cast<int64_t>(lo) * ldg + hi]);  // upper triangle is the computed one
+    double g = static_cast<double>(G[static_cast<int64_t>(lo) * ldg + hi]);  // upper triangle is the computed one
+    if (cross) g += static_cast<double>(cross[static_cast<int64_t>(r) * ldg + c]) + static_cast<double>(cross[static_cast<int64_t>(c) * ldg + r]);
     H[i] = g - n_total * delta[r] * delta[c] + (r == c ? lam : 0.0);
   }
 }
 void launch_build_system(const float* G, int ldg, const double* delta, double n_total, double lam, double* H, int b,
-                         cudaStream_t st) {
+                         cudaStream_t st, const float* cross) {
   if (b == 0) return;
-  build_system_kernel<<<grid_for(static_cast<int64_t>(b) * b, 256), 256, 0, st>>>(G, ldg, delta, n_total, lam, H, b);
+  build_system_kernel<<<grid_for(static_cast<int64_t>(b) * b, 256), 256, 0, st>>>(G, ldg, delta, n_total, lam, H, b, cross);
 }
 
 __global__ void build_rhs_kernel(const float* __restrict__ C, int ldc, const double* __restrict__ delta,
@@ -533,8 +536,10 @@ void launch_f32_to_f16_rows(const float* src, int64_t src_ld, void* dst, int64_t
 }
 
 // fp16 twin of round_colsum_kernel: R16[:, :k] = fp16(R * scale[0]), columns >= k zero; sums as before (of R itself)
+// R16lo (optional, split-operand mode): the fp16 rounding error of the scaled value, fp16(R * scale - R16)
 __global__ void round_colsum16_kernel(const float* __restrict__ R, __half* __restrict__ R16, int64_t ld, int64_t rows, int k,
-                                      double* __restrict__ sums, int64_t rows_per_block, const float* __restrict__ scale) {
+                                      double* __restrict__ sums, int64_t rows_per_block, const float* __restrict__ scale,
+                                      __half* __restrict__ R16lo) {
   __shared__ double red[8][128];
   const float sc = __ldg(scale);
   const int c4 = (blockIdx.x * 32 + threadIdx.x) * 4;
@@ -561,6 +566,14 @@ __global__ void round_colsum16_kernel(const float* __restrict__ R, __half* __res
       pk.x = *reinterpret_cast<const unsigned*>(&h0);
       pk.y = *reinterpret_cast<const unsigned*>(&h1);
       *reinterpret_cast<uint2*>(R16 + r * ld + c4) = pk;
+      if (R16lo) {
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+        const __half2 l0 = __floats2half2_rn(o[0] - f0.x, o[1] - f0.y), l1 = __floats2half2_rn(o[2] - f1.x, o[3] - f1.y);
+        uint2 pl;
+        pl.x = *reinterpret_cast<const unsigned*>(&l0);
+        pl.y = *reinterpret_cast<const unsigned*>(&l1);
+        *reinterpret_cast<uint2*>(R16lo + r * ld + c4) = pl;
+      }
     }
   }
 #pragma unroll
@@ -576,30 +589,34 @@ __global__ void round_colsum16_kernel(const float* __restrict__ R, __half* __res
   }
 }
 void launch_round_colsum16(const float* R, void* R16, int64_t ld, int64_t rows, int k, double* sums, const float* scale,
-                           cudaStream_t st) {
+                           cudaStream_t st, void* R16lo) {
   if (rows == 0) return;
   const int64_t rpb = 1024;
   dim3 grid(static_cast<unsigned>((ld + 127) / 128), static_cast<unsigned>((rows + rpb - 1) / rpb));
-  round_colsum16_kernel<<<grid, dim3(32, 8), 0, st>>>(R, static_cast<__half*>(R16), ld, rows, k, sums, rpb, scale);
+  round_colsum16_kernel<<<grid, dim3(32, 8), 0, st>>>(R, static_cast<__half*>(R16), ld, rows, k, sums, rpb, scale,
+                                                      static_cast<__half*>(R16lo));
 }
 
 // fp16 twin of pack_update_kernel: bop16[c][f] = fp16(dW[f][c] * scale[0]); Wmodel and cbias exactly as the tf32 version
 __global__ void pack_update16_kernel(const double* __restrict__ dW, double* __restrict__ Wmodel,
                                      const double* __restrict__ delta, __half* __restrict__ bop, int ldb,
-                                     float* __restrict__ cbias, int b, int k, const float* __restrict__ scale) {
+                                     float* __restrict__ cbias, int b, int k, const float* __restrict__ scale,
+                                     __half* __restrict__ bop_lo) {
   const int c = blockIdx.x;
   const double sc = static_cast<double>(__ldg(scale));
   __shared__ double red[256];
   double acc = 0;
   for (int f = threadIdx.x; f < ldb; f += blockDim.x) {
-    float h = 0.f;
+    double ws = 0.0;
     if (c < k && f < b) {
       const double w = dW[static_cast<int64_t>(c) * b + f];
       if (Wmodel) Wmodel[static_cast<int64_t>(c) * b + f] += w;
       if (delta) acc += delta[f] * w;
-      h = static_cast<float>(w * sc);
+      ws = w * sc;
     }
-    bop[static_cast<int64_t>(c) * ldb + f] = __float2half_rn(h);
+    const __half hh = __float2half_rn(static_cast<float>(ws));
+    bop[static_cast<int64_t>(c) * ldb + f] = hh;
+    if (bop_lo) bop_lo[static_cast<int64_t>(c) * ldb + f] = __float2half_rn(static_cast<float>(ws - static_cast<double>(__half2float(hh))));
   }
   red[threadIdx.x] = acc;
   __syncthreads();
@@ -610,9 +627,64 @@ __global__ void pack_update16_kernel(const double* __restrict__ dW, double* __re
   if (threadIdx.x == 0 && cbias) cbias[c] = static_cast<float>(red[0]);
 }
 void launch_pack_update16(const double* dW, double* Wmodel, const double* delta, void* bop16, int ldb, float* cbias, int b, int k,
-                          int kpad, const float* scale, cudaStream_t st) {
+                          int kpad, const float* scale, cudaStream_t st, void* bop16_lo) {
   if (kpad == 0) return;
-  pack_update16_kernel<<<kpad, 256, 0, st>>>(dW, Wmodel, delta, static_cast<__half*>(bop16), ldb, cbias, b, k, scale);
+  pack_update16_kernel<<<kpad, 256, 0, st>>>(dW, Wmodel, delta, static_cast<__half*>(bop16), ldb, cbias, b, k, scale,
+                                             static_cast<__half*>(bop16_lo));
+}
+
+// ---- split-operand mode (fp16 x 2): v = hi + lo with hi = fp16(v), lo = fp16(v - hi)  (21 significant bits in two fp16)
+// slab: hi / lo planes of an fp32 matrix, plus the column sums of hi + lo (fp32 atomics; must be zeroed)
+__global__ void split_rows16_kernel(const float* __restrict__ src, int64_t ld_src, __half* __restrict__ hi, __half* __restrict__ lo,
+                                    int64_t ld_dst, int64_t rows, int cols, float* __restrict__ colsum, int64_t rows_per_block) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // one column per thread, coalesced along the row
+  if (c >= ld_dst) return;
+  const int64_t r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float acc = 0.f;
+  for (int64_t r = r0; r < r1; ++r) {
+    const float v = c < cols ? src[r * ld_src + c] : 0.f;
+    const __half h = __float2half_rn(v);
+    const float hf = __half2float(h);
+    const __half l = __float2half_rn(v - hf);
+    hi[r * ld_dst + c] = h;
+    lo[r * ld_dst + c] = l;
+    acc += hf + __half2float(l);
+  }
+  if (colsum && c < cols) atomicAdd(colsum + c, acc);
+}
+void launch_split_rows16(const float* src, int64_t ld_src, void* hi, void* lo, int64_t ld_dst, int64_t rows, int cols, float* colsum,
+                         cudaStream_t st) {
+  if (rows == 0) return;
+  const int64_t rpb = 256;
+  dim3 grid(static_cast<unsigned>((ld_dst + 127) / 128), static_cast<unsigned>((rows + rpb - 1) / rpb));
+  split_rows16_kernel<<<grid, 128, 0, st>>>(src, ld_src, static_cast<__half*>(hi), static_cast<__half*>(lo), ld_dst, rows, cols, colsum, rpb);
+}
+// projection operands, concatenated along K so that ONE GEMM of depth 3 * cols accumulates hi*hi + lo*hi + hi*lo:
+//   pattern 0 (left operand X):  dst row = [ hi | lo | hi ],   pattern 1 (right operand W): dst row = [ hi | hi | lo ]
+__global__ void split_concat3_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int cols,
+                                     const float* __restrict__ scale, __half* __restrict__ dst, int64_t ld_dst, int pattern) {
+  const float sc = scale ? __ldg(scale) : 1.f;
+  const int64_t total = rows * ld_dst;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / ld_dst;
+    const int c = static_cast<int>(i - r * ld_dst);
+    __half out = __float2half_rn(0.f);
+    if (c < 3 * cols) {
+      const int part = c / cols, cc = c - part * cols;
+      const float v = src[r * ld_src + cc] * sc;
+      const __half h = __float2half_rn(v);
+      const bool want_lo = pattern == 0 ? part == 1 : part == 2;
+      out = want_lo ? __float2half_rn(v - __half2float(h)) : h;
+    }
+    dst[i] = out;
+  }
+}
+void launch_split_concat3(const float* src, int64_t ld_src, int64_t rows, int cols, const float* scale, void* dst, int64_t ld_dst,
+                          int pattern, cudaStream_t st) {
+  if (rows == 0) return;
+  split_concat3_kernel<<<grid_for(rows * ld_dst, 256), 256, 0, st>>>(src, ld_src, rows, cols, scale, static_cast<__half*>(dst), ld_dst,
+                                                                    pattern);
 }
 
 }  // namespace ks

@@ -341,7 +341,8 @@ void Ctx::check_async(const char* what) {
 // ------------------------------------------------------------------------------------ feature source
 __global__ void combine_scales_kernel(const float* a, const float* b, float* out) { out[0] = a[1] * b[1]; }
 
-void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out, bool want_f16) {
+void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out, int precision) {
+  const bool want_f16 = precision == KS_PRECISION_F16, want_x2 = precision == KS_PRECISION_F16X2;
   if (features != 0) {
     if (x_in != 0 || n_rfs != 0) throw KsError{KS_ERR_INVALID, "pass either features or (x_in, rfs), not both"};
     out.F = &c.matrix(features);
@@ -388,7 +389,7 @@ void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, i
   launch_center_round(out.X->d, out.X->ld, 0, out.zeros.as<float>(), out.xop.as<float>(), nullptr, out.X->ld, out.n_rows,
                       static_cast<int>(out.X->cols), c.st);
   c.launches += 1;
-  if (want_f16 && c.proj_f16) {
+  if ((want_f16 && c.proj_f16) || want_x2) {
     // fp16 copies of X and W for the kind::f16 projection.  Each carries its own power-of-two scale (largest magnitude
     // mapped into [2048, 4096]), so the input units do not matter; the product of the two inverse scales is applied to the
     // fp32 accumulator in the epilogue.  Same 10-bit mantissa as the tf32 operands above.
@@ -401,12 +402,21 @@ void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, i
     launch_pow2_scale(mb + 1, 4096.f, ps + 4, c.st);
     launch_pow2_scale(mb + 2, 4096.f, ps + 6, c.st);
     combine_scales_kernel<<<1, 1, 0, c.st>>>(ps + 4, ps + 6, ps);
-    out.xop16.alloc(2 * static_cast<size_t>(std::max<int64_t>(out.n_rows, 1) * out.X->ld));
-    out.w16.alloc(2 * static_cast<size_t>(total * out.ldw));
-    launch_f32_to_f16_rows(out.X->d, out.X->ld, out.xop16.p, out.X->ld, out.n_rows, out.X->cols, c.st, ps + 4);
-    launch_f32_to_f16_rows(out.Wall, out.ldw, out.w16.p, out.ldw, total, out.d_in, c.st, ps + 6);
+    if (want_x2) {
+      out.ldx3 = out.ldw3 = round_up(3 * out.d_in, 64);
+      out.x3.alloc(2 * static_cast<size_t>(std::max<int64_t>(out.n_rows, 1) * out.ldx3));
+      out.w3.alloc(2 * static_cast<size_t>(total * out.ldw3));
+      launch_split_concat3(out.X->d, out.X->ld, out.n_rows, static_cast<int>(out.d_in), ps + 4, out.x3.p, out.ldx3, 0, c.st);
+      launch_split_concat3(out.Wall, out.ldw, total, static_cast<int>(out.d_in), ps + 6, out.w3.p, out.ldw3, 1, c.st);
+      out.proj_x2 = true;
+    } else {
+      out.xop16.alloc(2 * static_cast<size_t>(std::max<int64_t>(out.n_rows, 1) * out.X->ld));
+      out.w16.alloc(2 * static_cast<size_t>(total * out.ldw));
+      launch_f32_to_f16_rows(out.X->d, out.X->ld, out.xop16.p, out.X->ld, out.n_rows, out.X->cols, c.st, ps + 4);
+      launch_f32_to_f16_rows(out.Wall, out.ldw, out.w16.p, out.ldw, total, out.d_in, c.st, ps + 6);
+      out.proj16 = true;
+    }
     c.launches += 7;
-    out.proj16 = true;
   }
 }
 
@@ -427,19 +437,27 @@ static void tmap_or_throw(CUtensorMap* m, const float* base, int64_t rows, int64
 }
 
 void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, void* slab_v, int64_t lds,
-                  int64_t row_begin, int64_t rows, bool round_out, float* colsum, cudaStream_t st, bool out16) {
+                  int64_t row_begin, int64_t rows, bool round_out, float* colsum, cudaStream_t st, bool out16, bool x2) {
   if (rows <= 0 || cols <= 0) return;
   if (!st) st = c.st;
   float* slab = static_cast<float*>(slab_v);
   if (src.F) {
-    if (!round_out || out16) throw KsError{KS_ERR_INVALID, "unrounded / fp16 slabs only for generated features"};
+    if (!round_out || out16 || x2) throw KsError{KS_ERR_INVALID, "unrounded / fp16 slabs only for generated features"};
     launch_center_round(src.F->d + row_begin * src.F->ld, src.F->ld, static_cast<int>(c0), shift, slab, colsum, lds, rows,
                         static_cast<int>(cols), st);
     c.launches += 1;
     return;
   }
   KmLaunch k;
-  if (out16 && src.proj16) {  // fp16 operands: 64 K-elements (128 B) per box row
+  int64_t kdepth = src.d_in;
+  if (x2) {  // split operands concatenated along K: depth 3 d_in, fp32 output, no rounding
+    if (!src.proj_x2 || out16 || round_out) throw KsError{KS_ERR_INVALID, "split-operand slab requested without split operands"};
+    kdepth = 3 * src.d_in;
+    tmap16_or_throw(&k.tmA, static_cast<const uint16_t*>(src.x3.p) + row_begin * src.ldx3, rows, kdepth, src.ldx3, 64, 128, TMAP_SW128);
+    tmap16_or_throw(&k.tmB, static_cast<const uint16_t*>(src.w3.p) + c0 * src.ldw3, cols, kdepth, src.ldw3, 64, 256, TMAP_SW128);
+    k.f16 = 1;
+    k.p.acc_scale_ptr = src.pscale.as<float>();
+  } else if (out16 && src.proj16) {  // fp16 operands: 64 K-elements (128 B) per box row
     tmap16_or_throw(&k.tmA, static_cast<const uint16_t*>(src.xop16.p) + row_begin * src.X->ld, rows, src.d_in, src.X->ld, 64, 128,
                     TMAP_SW128);
     tmap16_or_throw(&k.tmB, static_cast<const uint16_t*>(src.w16.p) + c0 * src.ldw, cols, src.d_in, src.ldw, 64, 256, TMAP_SW128);
@@ -457,7 +475,7 @@ void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* s
   k.p.colsum = colsum;
   k.p.M = static_cast<int>(rows);
   k.p.N = static_cast<int>(cols);
-  k.p.K = static_cast<int>(src.d_in);
+  k.p.K = static_cast<int>(kdepth);
   k.p.flags = round_out ? 0 : KM_FLAG_NO_ROUND;
   k.epi = EPI_COS;
   k.pair = 0;
@@ -497,7 +515,8 @@ const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, b
 }
 
 void launch_gram_block(Ctx& c, const void* slab, int64_t lds, int64_t rows, int b, const void* R, int64_t ldr, int kcols,
-                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c, cudaStream_t st, bool f16) {
+                       float* G, int ldg, float* C, int ldc, bool with_g, bool with_c, cudaStream_t st, bool f16,
+                       int64_t chunk_rows) {
   if (rows <= 0 || b <= 0 || (!with_g && !with_c)) return;
   if (!st) st = c.st;
   GramLaunch g;
@@ -524,7 +543,7 @@ void launch_gram_block(Ctx& c, const void* slab, int64_t lds, int64_t rows, int 
   // chunks mean less reduce traffic and fewer, longer CTAs next to the critical chain's kernels; short chunks keep enough
   // CTAs per launch to balance 74 CTA pairs when the rows are sharded.  Measured in the config-3 fit (tools/ab_fit.py,
   // fp16 operands, N = 1M): 4096 -> 660 ms, 8192 -> 655 ms, 16384 -> 639 ms, 32768 -> 650 ms.
-  int64_t chunk = c.gram_chunk_rows;
+  int64_t chunk = chunk_rows > 0 ? chunk_rows : c.gram_chunk_rows;
   if (chunk <= 0) chunk = !f16 ? 4096 : rows >= 400000 ? 16384 : rows >= 200000 ? 8192 : 4096;
   chunk = std::max<int64_t>(stage_rows, chunk / stage_rows * stage_rows);
   g.chunk_rows = static_cast<int>(chunk);
@@ -661,12 +680,20 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   // big GEMMs run as kind::f16 -- same 10-bit mantissa as tf32 at twice the MMA rate and half the slab bytes.  Only for
   // generated cosine features (|value| <= 2: no range problem); the residual and the increments are scaled by device-chosen
   // powers of two.  Materialised feature matrices have arbitrary scale and keep the tf32 path.
-  const bool f16 = precision == KS_PRECISION_F16 && !src.F;
+  // Split-operand mode (KS_PRECISION_F16X2, experimental): every fp16 operand v is carried as hi + lo (hi = fp16(v),
+  // lo = fp16(v - hi): 21 significant bits) and every product keeps hi*hi + hi*lo + lo*hi, using the same kernels three
+  // times (the projection once, on operands concatenated along K).  Modelled rel-Frobenius(W) ~ 2e-7 instead of 7e-4
+  // (tests/test_precision_model.py) at ~3x the fp16 tensor work.
+  const bool x2 = precision == KS_PRECISION_F16X2 && !src.F && src.proj_x2;
+  const bool f16 = (precision == KS_PRECISION_F16 || x2) && !src.F;
   const size_t es = f16 ? 2 : 4;  // bytes per slab / operand element
-  DevBuf r_f32, r_tf32, cm, rhs, dwb, rsum, bop, cbias, samp, fsum, scales;
+  const int64_t x2_chunk = 2048;  // short accumulation chains: the tensor core's fp32 accumulate truncates (~2^-25 per MMA step)
+  DevBuf r_f32, r_tf32, cm, rhs, dwb, rsum, bop, cbias, samp, fsum, scales, sf32, r_lo, bop_lo;
+  std::unique_ptr<DevBuf[]> slab_lo;
   std::unique_ptr<DevBuf[]> slab(new DevBuf[NBUF]), gbuf(new DevBuf[NBUF]), Hbuf(new DevBuf[NBUF]), ssum(new DevBuf[NBUF]);
   r_f32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * kpad));
   r_tf32.alloc(f16 ? r_f32.bytes / 2 : r_f32.bytes);
+  if (x2) r_lo.alloc(r_tf32.bytes);
   launch_init_residual(Y.d, Y.ld, model->intercept.as<double>(), r_f32.as<float>(), kpad, n_loc, k, S1);
   c.launches += 1;
   // scales: [0] max|R0| bits, [1] max|dW| bits (per block), then float pairs {2^e, 2^-e}: [2,3] residual, [4,5] increment
@@ -688,7 +715,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   const bool cache_factors = num_iter > 1;
   for (int i = 0; i < NBUF; ++i) {
     slab[i].alloc(es * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));
-    gbuf[i].alloc(sizeof(float) * g_elems);
+    gbuf[i].alloc(sizeof(float) * g_elems * (x2 ? 2 : 1));  // x2: S_hi^T S_hi (upper tiles) followed by the full S_hi^T S_lo
     ssum[i].alloc(sizeof(float) * lds);
     if (!cache_factors) Hbuf[i].alloc(sizeof(double) * static_cast<size_t>(bmax) * bmax);
   }
@@ -697,6 +724,12 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   dwb.alloc(rhs.bytes);
   rsum.alloc(sizeof(double) * kpad);
   bop.alloc(es * static_cast<size_t>(kpad) * lds);
+  if (x2) {
+    slab_lo.reset(new DevBuf[NBUF]);
+    for (int i = 0; i < NBUF; ++i) slab_lo[i].alloc(slab[i].bytes);
+    sf32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));  // unrounded block before the split
+    bop_lo.alloc(bop.bytes);
+  }
   cbias.alloc(sizeof(float) * kpad);
   samp.alloc(sizeof(double) * (bmax + 1));  // sample column sums + sample row count (generated features)
   std::vector<std::unique_ptr<DevBuf>> factors(nb), deltas(nb), shifts(nb);
@@ -758,8 +791,10 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
         const int64_t ns = std::min<int64_t>(n_loc, c.sample_rows);
         KS_CUDA(cudaMemsetAsync(samp.p, 0, samp.bytes, S2));
         KS_CUDA(cudaMemsetAsync(ssum[buf].p, 0, ssum[buf].bytes, S2));
-        produce_slab(c, src, c0, b, src.zeros.as<float>(), slab[buf].p, lds, 0, ns, /*round_out=*/false,
-                     ssum[buf].as<float>(), S2, f16);
+        if (x2) produce_slab(c, src, c0, b, src.zeros.as<float>(), sf32.p, lds, 0, ns, /*round_out=*/false, ssum[buf].as<float>(), S2,
+                             false, true);
+        else produce_slab(c, src, c0, b, src.zeros.as<float>(), slab[buf].p, lds, 0, ns, /*round_out=*/false,
+                          ssum[buf].as<float>(), S2, f16);
         launch_f32_to_f64_rows(ssum[buf].as<float>(), lds, samp.as<double>(), bmax, 1, b, S2);  // 1 x b "matrix"
         c.launches += 1;
         set_f64_kernel<<<1, 1, 0, S2>>>(samp.as<double>() + bmax, static_cast<double>(ns));
@@ -771,8 +806,16 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       }
     }
     KS_CUDA(cudaMemsetAsync(ssum[buf].p, 0, ssum[buf].bytes, S2));
-    produce_slab(c, src, c0, b, shifts[j]->as<float>(), slab[buf].p, lds, 0, n_loc, true,
-                 it == 0 ? ssum[buf].as<float>() : nullptr, S2, f16);
+    if (x2) {
+      produce_slab(c, src, c0, b, shifts[j]->as<float>(), sf32.p, lds, 0, n_loc, /*round_out=*/false, nullptr, S2, false, true);
+      launch_split_rows16(sf32.as<float>(), lds, slab[buf].p, slab_lo[buf].p, lds, n_loc, b, it == 0 ? ssum[buf].as<float>() : nullptr,
+                          S2);
+      c.launches += 1;
+      if (!src.F) flops += 4.0 * static_cast<double>(n_loc) * src.d_in * b;  // two extra product terms of the projection
+    } else {
+      produce_slab(c, src, c0, b, shifts[j]->as<float>(), slab[buf].p, lds, 0, n_loc, true,
+                   it == 0 ? ssum[buf].as<float>() : nullptr, S2, f16);
+    }
     if (!src.F) flops += 2.0 * static_cast<double>(n_loc) * src.d_in * b;
     c.span_end(S2);
     KS_CUDA(cudaEventRecord(ev_slab[t], S2));
@@ -788,12 +831,18 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       if (exclusive_solve && t >= 1) KS_CUDA(cudaStreamWaitEvent(S2, ev_solved[t - 1], 0));
       c.span_begin(PH_GRAM, S2);  // G part of the Gram
       KS_CUDA(cudaMemsetAsync(gbuf[buf].p, 0, gbuf[buf].bytes, S2));
-      launch_gram_block(c, slab[buf].p, lds, n_loc, b, nullptr, 0, 0, gbuf[buf].as<float>(), ldg, nullptr, 0, true,
-                        false, S2, f16);
+      if (x2) {  // one launch: upper tiles of S_hi^T S_hi and all tiles of S_hi^T S_lo (the "C" slot with kcols = b)
+        launch_gram_block(c, slab[buf].p, lds, n_loc, b, slab_lo[buf].p, lds, b, gbuf[buf].as<float>(), ldg,
+                          gbuf[buf].as<float>() + g_elems, ldg, true, true, S2, true, x2_chunk);
+        flops += 4.0 * n_loc * static_cast<double>(b) * b;
+      } else {
+        launch_gram_block(c, slab[buf].p, lds, n_loc, b, nullptr, 0, 0, gbuf[buf].as<float>(), ldg, nullptr, 0, true,
+                          false, S2, f16);
+      }
       flops += 2.0 * n_loc * static_cast<double>(b) * b;
       c.span_end(S2);
       c.span_begin(PH_ALLREDUCE, S2);
-      c.allreduce_f32(gbuf[buf].as<float>(), g_elems, true);
+      c.allreduce_f32(gbuf[buf].as<float>(), g_elems * (x2 ? 2 : 1), true);
       c.allreduce_f32(ssum[buf].as<float>(), static_cast<size_t>(b), true);
       c.span_end(S2);
       KS_CUDA(cudaEventRecord(ev_g[t], S2));
@@ -825,7 +874,8 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
           KS_CUDA(cudaStreamWaitEvent(S3, ev_g[t], 0));
           c.span_begin(PH_SOLVE, S3);
           launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), nullptr, b, S3);
-          launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S3);
+          launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S3,
+                              x2 ? gbuf[buf].as<float>() + g_elems : nullptr);
           c.launches += 2;
           c.potrf(Hj, b, info_slot++, S3);
           c.potri(Hj, b, info_slot++, S3);
@@ -842,7 +892,8 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
         KS_CUDA(cudaStreamWaitEvent(S3, ev_g[t], 0));
         c.span_begin(PH_SOLVE, S3);
         launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), mean->as<double>(), b, S3);
-        launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S3);
+        launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S3,
+                              x2 ? gbuf[buf].as<float>() + g_elems : nullptr);
         c.launches += 2;
         c.potrf(Hj, b, info_slot++, S3);
         KS_CUDA(cudaMemsetAsync(W->p, 0, W->bytes, S3));
@@ -866,14 +917,21 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     c.span_begin(PH_OTHER);
     KS_CUDA(cudaMemsetAsync(cm.p, 0, sizeof(float) * c_elems, S1));
     KS_CUDA(cudaMemsetAsync(rsum.p, 0, rsum.bytes, S1));
-    if (f16) launch_round_colsum16(r_f32.as<float>(), r_tf32.p, kpad, n_loc, k, rsum.as<double>(), rscale, S1);
+    if (f16) launch_round_colsum16(r_f32.as<float>(), r_tf32.p, kpad, n_loc, k, rsum.as<double>(), rscale, S1, x2 ? r_lo.p : nullptr);
     else launch_round_colsum(r_f32.as<float>(), r_tf32.as<float>(), kpad, n_loc, k, rsum.as<double>(), S1);
     c.launches += 1;
     c.span_end();
     KS_CUDA(cudaStreamWaitEvent(S1, ev_slab[t], 0));
     c.span_begin(PH_UPDATE);  // A^T R part of the Gram (accounted with the residual chain)
     launch_gram_block(c, slab[buf].p, lds, n_loc, b, r_tf32.p, kpad, k, nullptr, 0, cm.as<float>(), ldc,
-                      false, true, S1, f16);
+                      false, true, S1, f16, x2 ? x2_chunk : 0);
+    if (x2) {  // + S_lo^T R_hi + S_hi^T R_lo, reduce-added into the same C
+      launch_gram_block(c, slab_lo[buf].p, lds, n_loc, b, r_tf32.p, kpad, k, nullptr, 0, cm.as<float>(), ldc, false, true, S1, true,
+                        x2_chunk);
+      launch_gram_block(c, slab[buf].p, lds, n_loc, b, r_lo.p, kpad, k, nullptr, 0, cm.as<float>(), ldc, false, true, S1, true,
+                        x2_chunk);
+      flops += 4.0 * n_loc * static_cast<double>(b) * k;
+    }
     flops += 2.0 * n_loc * static_cast<double>(b) * k;
     c.span_end();
     c.span_begin(PH_ALLREDUCE);
@@ -919,7 +977,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       launch_max_abs_f64(dw_ptr, static_cast<int64_t>(b) * k, maxbits + 1, S1);
       launch_pow2_scale(maxbits + 1, 8192.f, dwscale, S1);
       launch_pack_update16(dw_ptr, model->W[j]->as<double>(), deltas[j]->as<double>(), bop.p, static_cast<int>(lds),
-                           cbias.as<float>(), b, k, static_cast<int>(kpad), dwscale, S1);
+                           cbias.as<float>(), b, k, static_cast<int>(kpad), dwscale, S1, x2 ? bop_lo.p : nullptr);
       c.launches += 2;
     } else {
       launch_pack_update(dw_ptr, model->W[j]->as<double>(), deltas[j]->as<double>(), bop.as<float>(), nullptr,
@@ -931,6 +989,13 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     c.span_begin(PH_UPDATE);
     launch_update(c, slab[buf].p, lds, n_loc, b, bop.p, lds, k, r_f32.as<float>(), kpad, cbias.as<float>(),
                   EPI_UPDATE, /*reduce=*/true, S1, f16, f16 ? dwscale + 1 : nullptr);
+    if (x2) {  // - S_lo dW_hi - S_hi dW_lo (the constant delta^T dW is applied once, above)
+      launch_update(c, slab_lo[buf].p, lds, n_loc, b, bop.p, lds, k, r_f32.as<float>(), kpad, nullptr, EPI_UPDATE, true, S1, true,
+                    dwscale + 1);
+      launch_update(c, slab[buf].p, lds, n_loc, b, bop_lo.p, lds, k, r_f32.as<float>(), kpad, nullptr, EPI_UPDATE, true, S1, true,
+                    dwscale + 1);
+      flops += 4.0 * n_loc * static_cast<double>(b) * k;
+    }
     flops += 2.0 * n_loc * static_cast<double>(b) * k;
     c.span_end();
     KS_CUDA(cudaEventRecord(ev_upd[t], S1));
@@ -976,7 +1041,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
      << ",\"world\":" << c.world << ",\"total_ms\":" << total_ms << ",\"featurize_ms\":" << ms[PH_FEATURIZE]
      << ",\"gram_ms\":" << ms[PH_GRAM] << ",\"allreduce_ms\":" << ms[PH_ALLREDUCE] << ",\"solve_ms\":" << ms[PH_SOLVE]
      << ",\"update_ms\":" << ms[PH_UPDATE] << ",\"other_ms\":" << ms[PH_OTHER] << ",\"local_flops\":" << flops
-     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"" << (f16 ? "f16" : "tf32x1") << "\",\"streams\":3,\"solve\":\"" << (use_inv ? "inverse-owner" : shard_solve ? "potrs-column-sharded" : "potrs")
+     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"" << (x2 ? "f16x2" : f16 ? "f16" : "tf32x1") << "\",\"streams\":3,\"solve\":\"" << (use_inv ? "inverse-owner" : shard_solve ? "potrs-column-sharded" : "potrs")
      << "\",\"host_ms\":"
      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count() << "}";
   c.stats_json = js.str();
@@ -1386,11 +1451,11 @@ KS_API int32_t ks_blockls_fit(int64_t ctx, int64_t features, int64_t x_in, const
                        int64_t* out_model) {
   return guard(ctx, [&](Ctx& c) {
     if (!out_model) throw KsError{KS_ERR_INVALID, "null out_model"};
-    if (precision_mode != KS_PRECISION_TF32 && precision_mode != KS_PRECISION_F16)
+    if (precision_mode != KS_PRECISION_TF32 && precision_mode != KS_PRECISION_F16 && precision_mode != KS_PRECISION_F16X2)
       throw KsError{KS_ERR_INVALID, "unsupported precision_mode"};
+    const int prec = (c.precision == KS_PRECISION_F16 && precision_mode == KS_PRECISION_TF32) ? KS_PRECISION_F16 : precision_mode;
     FeatSrc src;
-    make_feat_src(c, features, x_in, rfs, n_rfs, src, precision_mode == KS_PRECISION_F16 || c.precision == KS_PRECISION_F16);
-    const int prec = c.precision == KS_PRECISION_F16 ? KS_PRECISION_F16 : precision_mode;  // the context option overrides
+    make_feat_src(c, features, x_in, rfs, n_rfs, src, prec);
     *out_model = fit_blockls(c, src, c.matrix(labels), block_size, num_iter, lambda, num_features_or_0, prec);
   });
 }

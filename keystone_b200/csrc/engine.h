@@ -202,6 +202,11 @@ struct FeatSrc {
   // pscale[0] = 1 / (x scale * w scale) is applied to the accumulator before the cosine
   DevBuf xop16, w16, pscale;
   bool proj16 = false;
+  // split-operand mode (KS_PRECISION_F16X2): K-concatenated fp16 operands [x_hi | x_lo | x_hi] and [w_hi | w_hi | w_lo], so one
+  // GEMM of depth 3 d_in accumulates x_hi w_hi + x_lo w_hi + x_hi w_lo
+  DevBuf x3, w3;
+  int64_t ldx3 = 0, ldw3 = 0;
+  bool proj_x2 = false;
   DevBuf wcat, bcat;
   float* Wall = nullptr;
   float* ball = nullptr;
@@ -210,18 +215,18 @@ struct FeatSrc {
   DevBuf zeros;  // max(D-block, d_in) zero floats
 };
 void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out,
-                   bool want_f16 = false);
+                   int precision = 0);  // KS_PRECISION_*: which operand copies of X / W to prepare
 // slab[rows x lds] = round_tf32(features[row_begin : row_begin+rows, c0 : c0+cols] - shift)   (shift may be the zero vector)
 // colsum (optional, fp32[cols], must be zeroed): receives the column sums of the stored slab
 // out16: the slab is fp16 (lds in fp16 elements), generated features only
 void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, void* slab, int64_t lds,
                   int64_t row_begin, int64_t rows, bool round_out = true, float* colsum = nullptr, cudaStream_t st = nullptr,
-                  bool out16 = false);
+                  bool out16 = false, bool x2 = false);  // x2: unrounded fp32 slab from the K-concatenated split operands
 const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, bool pair, int* num_tiles);
 // f16: slab and R are fp16 matrices (leading dimensions in elements); G / C stay fp32
 void launch_gram_block(Ctx& c, const void* slab, int64_t lds, int64_t rows, int b, const void* R, int64_t ldr, int kcols,
                        float* G, int ldg, float* C, int ldc, bool with_g, bool with_c, cudaStream_t st = nullptr,
-                       bool f16 = false);
+                       bool f16 = false, int64_t chunk_rows = 0);  // chunk_rows 0: the context's choice
 // out[rows x k] (+)= (epi == EPI_UPDATE ? -1 : +1) * slab[rows x b] * bop[k x b]^T + cbias   (reduce: add into out)
 // f16: slab and bop are fp16; the product is multiplied by *acc_scale_ptr (device scalar, may be null) before the epilogue
 void launch_update(Ctx& c, const void* slab, int64_t lds, int64_t rows, int b, const void* bop, int64_t ldb, int k,

@@ -83,7 +83,7 @@ void launch_divide_by_count(const double* sums, const double* count, float* out,
 void launch_delta_mean(const float* ssum, const float* shift, double n_total, double* delta, double* mean, int b, cudaStream_t st);
 // H (fp64, column-major b x b, ld = b) = sym(G) - n * delta delta^T + lam * I
 void launch_build_system(const float* G, int ldg, const double* delta, double n_total, double lam, double* H, int b,
-                         cudaStream_t st);
+                         cudaStream_t st, const float* cross = nullptr);  // cross: S_hi^T S_lo (full b x b, ld = ldg), split mode
 // RHS (fp64 column-major b x k, ld = b) = C[:, :k] - n * delta * rbar^T - lam * Wold
 void launch_build_rhs(const float* C, int ldc, const double* delta, const double* rsum, double n_total, double lam,
                       const double* Wold, double* rhs, int b, int k, cudaStream_t st, const float* c_scale = nullptr);
@@ -108,8 +108,13 @@ void launch_pow2_scale(const unsigned* maxbits, float target, float* scale, cuda
 void launch_f32_to_f16_rows(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int64_t cols, cudaStream_t st,
                             const float* scale = nullptr);  // optional device scalar multiplied in before the conversion
 void launch_round_colsum16(const float* R, void* R16, int64_t ld, int64_t rows, int k, double* sums, const float* scale,
-                           cudaStream_t st);
+                           cudaStream_t st, void* R16lo = nullptr);
 void launch_pack_update16(const double* dW, double* Wmodel, const double* delta, void* bop16, int ldb, float* cbias, int b, int k,
-                          int kpad, const float* scale, cudaStream_t st);
+                          int kpad, const float* scale, cudaStream_t st, void* bop16_lo = nullptr);
+// split-operand mode: hi / lo fp16 planes of an fp32 matrix (+ column sums of hi + lo), and the K-concatenated projection operands
+void launch_split_rows16(const float* src, int64_t ld_src, void* hi, void* lo, int64_t ld_dst, int64_t rows, int cols, float* colsum,
+                         cudaStream_t st);
+void launch_split_concat3(const float* src, int64_t ld_src, int64_t rows, int cols, const float* scale, void* dst, int64_t ld_dst,
+                          int pattern, cudaStream_t st);
 
 }  // namespace ks

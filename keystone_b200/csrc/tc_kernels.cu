@@ -886,6 +886,7 @@ cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st) {
   if (k.f16 && k.epi == EPI_UPDATE) return launch_km2_t<EPI_UPDATE, true, 4>(k, st);
   if (k.f16 && k.epi == EPI_APPLY) return launch_km2_t<EPI_APPLY, true, 4>(k, st);
   if (k.out16 && k.f16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, true, true, 256, 3>(k, st);
+  if (k.f16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, true, false, 256, 3>(k, st);  // fp16 operands, fp32 slab (split mode)
   if (k.out16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, false, true, 256, 3>(k, st);
   if (k.pair && k.epi == EPI_UPDATE) return launch_km2_t<EPI_UPDATE, false, 4>(k, st);
   if (k.pair && k.epi == EPI_APPLY) return launch_km2_t<EPI_APPLY, false, 4>(k, st);

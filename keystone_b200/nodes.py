@@ -247,8 +247,8 @@ class BlockLeastSquaresEstimator(LabelEstimator, WeightedNode):
         """precision: "tf32" (default) or "f16" -- fp16 operands for the three big GEMMs when the features are generated
         cosine features (KS_PRECISION_F16 in include/keystone_b200.h); same mantissa, twice the tensor-core rate."""
         self.block_size, self.num_iter, self.lam, self.num_features_opt, self.ctx = block_size, num_iter, lam, num_features_opt, ctx
-        if precision not in ("tf32", "f16"):
-            raise ValueError("precision must be 'tf32' or 'f16'")
+        if precision not in ("tf32", "f16", "f16x2"):
+            raise ValueError("precision must be 'tf32', 'f16' or 'f16x2' (experimental split-operand mode)")
         self.precision = precision
         self.weight = 3 * num_iter + 1  # BlockLinearMapper.scala:204
 
@@ -260,7 +260,8 @@ class BlockLeastSquaresEstimator(LabelEstimator, WeightedNode):
         h = C.c_int64(0)
         check(ctx.handle, lib().ks_blockls_fit(ctx.handle, f, x, rfs, n, lb.handle, self.block_size, self.num_iter, self.lam,
                                                 self.num_features_opt or 0,
-                                                _capi.KS_PRECISION_F16 if self.precision == "f16" else _capi.KS_PRECISION_TF32,
+                                                {"tf32": _capi.KS_PRECISION_TF32, "f16": _capi.KS_PRECISION_F16,
+                                                 "f16x2": _capi.KS_PRECISION_F16X2}[self.precision],
                                                 C.byref(h)))
         return BlockLinearMapper(ctx, h.value)
 

@@ -263,6 +263,28 @@ def test_blockls_fit_f16_input_scale_invariance(ctx):
         assert rel < W_TOL, (sx, rel)
 
 
+EXPERIMENTAL = pytest.mark.skipif(os.environ.get("KS_TEST_EXPERIMENTAL") != "1",
+                                  reason="split-operand mode: written without GPU access, enable with KS_TEST_EXPERIMENTAL=1")
+
+
+@EXPERIMENTAL
+@pytest.mark.parametrize("bs,iters", [(256, 1), (200, 2)])
+def test_blockls_fit_f16x2_split_operands(ctx, bs, iters):
+    """KS_PRECISION_F16X2: same problem as the fp16 test, tolerance 100x tighter (model: 2e-7, tests/test_precision_model.py;
+    the tensor core's truncating fp32 accumulation is expected to leave ~1e-6)."""
+    n, k = 4000, 10
+    feats, F, cls = _cosine_problem(ctx, 4, n, 44, 256, k, 3)
+    y = ctx.labels_from_classes(cls, k)
+    Y = ko.class_label_indicators(cls, k)
+    model = ks.BlockLeastSquaresEstimator(bs, iters, 2.0, precision="f16x2").fit(feats, y)
+    assert ctx.last_fit_stats()["mma"] == "f16x2"
+    xs, b0, mus = ko.block_ls_fit(F, Y, bs, iters, 2.0)
+    Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
+    rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
+    assert rel < 5e-5, rel
+    assert np.abs(np.concatenate(model.feature_means) - np.concatenate(mus)).max() < 5e-6
+
+
 def test_blockls_f16_falls_back_to_tf32_for_materialized_features(ctx):
     rng = np.random.default_rng(12)
     F = rng.standard_normal((1500, 300)) * 1e4     # far outside fp16's range once squared: must not be computed in fp16

@@ -141,3 +141,60 @@ def test_residual_scale_must_be_global_across_ranks():
     assert s_loc[0] != s_loc[1]
     c_wrong = sum(s.T @ to_f16(r * sl) for s, r, sl in zip(S, R, s_loc)) / s_loc[0]   # summed as if one scale applied
     assert relfro(c_wrong, exact) > 1.0
+
+
+# ------------------------------------------------------------------------------------ split-operand mode (KS_PRECISION_F16X2)
+def split16(x):
+    hi = to_f16(x)
+    return hi, to_f16(x - hi)
+
+
+def model_fit_split(X, params, Y, lam):
+    """engine.cu::fit_blockls with x2 = true: every fp16 operand as hi + lo, products hi*hi + hi*lo + lo*hi; the projection as ONE
+    GEMM on operands concatenated along K ([x_hi | x_lo | x_hi] . [w_hi | w_hi | w_lo]^T), as make_feat_src builds them."""
+    n = X.shape[0]
+    ymean = Y.mean(0)
+    R = Y - ymean
+    sr = pow2_scale(np.abs(R).max(), 4096.0)
+    sx = pow2_scale(np.abs(X).max(), 4096.0)
+    xh, xl = split16(X * sx)
+    X3 = np.concatenate([xh, xl, xh], 1)
+    Ws = []
+    for W, bias in params:
+        Wf = W.astype(np.float32).astype(np.float64)
+        sw = pow2_scale(np.abs(Wf).max(), 4096.0)
+        wh, wl = split16(Wf * sw)
+        W3 = np.concatenate([wh, wh, wl], 1)
+        F = np.cos((X3 @ W3.T) / (sx * sw) + bias)
+        S = (F - F[: min(n, 1024)].mean(0)).astype(np.float32).astype(np.float64)      # the fp32 block before the split
+        sh, sl = split16(S)
+        delta = (sh + sl).mean(0)
+        cross = sh.T @ sl
+        G = sh.T @ sh + cross + cross.T - n * np.outer(delta, delta) + lam * np.eye(S.shape[1])
+        rh, rl = split16(R * sr)
+        C = (sh.T @ rh + sl.T @ rh + sh.T @ rl) / sr - n * np.outer(delta, R.mean(0))
+        dW = np.linalg.solve(G, C)
+        sd = pow2_scale(np.abs(dW).max(), 8192.0)
+        dh, dl = split16(dW * sd)
+        R = R - ((sh @ dh + sl @ dh + sh @ dl) / sd - delta @ dW)
+        Ws.append(dW)
+    return np.concatenate(Ws, 0)
+
+
+def test_split_operand_mode_reaches_fp32_class_accuracy():
+    X, params, Y = problem(seed=8)
+    W0 = model_fit(X, params, Y, 1.0, "exact")
+    e1 = relfro(model_fit(X, params, Y, 1.0, "f16"), W0)
+    e2 = relfro(model_fit_split(X, params, Y, 1.0), W0)
+    assert e2 < 1e-5 and e2 < e1 / 100, (e1, e2)          # SURVEY 8(d) parity-mode target: 1e-4
+
+
+def test_k_concatenation_equals_three_products():
+    rng = np.random.default_rng(9)
+    x, w = rng.standard_normal((50, 33)), rng.standard_normal((20, 33))
+    xh, xl = split16(x)
+    wh, wl = split16(w)
+    lhs = np.concatenate([xh, xl, xh], 1) @ np.concatenate([wh, wh, wl], 1).T
+    assert np.allclose(lhs, xh @ wh.T + xl @ wh.T + xh @ wl.T, rtol=0, atol=1e-12)
+    assert np.abs(lhs - x @ w.T).max() < 1e-5 * np.abs(x @ w.T).max() + 1e-6      # vs 5e-4 relative for the single fp16 product
+
