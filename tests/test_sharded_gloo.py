@@ -71,3 +71,47 @@ def test_sharded_blockls_algebra_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert len(ret) == world and all(v < 1e-9 for v in ret.values()), dict(ret)
+
+
+def _solve_worker(rank, world, port, ret):
+    """Host logic of the column-sharded solve and of the global residual scale (engine.cu::fit_blockls, world > 1)."""
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(5)
+        b, k = 48, 7                                          # k not divisible by the world size: uneven slices
+        A = rng.standard_normal((200, b))
+        H = A.T @ A + 0.5 * np.eye(b)
+        rhs = rng.standard_normal((b, k))
+        L = np.linalg.cholesky(H)
+        col0 = lambda r: k * r // world                       # rank r owns columns [k r / world, k (r+1) / world)
+        m0, m1 = col0(rank), col0(rank + 1)
+        full = np.asfortranarray(rhs.copy())                  # column-major like the device buffer: a slice is contiguous
+        y = np.linalg.solve(L, full[:, m0:m1])
+        full[:, m0:m1] = np.linalg.solve(L.T, y)              # in-place solve of the own slice
+        for r in range(world):                                # one broadcast per owner, in place (grouped on the device)
+            t = torch.from_numpy(np.ascontiguousarray(full[:, col0(r):col0(r + 1)].T))
+            dist.broadcast(t, src=r)
+            full[:, col0(r):col0(r + 1)] = t.numpy().T
+        ref = np.linalg.solve(H, rhs)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, full.tobytes())
+        # residual scale: every rank must use the power of two of the GLOBAL max |R| (ncclMax all-reduce of the bit pattern)
+        local_max = np.float32(3.0 if rank == 0 else 0.002)
+        bits = torch.tensor([int(np.float32(local_max).view(np.uint32))], dtype=torch.int64)
+        dist.all_reduce(bits, op=dist.ReduceOp.MAX)           # non-negative floats order like their bit patterns
+        gmax = np.array([bits.item()], dtype=np.uint32).view(np.float32)[0]
+        ret[rank] = (float(np.abs(full - ref).max()), all(g == gathered[0] for g in gathered), float(gmax))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_column_sharded_solve_and_global_scale_world2():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_solve_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for err, identical, gmax in ret.values():
+        assert err < 1e-10 and identical and gmax == 3.0      # same bytes on every rank; the global maximum everywhere
