@@ -457,3 +457,41 @@ def block_ls_solve_from_sums(G, C, sa, sr, n_total: int, lam: float, w_old: Opti
         Cc = Cc - lam * w_old
     dW = _solve_spd(Gc + lam * np.eye(G.shape[0]), Cc)
     return dW, delta
+
+
+# --------------------------------------------------------------------------------------
+# Evaluation ("next" row of SURVEY section 8(f): the consumer of BlockLinearMapper -> MaxClassifier output).
+# Restated for the parity tests of the on-device confusion matrix that follows the solver; not on the measured path yet.
+# --------------------------------------------------------------------------------------
+def confusion_matrix(predictions: np.ndarray, actuals: np.ndarray, num_classes: int) -> np.ndarray:
+    """K/evaluation/MulticlassClassifierEvaluator.scala:149-160: rows = true class, columns = predicted class, counts."""
+    cm = np.zeros((num_classes, num_classes))
+    np.add.at(cm, (np.asarray(actuals, dtype=np.int64), np.asarray(predictions, dtype=np.int64)), 1.0)
+    return cm
+
+
+def multiclass_metrics(cm: np.ndarray, beta: float = 1.0) -> dict:
+    """MulticlassMetrics (K/evaluation/MulticlassClassifierEvaluator.scala:23-54) over BinaryClassificationMetrics
+    (K/evaluation/BinaryClassifierEvaluator.scala:16-41): per-class contingency tables from the confusion matrix, macro =
+    mean over classes, micro = the metric of the merged (summed) table."""
+    cm = np.asarray(cm, dtype=np.float64)
+    total = cm.sum()
+    tp = np.diag(cm).copy()
+    fp = cm.sum(axis=0) - tp                 # predictedSums - tp
+    tn = total - cm.sum(axis=1) - fp         # total - actualsSums - fp
+    fn = total - tp - fp - tn
+
+    def fscore(tp_, fp_, fn_):
+        return (1.0 + beta * beta) * tp_ / ((1.0 + beta * beta) * tp_ + beta * beta * fn_ + fp_)
+
+    with np.errstate(invalid="ignore", divide="ignore"):
+        precision, recall = tp / (tp + fp), tp / (tp + fn)
+        accuracy = (tp + tn) / (tp + fp + tn + fn)
+        f = fscore(tp, fp, fn)
+        TP, FP, FN = tp.sum(), fp.sum(), fn.sum()
+        out = {"class_precision": precision, "class_recall": recall, "class_fscore": f,
+               "avg_accuracy": accuracy.mean(), "avg_error": 1.0 - accuracy.mean(),
+               "macro_precision": precision.mean(), "macro_recall": recall.mean(), "macro_fscore": f.mean(),
+               "total_accuracy": TP / (TP + FP), "total_error": FN / (FN + TP),
+               "micro_precision": TP / (TP + FP), "micro_recall": TP / (TP + FN), "micro_fscore": fscore(TP, FP, FN)}
+    return out

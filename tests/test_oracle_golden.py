@@ -235,3 +235,25 @@ def test_compute_cost_definition():
     assert np.isclose(c0, ((A @ W + b - Y) ** 2).sum() / 100.0)
     c1 = ko.compute_cost(A, Y, 0.3, xs, 4, b)
     assert np.isclose(c1, c0 + 0.15 * (W ** 2).sum())
+
+
+def test_multiclass_evaluator_known_answer():
+    """T/evaluation/MulticlassClassifierEvaluatorSuite.scala:9-68: the suite's 9 (prediction, label) pairs, its confusion
+    matrix and every metric it asserts (delta 1e-7)."""
+    pairs = [(0, 0), (0, 1), (0, 0), (1, 0), (1, 1), (1, 1), (1, 1), (2, 2), (2, 0)]
+    pred, act = np.array([p for p, _ in pairs]), np.array([a for _, a in pairs])
+    cm = ko.confusion_matrix(pred, act, 3)
+    assert np.array_equal(cm, np.array([[2, 1, 1], [1, 3, 0], [0, 0, 1]], dtype=float))   # rows = true class
+    p = [2.0 / 3, 3.0 / 4, 1.0 / 2]
+    r = [2.0 / 4, 3.0 / 4, 1.0]
+    f1 = [2 * a * b / (a + b) for a, b in zip(p, r)]
+    f2 = [5 * a * b / (4 * a + b) for a, b in zip(p, r)]
+    m1, m2 = ko.multiclass_metrics(cm), ko.multiclass_metrics(cm, beta=2.0)
+    d = 1e-7
+    assert np.abs(m1["class_precision"] - p).max() < d and np.abs(m1["class_recall"] - r).max() < d
+    assert np.abs(m1["class_fscore"] - f1).max() < d and np.abs(m2["class_fscore"] - f2).max() < d
+    assert abs(m1["micro_recall"] - 6.0 / 9.0) < d
+    assert abs(m1["micro_recall"] - m1["micro_precision"]) < d and abs(m1["micro_recall"] - m1["micro_fscore"]) < d
+    assert abs(m1["macro_precision"] - sum(p) / 3) < d and abs(m1["macro_recall"] - sum(r) / 3) < d
+    assert abs(m1["macro_fscore"] - sum(f1) / 3) < d and abs(m2["macro_fscore"] - sum(f2) / 3) < d
+    assert abs(m1["total_accuracy"] - 6.0 / 9.0) < d and abs(m1["total_error"] - 3.0 / 9.0) < d
