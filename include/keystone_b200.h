@@ -144,6 +144,11 @@ KS_API int32_t ks_model_apply_argmax(int64_t ctx, int64_t model, int64_t feature
 /* applyAndEvaluate (BlockLinearMapper.scala:95-137): the cumulative prediction after block j (intercept included). */
 KS_API int32_t ks_model_apply_partial(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs,
                                int32_t n_rfs, int32_t last_block, int64_t* out_predictions);
+/* EXPERIMENTAL (next row of the scope table, not yet validated on hardware): apply -> MaxClassifier on predictions and on the
+   +-1 indicator labels -> confusion matrix (K/evaluation/MulticlassClassifierEvaluator.scala:130-161), all on the device,
+   summed over the ranks; out_counts is k x k row-major, rows = true class, columns = predicted class.  Collective. */
+KS_API int32_t ks_model_confusion_matrix(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs,
+                                         int32_t n_rfs, int64_t labels, double* out_counts);
 /* BlockLeastSquaresEstimator.computeCost (K/nodes/learning/BlockLinearMapper.scala:142-187); collective. */
 KS_API int32_t ks_model_cost(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
                       int64_t labels, double lambda, double* out_cost);

@@ -18,3 +18,8 @@ from .nodes import (  # noqa: F401
     VectorCombiner,
     VectorSplitter,
 )
+from .evaluation import (  # noqa: F401  (experimental: the row after the solver)
+    BinaryClassificationMetrics,
+    MulticlassClassifierEvaluator,
+    MulticlassMetrics,
+)

@@ -88,6 +88,7 @@ def _declare(L: C.CDLL) -> None:
     sig("ks_model_apply_argmax", i64, i64, i64, i64, p_i64, i32, C.c_void_p)
     sig("ks_model_apply_partial", i64, i64, i64, i64, p_i64, i32, i32, p_i64)
     sig("ks_model_cost", i64, i64, i64, i64, p_i64, i32, i64, f64, p_f64)
+    sig("ks_model_confusion_matrix", i64, i64, i64, i64, p_i64, i32, i64, C.c_void_p)
     sig("ks_model_destroy", i64, i64)
     sig("ks_last_fit_stats_json", i64, C.c_char_p, i64)
     sig("ks_debug_gram", i64, i64, i64, C.c_void_p, i64, C.c_void_p, i64)

@@ -687,4 +687,18 @@ void launch_split_concat3(const float* src, int64_t ld_src, int64_t rows, int co
                                                                     pattern);
 }
 
+// ---- evaluation: confusion matrix counts[actual * k + predicted] += 1 (K/evaluation/MulticlassClassifierEvaluator.scala:149-160)
+__global__ void confusion_kernel(const int32_t* __restrict__ pred, const int32_t* __restrict__ act, int64_t n, int k,
+                                 unsigned long long* __restrict__ counts) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int p = pred[i], a = act[i];
+    if (static_cast<unsigned>(p) < static_cast<unsigned>(k) && static_cast<unsigned>(a) < static_cast<unsigned>(k))
+      atomicAdd(counts + static_cast<int64_t>(a) * k + p, 1ULL);
+  }
+}
+void launch_confusion(const int32_t* pred, const int32_t* act, int64_t n, int k, unsigned long long* counts, cudaStream_t st) {
+  if (n == 0) return;
+  confusion_kernel<<<grid_for(n, 256), 256, 0, st>>>(pred, act, n, k, counts);
+}
+
 }  // namespace ks

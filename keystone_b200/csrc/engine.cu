@@ -1581,6 +1581,34 @@ KS_API int32_t ks_model_apply_argmax(int64_t ctx, int64_t model, int64_t feature
     c.check_async("apply_argmax");
   });
 }
+KS_API int32_t ks_model_confusion_matrix(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs,
+                                         int32_t n_rfs, int64_t labels, double* out_counts) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!out_counts) throw KsError{KS_ERR_INVALID, "null output"};
+    Model& m = c.model(model);
+    Matrix& L = c.matrix(labels);
+    FeatSrc src;
+    make_feat_src(c, features, x_in, rfs, n_rfs, src);
+    if (L.rows != src.n_rows || L.cols != m.k) throw KsError{KS_ERR_INVALID, "labels shape mismatch"};
+    const int k = static_cast<int>(m.k);
+    auto y = apply_model(c, m, src, -1, true);
+    DevBuf pred, act, counts;
+    pred.alloc(sizeof(int32_t) * static_cast<size_t>(std::max<int64_t>(y->rows, 1)));
+    act.alloc(pred.bytes);
+    counts.alloc(sizeof(unsigned long long) * static_cast<size_t>(k) * k);
+    KS_CUDA(cudaMemsetAsync(counts.p, 0, counts.bytes, c.st));
+    launch_argmax_rows(y->d, y->ld, y->rows, k, pred.as<int32_t>(), c.st);   // MaxClassifier on the predictions ...
+    launch_argmax_rows(L.d, L.ld, L.rows, k, act.as<int32_t>(), c.st);       // ... and on the +-1 indicator labels
+    launch_confusion(pred.as<int32_t>(), act.as<int32_t>(), y->rows, k, counts.as<unsigned long long>(), c.st);
+    c.launches += 3;
+    if (c.world > 1)
+      KS_NCCL(nccl_api().AllReduce(counts.p, counts.p, static_cast<size_t>(k) * k, ncclUint64, ncclSum, c.comm, c.st));
+    std::vector<unsigned long long> h(static_cast<size_t>(k) * k);
+    KS_CUDA(cudaMemcpyAsync(h.data(), counts.p, counts.bytes, cudaMemcpyDeviceToHost, c.st));
+    c.check_async("confusion_matrix");
+    for (size_t i = 0; i < h.size(); ++i) out_counts[i] = static_cast<double>(h[i]);
+  });
+}
 KS_API int32_t ks_model_cost(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
                       int64_t labels, double lambda, double* out_cost) {
   return guard(ctx, [&](Ctx& c) {

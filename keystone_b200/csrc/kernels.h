@@ -94,6 +94,8 @@ void launch_pack_update(const double* dW, double* Wmodel, const double* delta, f
 void launch_pack_apply(const double* W, const double* mean_or_null, const double* intercept_or_null, float* bop_hi,
                        int ldb, float* cbias, int b, int k, int kpad, cudaStream_t st);
 void launch_argmax_rows(const float* Y, int64_t ld, int64_t rows, int k, int32_t* out, cudaStream_t st);
+// counts[actual * k + predicted] += 1 over n samples (counts must be zeroed); out-of-range classes are skipped
+void launch_confusion(const int32_t* pred, const int32_t* act, int64_t n, int k, unsigned long long* counts, cudaStream_t st);
 void launch_sq_err(const float* Y, int64_t ldy, const float* L, int64_t ldl, int64_t rows, int k, double* out,
                    cudaStream_t st);
 void launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);

@@ -141,3 +141,22 @@ def test_estimator_constants_match_reference():
     assert np.isclose(c, 3 * (max(3.8e-4 * flops, 2.9e-1 * byt) + 1.32 * net))
     assert ks.VectorSplitter(5).bounds(12) == [(0, 5), (5, 10), (10, 12)]
     assert ks.VectorSplitter(8, 12).bounds(20) == [(0, 8), (8, 12)]
+
+
+def test_multiclass_metrics_host_formulas_match_the_reference_suite():
+    """T/evaluation/MulticlassClassifierEvaluatorSuite.scala:9-68 through the product's host-side metric formulas, and the
+    same numbers from the oracle restatement (the device part, the counting, is exercised by the GPU tests)."""
+    import numpy as np
+    import keystone_b200 as ks
+    from oracle import keystone_oracle as ko
+    cm = np.array([[2, 1, 1], [1, 3, 0], [0, 0, 1]], dtype=float)
+    m = ks.MulticlassClassifierEvaluator.from_confusion_matrix(cm)
+    o = ko.multiclass_metrics(cm)
+    assert abs(m.classMetrics[0].precision - 2.0 / 3) < 1e-12 and abs(m.classMetrics[2].recall - 1.0) < 1e-12
+    assert abs(m.microRecall - 6.0 / 9) < 1e-12 and abs(m.microPrecision - m.microRecall) < 1e-12
+    for mine, theirs in [(m.macroPrecision, o["macro_precision"]), (m.macroRecall, o["macro_recall"]),
+                         (m.macroFScore(), o["macro_fscore"]), (m.microFScore(), o["micro_fscore"]),
+                         (m.totalAccuracy, o["total_accuracy"]), (m.totalError, o["total_error"]),
+                         (m.avgAccuracy, o["avg_accuracy"]), (m.avgError, o["avg_error"])]:
+        assert abs(mine - theirs) < 1e-12
+    assert abs(m.macroFScore(2.0) - ko.multiclass_metrics(cm, beta=2.0)["macro_fscore"]) < 1e-12

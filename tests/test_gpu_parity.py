@@ -418,3 +418,22 @@ def test_chol_solve_kernel(ctx, n, k):
         out[use_cusolver] = (X, ms.value)
         assert np.abs(X - ref).max() < 1e-9 * max(1.0, np.abs(ref).max()) * np.linalg.cond(H)
     print(f"chol_solve n={n} k={k}: kernel {out[0][1]:.3f} ms, cusolver potrs {out[1][1]:.3f} ms")
+
+
+@EXPERIMENTAL
+def test_device_confusion_matrix_matches_oracle(ctx):
+    """ks_model_confusion_matrix: apply -> MaxClassifier -> counts on the device vs the oracle's confusion matrix of the same
+    predictions (integer counts: exact)."""
+    rng = np.random.default_rng(31)
+    n, d, k = 5000, 60, 7
+    F = rng.standard_normal((n, d))
+    cls = rng.integers(0, k, n)
+    Y = ko.class_label_indicators(cls, k)
+    model = ks.BlockLeastSquaresEstimator(32, 1, 1.0).fit(ctx.matrix(F), ctx.matrix(Y))
+    pred = model.apply_argmax(ctx.matrix(F))
+    metrics = ks.MulticlassClassifierEvaluator(k).evaluate_model(model, ctx.matrix(F), ctx.matrix(Y))
+    ref = ko.confusion_matrix(pred, cls, k)
+    assert np.array_equal(metrics.confusionMatrix, ref)
+    assert metrics.confusionMatrix.sum() == n
+    assert abs(metrics.totalAccuracy - (pred == cls).mean()) < 1e-12
+
