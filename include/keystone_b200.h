@@ -72,7 +72,11 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
 KS_API int32_t ks_ctx_destroy(int64_t ctx);
 KS_API const char* ks_last_error(int64_t ctx);
 KS_API int32_t ks_ctx_synchronize(int64_t ctx);
-/* tunables: "gram_chunk_rows", "sample_rows" */
+/* tunables (defaults in brackets): "gram_chunk_rows" [0 = chosen from the local row count], "sample_rows" [16384: rows per rank
+ * for the shift estimate of generated features], "precision" [0; 1 selects KS_PRECISION_F16 for fits called with TF32],
+ * "gram_pair" [1: cta_group::2 kernels], "epi_multi" [1: rotating epilogue staging buffers], "proj_f16" [1: fp16 projection
+ * operands in fp16 mode], "shard_solve" [1: triangular solves sharded by right-hand-side columns over the ranks],
+ * "reserve_sms" [8], "timing" [1]; experimental: "custom_solve", "inv_min_world", "exclusive_solve_min_world". */
 KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value);
 
 /* ---- row-sharded matrices (this rank's rows) ---------------------------------------------
