@@ -18,15 +18,22 @@ Pinning status
 * ``standard_scaler_*``: PINNED by the golden rows of ``T/nodes/stats/StandardScalerSuite.scala``.
 * ``cosine_random_features``, ``vector_splitter``, ``block_linear_apply``,
   ``linear_map_fit``: PINNED by the formula / known-answer tests of the matching suites.
-* ``block_ls_fit``: **parity unpinned** at the mlmatrix boundary.  Its arithmetic lives in
-  the un-vendored dependency ``edu.berkeley.cs.amplab:mlmatrix:0.2`` (``build.sbt:44``) and
-  no reference test pins its numerical output.  It restates the published algorithm of
-  ``BlockCoordinateDescent.solveOnePassL2`` / ``solveLeastSquaresWithL2`` with
-  ``NormalEquations`` (per block: tree-summed ``(A_j^T A_j, A_j^T r)``, then
-  ``(A_j^T A_j + lambda I) \\ A_j^T r``, lambda un-scaled, sequential block order) and is
-  anchored on the call site ``K/nodes/learning/BlockLinearMapper.scala:212-243`` plus the
-  invariants checked in ``tests/test_oracle_golden.py`` (nb=1 == closed-form centred ridge
-  == ``LinearMapEstimator``; many sweeps converge to the same; LinearMapperSuite known answer).
+* ``block_ls_fit``: PINNED INDIRECTLY through in-repo reference arithmetic.  Its own arithmetic
+  lives in the un-vendored dependency ``edu.berkeley.cs.amplab:mlmatrix:0.2`` (``build.sbt:44``)
+  and no reference test pins its numerical output directly.  But ``trainWithL2`` with
+  ``mixtureWeight = 0`` (``K/nodes/learning/BlockWeightedLeastSquares.scala:216-273``, which the
+  reference's suite pins on the fixtures) is algebraically the same block coordinate descent with
+  ``lambda * N``: ``tests/test_oracle_golden.py::test_block_ls_pinned_by_bwls_with_zero_mixture_weight``
+  checks ``bwls_fit(A, B, b, it, lam, 0) == block_ls_fit(A, B, b, it, lam * N)`` (weights and the
+  folded intercept ``ybar - sum_j mu_j^T W_j``) to 1e-12 on ``aMat/bMat`` for b = 4, 5, 12 and
+  1-3 sweeps, and the GPU tests check the same identity through ``ks_blockwls_fit`` /
+  ``ks_blockls_fit``.  What REMAINS UNPINNED is mlmatrix's own conventions, which no in-repo code
+  shows: that ``NormalEquations`` adds ``lambda`` un-scaled by N (taken from the call site
+  ``K/nodes/learning/BlockLinearMapper.scala:234-240`` passing ``Array(lambda)`` straight through),
+  and the block order of multi-sweep ``solveLeastSquaresWithL2`` (sequential assumed, as in
+  ``trainWithL2`` ``:179-180``).  Further invariants in ``tests/test_oracle_golden.py``: nb = 1 ==
+  closed-form centred ridge == ``LinearMapEstimator``; many sweeps converge to the same;
+  LinearMapperSuite known answer.
 """
 from __future__ import annotations
 

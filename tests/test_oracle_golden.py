@@ -257,3 +257,29 @@ def test_multiclass_evaluator_known_answer():
     assert abs(m1["macro_precision"] - sum(p) / 3) < d and abs(m1["macro_recall"] - sum(r) / 3) < d
     assert abs(m1["macro_fscore"] - sum(f1) / 3) < d and abs(m2["macro_fscore"] - sum(f2) / 3) < d
     assert abs(m1["total_accuracy"] - 6.0 / 9.0) < d and abs(m1["total_error"] - 3.0 / 9.0) < d
+
+
+# ---- pin of block_ls_fit on in-repo reference arithmetic ---------------------------------------------------------------
+@pytest.mark.parametrize("bs", [4, 5, 12])
+@pytest.mark.parametrize("iters", [1, 2, 3])
+def test_block_ls_pinned_by_bwls_with_zero_mixture_weight(golden_dir, bs, iters):
+    """`trainWithL2` with mixtureWeight = 0 (K/nodes/learning/BlockWeightedLeastSquares.scala:216-273: jointXTX = popCov =
+    A_c^T A_c / N, jointXTR = popXTR - popMean * residualMean, solve (popCov + lambda I) dW = jointXTR - lambda W) is
+    algebraically the BlockLS step with lambda * N: (A_c^T A_c + lambda N I) dW = A_c^T R - lambda N W.  The reference's own
+    suite pins `trainWithL2` on these fixtures, so this identity ties `block_ls_fit` (whose mlmatrix arithmetic is absent from
+    /root/reference) to reference code that IS in the repo: weights per block and the folded intercept
+    ybar - sum_j mu_j^T W_j (:314-319) must agree to rounding."""
+    A, B = _load(golden_dir, "aMat.csv", "bMat.csv")
+    n = A.shape[0]
+    lam = 0.1
+    xs_w, final_b = ko.bwls_fit(A, B, bs, iters, lam, 0.0)
+    xs, ybar, mus = ko.block_ls_fit(A, B, bs, iters, lam * n)
+    for xw, x in zip(xs_w, xs):
+        assert np.abs(xw - x).max() < 1e-12
+    folded = ybar - sum(mu @ x for mu, x in zip(mus, xs))
+    assert np.abs(final_b - folded).max() < 1e-12
+    # and on the shuffled fixture (rows regrouped by class inside trainWithL2: the BlockLS result is row-order invariant)
+    As, Bs = _load(golden_dir, "aMatShuffled.csv", "bMatShuffled.csv")
+    xs_s, _, _ = ko.block_ls_fit(As, Bs, bs, iters, lam * n)
+    for xw, x in zip(xs_w, xs_s):
+        assert np.abs(xw - x).max() < 1e-10
