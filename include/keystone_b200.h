@@ -50,14 +50,18 @@ extern "C" {
 #define KS_ERR_HANDLE (-6)
 #define KS_ERR_NOT_SPD (-7)
 
-/* precision_mode of the fit/apply entry points */
-#define KS_PRECISION_TF32 0  /* operands rounded to tf32 (round-to-nearest), fp32 accumulate, fp64 solve */
-#define KS_PRECISION_F16 1   /* ks_blockls_fit on generated (cosine) features: fp16 operands (same 10-bit mantissa as tf32,
-                                residual / increments scaled by device-chosen powers of two), kind::f16 MMA at twice the
-                                tf32 rate, fp32 accumulate, fp64 solve; materialised feature matrices fall back to tf32 */
-#define KS_PRECISION_F16X2 2 /* EXPERIMENTAL (not yet validated on hardware): every fp16 operand carried as hi + lo (21 significant
-                                bits), products keep hi*hi + hi*lo + lo*hi on the same kernels; ~3x the fp16 tensor work;
-                                ks_blockls_fit on generated features only (others fall back to tf32) */
+/* precision_mode of the fit entry points.  All modes accumulate in fp32 inside the tensor core, assemble and solve the
+ * reduced b x b systems in fp64 (centring correction, Cholesky, triangular solves) and keep the model in fp64. */
+#define KS_PRECISION_DEFAULT (-1) /* the context's setting (ks_ctx_set_option "precision"; initial value KS_PRECISION_F16X2) */
+#define KS_PRECISION_TF32 0  /* one tf32 MMA per product: operands rounded to tf32 (10-bit mantissa, round-to-nearest) */
+#define KS_PRECISION_F16 1   /* fast mode.  Generated (cosine) features: fp16 operands (same 10-bit mantissa as tf32, residual /
+                                increments scaled by device-chosen powers of two), kind::f16 MMA at twice the tf32 rate;
+                                materialised feature matrices fall back to KS_PRECISION_TF32 */
+#define KS_PRECISION_F16X2 2 /* parity mode (split operands): every MMA operand v is carried as hi + lo (hi = round(v),
+                                lo = round(v - hi): >= 21 significant bits) and every product keeps hi*hi + hi*lo + lo*hi on the
+                                same kernels.  Generated features: fp16 pairs (kind::f16, ~3x the fast mode's tensor work);
+                                materialised feature matrices: tf32 pairs (kind::tf32).  Measured against the fp64 oracle:
+                                see DESIGN.md section 6 */
 
 #define KS_NCCL_ID_BYTES 128
 
@@ -73,10 +77,13 @@ KS_API int32_t ks_ctx_destroy(int64_t ctx);
 KS_API const char* ks_last_error(int64_t ctx);
 KS_API int32_t ks_ctx_synchronize(int64_t ctx);
 /* tunables (defaults in brackets): "gram_chunk_rows" [0 = chosen from the local row count], "sample_rows" [16384: rows per rank
- * for the shift estimate of generated features], "precision" [0; 1 selects KS_PRECISION_F16 for fits called with TF32],
- * "gram_pair" [1: cta_group::2 kernels], "epi_multi" [1: rotating epilogue staging buffers], "proj_f16" [1: fp16 projection
- * operands in fp16 mode], "shard_solve" [1: triangular solves sharded by right-hand-side columns over the ranks],
- * "reserve_sms" [8], "timing" [1]; experimental: "custom_solve", "inv_min_world", "exclusive_solve_min_world". */
+ * for the shift estimate of generated features], "precision" [2 = KS_PRECISION_F16X2: what KS_PRECISION_DEFAULT and the entry
+ * points without a precision argument use], "gram_pair" [1: cta_group::2 kernels], "epi_multi" [1: rotating epilogue staging
+ * buffers], "proj_f16" [1: fp16 projection operands in fp16 mode], "shard_solve" [1: triangular solves sharded by
+ * right-hand-side columns over the ranks], "reserve_sms" [8], "timing" [1], "pipeline" [1: all tensor-core kernels of a fit on
+ * one stream, solve / factor chains beside it; 0: the two-stream arrangement of round 1], "host_mirror" [1: fits copy each
+ * finished model block into pinned host memory while they run]; "custom_solve" [0: cusolverDnDpotrs; 1: the library's
+ * own multi-right-hand-side triangular solve kernel]. */
 KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value);
 
 /* ---- row-sharded matrices (this rank's rows) ---------------------------------------------
@@ -139,6 +146,11 @@ KS_API int32_t ks_model_block_rows(int64_t ctx, int64_t model, int32_t j, int64_
 KS_API int32_t ks_model_get_block(int64_t ctx, int64_t model, int32_t j, double* W_colmajor_out, double* mean_out,
                            int32_t* has_mean);
 KS_API int32_t ks_model_get_intercept(int64_t ctx, int64_t model, double* b_out, int32_t* has_intercept);
+/* Zero-copy access to the model's pinned host mirror (written by async device-to-host copies while the fit was still running):
+ * *W_ptr = block j, column-major rows_j x k; *mean_ptr = rows_j means or NULL; *intercept_ptr = k values or NULL.  The pointers
+ * stay valid until ks_model_destroy.  Any argument may be NULL.  (A JNI caller hands them to SetDoubleArrayRegion.) */
+KS_API int32_t ks_model_host_view(int64_t ctx, int64_t model, int32_t j, const double** W_ptr, const double** mean_ptr,
+                                  const double** intercept_ptr);
 /* BlockLinearMapper.apply(RDD) :40-73 -> new (N x k) matrix of predictions. */
 KS_API int32_t ks_model_apply(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
                        int64_t* out_predictions);
@@ -148,8 +160,7 @@ KS_API int32_t ks_model_apply_argmax(int64_t ctx, int64_t model, int64_t feature
 /* applyAndEvaluate (BlockLinearMapper.scala:95-137): the cumulative prediction after block j (intercept included). */
 KS_API int32_t ks_model_apply_partial(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs,
                                int32_t n_rfs, int32_t last_block, int64_t* out_predictions);
-/* EXPERIMENTAL (next row of the scope table, not yet validated on hardware): apply -> MaxClassifier on predictions and on the
-   +-1 indicator labels -> confusion matrix (K/evaluation/MulticlassClassifierEvaluator.scala:130-161), all on the device,
+/* apply -> MaxClassifier on predictions and on the +-1 indicator labels -> confusion matrix (K/evaluation/MulticlassClassifierEvaluator.scala:130-161), all on the device,
    summed over the ranks; out_counts is k x k row-major, rows = true class, columns = predicted class.  Collective. */
 KS_API int32_t ks_model_confusion_matrix(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs,
                                          int32_t n_rfs, int64_t labels, double* out_counts);
@@ -173,7 +184,8 @@ KS_API int32_t ks_debug_gram(int64_t ctx, int64_t a, int64_t b, double* out_g, i
 KS_API int32_t ks_debug_time_gram(int64_t ctx, int64_t a, int64_t b, int32_t iters, double* out_ms);
 
 /* X = H^-1 B for a symmetric positive definite H (column-major n x n) and B (column-major n x k): Cholesky with cuSOLVER, then
- * either the library's single-kernel multi-RHS solve (use_cusolver = 0, the product path) or cusolverDnDpotrs; best-of-3 ms. */
+ * either the library's own multi-RHS solve kernel (use_cusolver = 0; option "custom_solve") or cusolverDnDpotrs (the default of
+ * the fits); best-of-3 ms. */
 KS_API int32_t ks_debug_chol_solve(int64_t ctx, const double* H_colmajor, int32_t n, const double* B_colmajor, int32_t k,
                                    int32_t use_cusolver, double* X_out, double* out_ms);
 

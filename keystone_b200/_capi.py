@@ -17,7 +17,10 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "keystone_b200.h")
 KS_NCCL_ID_BYTES = 128
 KS_PRECISION_TF32 = 0
 KS_PRECISION_F16 = 1
-KS_PRECISION_F16X2 = 2  # experimental
+KS_PRECISION_F16X2 = 2  # split-operand parity mode
+KS_PRECISION_DEFAULT = -1
+PRECISIONS = {"tf32": KS_PRECISION_TF32, "f16": KS_PRECISION_F16, "f16x2": KS_PRECISION_F16X2, "parity": KS_PRECISION_F16X2,
+              "default": KS_PRECISION_DEFAULT}
 
 
 class KeystoneError(RuntimeError):
@@ -84,6 +87,7 @@ def _declare(L: C.CDLL) -> None:
     sig("ks_model_block_rows", i64, i64, i32, p_i64)
     sig("ks_model_get_block", i64, i64, i32, C.c_void_p, C.c_void_p, p_i32)
     sig("ks_model_get_intercept", i64, i64, C.c_void_p, p_i32)
+    sig("ks_model_host_view", i64, i64, i32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p))
     sig("ks_model_apply", i64, i64, i64, i64, p_i64, i32, p_i64)
     sig("ks_model_apply_argmax", i64, i64, i64, i64, p_i64, i32, C.c_void_p)
     sig("ks_model_apply_partial", i64, i64, i64, i64, p_i64, i32, i32, p_i64)

@@ -181,7 +181,7 @@ void launch_init_residual(const float* Y, int64_t ldy, const double* ymean, floa
 
 // block (32, 8), 4 columns per thread: same access pattern as colsum_kernel, plus the rounded copy.
 __global__ void round_colsum_kernel(const float* __restrict__ R, float* __restrict__ Rr, int64_t ld, int64_t rows, int k,
-                                    double* __restrict__ sums, int64_t rows_per_block) {
+                                    double* __restrict__ sums, int64_t rows_per_block, float* __restrict__ Rlo) {
   __shared__ double red[8][128];
   const int c4 = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int64_t r_begin = blockIdx.y * rows_per_block;
@@ -191,18 +191,21 @@ __global__ void round_colsum_kernel(const float* __restrict__ R, float* __restri
     for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
       const float4 v = *reinterpret_cast<const float4*>(R + r * ld + c4);
       const float in[4] = {v.x, v.y, v.z, v.w};
-      float o[4];
+      float o[4], l[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = c4 + j;
         if (c < k) {
           a[j] += in[j];
           o[j] = round_tf32_aux(in[j]);
+          l[j] = round_tf32_aux(in[j] - o[j]);  // split-operand mode: the tf32 rounding error, itself exact in fp32
         } else {
           o[j] = 0.f;
+          l[j] = 0.f;
         }
       }
       *reinterpret_cast<float4*>(Rr + r * ld + c4) = make_float4(o[0], o[1], o[2], o[3]);
+      if (Rlo) *reinterpret_cast<float4*>(Rlo + r * ld + c4) = make_float4(l[0], l[1], l[2], l[3]);
     }
   }
 #pragma unroll
@@ -217,17 +220,17 @@ __global__ void round_colsum_kernel(const float* __restrict__ R, float* __restri
     if (c < k) atomicAdd(sums + c, s);
   }
 }
-void launch_round_colsum(const float* R, float* Rr, int64_t ld, int64_t rows, int k, double* sums, cudaStream_t st) {
+void launch_round_colsum(const float* R, float* Rr, int64_t ld, int64_t rows, int k, double* sums, cudaStream_t st, float* Rlo) {
   if (rows == 0) return;
   const int64_t rpb = 1024;
   dim3 grid(static_cast<unsigned>((ld + 127) / 128), static_cast<unsigned>((rows + rpb - 1) / rpb));
-  round_colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(R, Rr, ld, rows, k, sums, rpb);
+  round_colsum_kernel<<<grid, dim3(32, 8), 0, st>>>(R, Rr, ld, rows, k, sums, rpb, Rlo);
 }
 
 // block (32, 8), 4 columns per thread, rows strided by 8 (coalesced 512 B per warp-row); optional column sums
 __global__ void center_round_kernel(const float* __restrict__ F, int64_t ldf, int c0, const float* __restrict__ shift,
                                     float* __restrict__ slab, float* __restrict__ colsum, int64_t lds, int64_t rows, int cols,
-                                    int64_t rows_per_block) {
+                                    int64_t rows_per_block, float* __restrict__ slab_lo) {
   __shared__ float red[8][128];
   const int c4 = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int64_t r_begin = blockIdx.y * rows_per_block;
@@ -238,13 +241,16 @@ __global__ void center_round_kernel(const float* __restrict__ F, int64_t ldf, in
 #pragma unroll
     for (int j = 0; j < 4; ++j) sh[j] = (c4 + j < cols) ? shift[c4 + j] : 0.f;
     for (int64_t r = r_begin + threadIdx.y; r < r_end; r += 8) {
-      float o[4];
+      float o[4], l[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        o[j] = (c4 + j < cols) ? round_tf32_aux(F[r * ldf + c0 + c4 + j] - sh[j]) : 0.f;  // c0 may be unaligned: scalar loads
-        a[j] += o[j];
+        const float v = (c4 + j < cols) ? F[r * ldf + c0 + c4 + j] - sh[j] : 0.f;  // c0 may be unaligned: scalar loads
+        o[j] = round_tf32_aux(v);
+        l[j] = slab_lo ? round_tf32_aux(v - o[j]) : 0.f;  // split-operand mode: hi + lo carries 21 bits of v
+        a[j] += o[j] + l[j];
       }
       *reinterpret_cast<float4*>(slab + r * lds + c4) = make_float4(o[0], o[1], o[2], o[3]);
+      if (slab_lo) *reinterpret_cast<float4*>(slab_lo + r * lds + c4) = make_float4(l[0], l[1], l[2], l[3]);
     }
   }
   if (colsum == nullptr) return;
@@ -261,11 +267,11 @@ __global__ void center_round_kernel(const float* __restrict__ F, int64_t ldf, in
   }
 }
 void launch_center_round(const float* F, int64_t ldf, int c0, const float* shift, float* slab, float* colsum, int64_t lds,
-                         int64_t rows, int cols, cudaStream_t st) {
+                         int64_t rows, int cols, cudaStream_t st, float* slab_lo) {
   if (rows == 0) return;
   const int64_t rpb = 256;
   dim3 grid(static_cast<unsigned>((lds + 127) / 128), static_cast<unsigned>((rows + rpb - 1) / rpb));
-  center_round_kernel<<<grid, dim3(32, 8), 0, st>>>(F, ldf, c0, shift, slab, colsum, lds, rows, cols, rpb);
+  center_round_kernel<<<grid, dim3(32, 8), 0, st>>>(F, ldf, c0, shift, slab, colsum, lds, rows, cols, rpb, slab_lo);
 }
 
 __global__ void divide_by_count_kernel(const double* __restrict__ sums, const double* __restrict__ count, float* out,
@@ -353,7 +359,7 @@ __global__ void pack_update_kernel(const double* __restrict__ dW, double* __rest
       if (delta) acc += delta[f] * w;
       const float wf = static_cast<float>(w);
       h = round_tf32_aux(wf);
-      l = static_cast<float>(w - static_cast<double>(h));
+      l = round_tf32_aux(static_cast<float>(w - static_cast<double>(h)));
     }
     bop_hi[static_cast<int64_t>(c) * ldb + f] = h;
     if (bop_lo) bop_lo[static_cast<int64_t>(c) * ldb + f] = l;
@@ -372,20 +378,24 @@ void launch_pack_update(const double* dW, double* Wmodel, const double* delta, f
   pack_update_kernel<<<kpad, 256, 0, st>>>(dW, Wmodel, delta, bop_hi, bop_lo, ldb, cbias, b, k);
 }
 
-__global__ void pack_apply_kernel(const double* __restrict__ W, const double* __restrict__ mean,
-                                  const double* __restrict__ intercept, float* __restrict__ bop_hi, int ldb,
-                                  float* __restrict__ cbias, int b, int k) {
+// cbias[c] = intercept[c] - sum_f (mean[f] - shift32[f]) W[f][c]: the slab was shifted by shift32 = fp32(mean), the rest of the
+// mean goes into the constant
+__global__ void pack_apply_kernel(const double* __restrict__ W, const double* __restrict__ mean, const float* __restrict__ shift32,
+                                  const double* __restrict__ intercept, float* __restrict__ bop_hi, float* __restrict__ bop_lo,
+                                  int ldb, float* __restrict__ cbias, int b, int k) {
   const int c = blockIdx.x;
   __shared__ double red[256];
   double acc = 0;
   for (int f = threadIdx.x; f < ldb; f += blockDim.x) {
-    float h = 0.f;
+    float h = 0.f, l = 0.f;
     if (c < k && f < b) {
       const double w = W[static_cast<int64_t>(c) * b + f];
-      if (mean) acc -= mean[f] * w;
+      if (mean) acc -= (mean[f] - static_cast<double>(shift32[f])) * w;
       h = round_tf32_aux(static_cast<float>(w));
+      l = round_tf32_aux(static_cast<float>(w - static_cast<double>(h)));
     }
     bop_hi[static_cast<int64_t>(c) * ldb + f] = h;
+    if (bop_lo) bop_lo[static_cast<int64_t>(c) * ldb + f] = l;
   }
   red[threadIdx.x] = acc;
   __syncthreads();
@@ -395,24 +405,26 @@ __global__ void pack_apply_kernel(const double* __restrict__ W, const double* __
   }
   if (threadIdx.x == 0) cbias[c] = static_cast<float>(red[0] + ((intercept && c < k) ? intercept[c] : 0.0));
 }
-void launch_pack_apply(const double* W, const double* mean_or_null, const double* intercept_or_null, float* bop_hi,
-                       int ldb, float* cbias, int b, int k, int kpad, cudaStream_t st) {
+void launch_pack_apply(const double* W, const double* mean_or_null, const float* shift32, const double* intercept_or_null,
+                       float* bop_hi, float* bop_lo, int ldb, float* cbias, int b, int k, int kpad, cudaStream_t st) {
   if (kpad == 0) return;
-  pack_apply_kernel<<<kpad, 256, 0, st>>>(W, mean_or_null, intercept_or_null, bop_hi, ldb, cbias, b, k);
+  pack_apply_kernel<<<kpad, 256, 0, st>>>(W, mean_or_null, shift32, intercept_or_null, bop_hi, bop_lo, ldb, cbias, b, k);
 }
 
 // CosineRandomFeatures W is (n_out x n_in) column-major fp64 (Breeze); the GEMM wants row-major [n_out][ld] tf32
-__global__ void w_to_operand_kernel(const double* __restrict__ W, int64_t n_out, int64_t n_in, float* __restrict__ dst, int64_t ld) {
+__global__ void w_to_operand_kernel(const double* __restrict__ W, int64_t n_out, int64_t n_in, float* __restrict__ dst, int64_t ld,
+                                    bool round) {
   const int64_t total = n_out * ld;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t o = i / ld, c = i - o * ld;
-    dst[i] = c < n_in ? round_tf32_aux(static_cast<float>(W[c * n_out + o])) : 0.f;
+    const float v = c < n_in ? static_cast<float>(W[c * n_out + o]) : 0.f;
+    dst[i] = round ? round_tf32_aux(v) : v;
   }
 }
-void launch_w_to_operand(const double* W_colmajor, int64_t n_out, int64_t n_in, float* dst, int64_t ld, cudaStream_t st) {
+void launch_w_to_operand(const double* W_colmajor, int64_t n_out, int64_t n_in, float* dst, int64_t ld, cudaStream_t st, bool round) {
   if (n_out == 0) return;
-  w_to_operand_kernel<<<grid_for(n_out * ld, 256), 256, 0, st>>>(W_colmajor, n_out, n_in, dst, ld);
+  w_to_operand_kernel<<<grid_for(n_out * ld, 256), 256, 0, st>>>(W_colmajor, n_out, n_in, dst, ld, round);
 }
 
 // ------------------------------------------------------------------ MaxClassifier (K/nodes/util/MaxClassifier.scala:9-11)
@@ -433,7 +445,7 @@ __global__ void argmax_rows_kernel(const float* __restrict__ Y, int64_t ld, int6
       const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
       if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    if (lane == 0) out[r] = bi;
+    if (lane == 0) out[r] = bi < k ? bi : 0;  // all-NaN / all -inf row: an in-range index, like Breeze's argmax
   }
 }
 void launch_argmax_rows(const float* Y, int64_t ld, int64_t rows, int k, int32_t* out, cudaStream_t st) {

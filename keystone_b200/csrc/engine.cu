@@ -44,27 +44,6 @@ SolverApi& solver_api() {
       load_sym(api.lib, "cusolverDnDpotrf_bufferSize", api.DpotrfBufferSize, "libcusolver");
       load_sym(api.lib, "cusolverDnDpotrf", api.Dpotrf, "libcusolver");
       load_sym(api.lib, "cusolverDnDpotrs", api.Dpotrs, "libcusolver");
-      load_sym(api.lib, "cusolverDnDpotri_bufferSize", api.DpotriBufferSize, "libcusolver");
-      load_sym(api.lib, "cusolverDnDpotri", api.Dpotri, "libcusolver");
-    } catch (const KsError& e) {
-      fail = e.msg;
-    }
-  });
-  if (!fail.empty()) throw KsError{KS_ERR_SOLVER, fail};
-  return api;
-}
-BlasApi& blas_api() {
-  static BlasApi api;
-  static std::once_flag once;
-  static std::string fail;
-  std::call_once(once, [] {
-    try {
-      api.lib = open_first({"libcublas.so.12", "libcublas.so", "/usr/local/cuda/lib64/libcublas.so.12"});
-      if (!api.lib) throw KsError{KS_ERR_SOLVER, std::string("cannot load libcublas: ") + dlerror()};
-      load_sym(api.lib, "cublasCreate_v2", api.Create, "libcublas");
-      load_sym(api.lib, "cublasDestroy_v2", api.Destroy, "libcublas");
-      load_sym(api.lib, "cublasSetStream_v2", api.SetStream, "libcublas");
-      load_sym(api.lib, "cublasDsymm_v2", api.Dsymm, "libcublas");
     } catch (const KsError& e) {
       fail = e.msg;
     }
@@ -154,6 +133,67 @@ void pool_release_all() {
   cudaSetDevice(cur);
 }
 
+// pinned host blocks (model mirrors, upload staging): same caching scheme, keyed by size only
+static std::multimap<size_t, void*> g_host_free;
+void* host_pool_alloc(size_t bytes) {
+  const size_t key = pool_round(bytes);
+  {
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    auto it = g_host_free.find(key);
+    if (it != g_host_free.end()) {
+      void* p = it->second;
+      g_host_free.erase(it);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, key, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    throw KsError{KS_ERR_CUDA, "cudaHostAlloc(" + std::to_string(key) + " bytes) failed: " + cudaGetErrorString(e)};
+  }
+  return p;
+}
+void host_pool_free(void* p, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  g_host_free.insert({pool_round(bytes), p});
+}
+static void host_pool_release_all() {
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  for (auto& kv : g_host_free) cudaFreeHost(kv.second);
+  g_host_free.clear();
+}
+
+void model_alloc_host(Model& m) {
+  size_t off = 0;
+  m.host_w_off.clear();
+  m.host_mean_off.clear();
+  for (size_t j = 0; j < m.brows.size(); ++j) {
+    m.host_w_off.push_back(off);
+    off += sizeof(double) * static_cast<size_t>(m.brows[j]) * m.k;
+    m.host_mean_off.push_back(off);
+    off += sizeof(double) * static_cast<size_t>(m.brows[j]);
+  }
+  m.host_b_off = off;
+  off += sizeof(double) * static_cast<size_t>(m.k);
+  m.host.alloc(off);
+  m.host_valid = true;
+}
+void model_block_to_host(Model& m, int j, cudaStream_t s) {
+  if (!m.host_valid) return;
+  uint8_t* h = static_cast<uint8_t*>(m.host.p);
+  KS_CUDA(cudaMemcpyAsync(h + m.host_w_off[j], m.W[j]->p, sizeof(double) * static_cast<size_t>(m.brows[j]) * m.k,
+                          cudaMemcpyDeviceToHost, s));
+  if (m.has_mean)
+    KS_CUDA(cudaMemcpyAsync(h + m.host_mean_off[j], m.mean[j]->p, sizeof(double) * static_cast<size_t>(m.brows[j]),
+                            cudaMemcpyDeviceToHost, s));
+}
+void model_intercept_to_host(Model& m, cudaStream_t s) {
+  if (!m.host_valid || !m.has_intercept) return;
+  KS_CUDA(cudaMemcpyAsync(static_cast<uint8_t*>(m.host.p) + m.host_b_off, m.intercept.p, sizeof(double) * static_cast<size_t>(m.k),
+                          cudaMemcpyDeviceToHost, s));
+}
+
 // ------------------------------------------------------------------------------------ Ctx
 static constexpr int kMaxInfo = 4096;
 
@@ -194,7 +234,7 @@ cudaEvent_t Ctx::get_event() {
 }
 void Ctx::span_begin(int phase, cudaStream_t s) {
   if (!timing) return;
-  Span sp{phase, get_event(), get_event(), s == st2 ? 2 : (s == st3 ? 3 : 1)};
+  Span sp{phase, get_event(), get_event(), s == st2 ? 2 : s == st3 ? 3 : s == st4 ? 4 : s == st5 ? 5 : 1};
   KS_CUDA(cudaEventRecord(sp.a, s ? s : st));
   spans.push_back(sp);
 }
@@ -233,6 +273,10 @@ void Ctx::allreduce_f64(double* p, size_t n, bool prep) {
   if (world <= 1 || n == 0) return;
   KS_NCCL(nccl_api().AllReduce(p, p, n, ncclFloat64, ncclSum, prep ? comm2 : comm, prep ? st2 : st));
 }
+void Ctx::allreduce_on(void* p, size_t n, bool f64, ncclComm_t cm, cudaStream_t s) {
+  if (world <= 1 || n == 0) return;
+  KS_NCCL(nccl_api().AllReduce(p, p, n, f64 ? ncclFloat64 : ncclFloat32, ncclSum, cm, s));
+}
 void Ctx::allreduce_max_u32(unsigned* p, size_t n) {
   if (world <= 1 || n == 0) return;
   KS_NCCL(nccl_api().AllReduce(p, p, n, ncclUint32, ncclMax, comm, st));
@@ -244,8 +288,8 @@ void Ctx::ensure_solver() {
   if (api.Create(&solver2) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnCreate failed"};
   if (api.SetStream(solver, st) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
   solver_stream = st;
-  dev_info.alloc(sizeof(int) * kMaxInfo);
-  KS_CUDA(cudaMemsetAsync(dev_info.p, 0, sizeof(int) * kMaxInfo, st));
+  dev_info.alloc(sizeof(int) * (kMaxInfo + 64));
+  KS_CUDA(cudaMemsetAsync(dev_info.p, 0, sizeof(int) * (kMaxInfo + 64), st));
 }
 void Ctx::potrf(double* H, int n, int info_slot, cudaStream_t s) {
   ensure_solver();
@@ -281,37 +325,49 @@ void Ctx::potrs(const double* H, int n, double* B, int nrhs, int info_slot, cuda
     throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrs failed"};
   launches += 1;
 }
-void Ctx::potri(double* H, int n, int info_slot, cudaStream_t s) {
+void Ctx::ensure_lanes(int n) {
   ensure_solver();
   SolverApi& api = solver_api();
-  if (s != solver2_stream) {
-    if (api.SetStream(solver2, s) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
-    solver2_stream = s;
+  int prio_least = 0, prio_greatest = 0;
+  KS_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+  while (static_cast<int>(lanes.size()) < n) {
+    auto ln = std::make_unique<SolveLane>();
+    KS_CUDA(cudaStreamCreateWithPriority(&ln->s, cudaStreamNonBlocking, prio_greatest));
+    if (api.Create(&ln->h) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnCreate failed"};
+    if (api.SetStream(ln->h, ln->s) != CUSOLVER_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cusolverDnSetStream failed"};
+    lanes.push_back(std::move(ln));
   }
-  int lwork = 0;
-  if (api.DpotriBufferSize(solver2, CUBLAS_FILL_MODE_LOWER, n, H, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
-    throw KsError{KS_ERR_SOLVER, "cusolverDnDpotri_bufferSize failed"};
-  if (lwork > solver_lwork) {
-    KS_CUDA(cudaStreamSynchronize(st));
-    KS_CUDA(cudaStreamSynchronize(st2));
-    KS_CUDA(cudaStreamSynchronize(st3));
-    solver_work.alloc(sizeof(double) * static_cast<size_t>(lwork));
-    solver_lwork = lwork;
-  }
-  if (api.Dpotri(solver2, CUBLAS_FILL_MODE_LOWER, n, H, n, solver_work.as<double>(), solver_lwork,
-                 dev_info.as<int>() + (info_slot % kMaxInfo)) != CUSOLVER_STATUS_SUCCESS)
-    throw KsError{KS_ERR_SOLVER, "cusolverDnDpotri failed"};
-  launches += 1;
 }
-void Ctx::symm_solve(const double* Hinv, int n, const double* B, int nrhs, double* out, cudaStream_t s) {
-  if (n == 0 || nrhs == 0) return;
-  BlasApi& api = blas_api();
-  if (!blas && api.Create(&blas) != CUBLAS_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cublasCreate failed"};
-  if (api.SetStream(blas, s) != CUBLAS_STATUS_SUCCESS) throw KsError{KS_ERR_SOLVER, "cublasSetStream failed"};
-  const double one = 1.0, zero = 0.0;
-  if (api.Dsymm(blas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, n, nrhs, &one, Hinv, n, B, n, &zero, out, n) !=
-      CUBLAS_STATUS_SUCCESS)
-    throw KsError{KS_ERR_SOLVER, "cublasDsymm failed"};
+void Ctx::lane_potrf_potrs(int q, double* H, int n, double* B, int nrhs, int info_slot) {
+  SolverApi& api = solver_api();
+  SolveLane& ln = *lanes[q];
+  int lwork = 0;
+  if (api.DpotrfBufferSize(ln.h, CUBLAS_FILL_MODE_LOWER, n, H, n, &lwork) != CUSOLVER_STATUS_SUCCESS)
+    throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrf_bufferSize failed"};
+  if (lwork > ln.lwork) {
+    KS_CUDA(cudaStreamSynchronize(ln.s));
+    ln.work.alloc(sizeof(double) * static_cast<size_t>(lwork));
+    ln.lwork = lwork;
+  }
+  int* info = dev_info.as<int>() + (info_slot % kMaxInfo);
+  if (api.Dpotrf(ln.h, CUBLAS_FILL_MODE_LOWER, n, H, n, ln.work.as<double>(), ln.lwork, info) != CUSOLVER_STATUS_SUCCESS)
+    throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrf failed"};
+  // potrs reports only argument errors: it shares a scratch slot past the factorisation statuses
+  if (api.Dpotrs(ln.h, CUBLAS_FILL_MODE_LOWER, n, nrhs, H, n, B, n, dev_info.as<int>() + kMaxInfo + q) != CUSOLVER_STATUS_SUCCESS)
+    throw KsError{KS_ERR_SOLVER, "cusolverDnDpotrs failed"};
+  launches += 2;
+}
+__global__ void infos_to_flag_kernel(int* info, int used, double* flag) {
+  int bad = 0;
+  for (int i = 0; i < used; ++i) {
+    if (info[i] != 0) ++bad;
+    info[i] = 0;
+  }
+  *flag = static_cast<double>(bad);
+}
+void Ctx::infos_to_flag(int used, double* flag, cudaStream_t s) {
+  ensure_solver();
+  infos_to_flag_kernel<<<1, 1, 0, s>>>(dev_info.as<int>(), used, flag);
   launches += 1;
 }
 void Ctx::check_infos(int used_slots) {
@@ -331,6 +387,7 @@ void Ctx::check_async(const char* what) {
   if (e == cudaSuccess && st2) e = cudaStreamSynchronize(st2);
   if (e == cudaSuccess && st3) e = cudaStreamSynchronize(st3);
   if (e == cudaSuccess && st4) e = cudaStreamSynchronize(st4);
+  if (e == cudaSuccess && st5) e = cudaStreamSynchronize(st5);
   if (e != cudaSuccess) {
     std::string extra;
     if (e == cudaErrorLaunchFailure || e == cudaErrorIllegalInstruction) extra = " (kernel trapped: barrier wait budget exceeded or illegal instruction)";
@@ -340,6 +397,50 @@ void Ctx::check_async(const char* what) {
 
 // ------------------------------------------------------------------------------------ feature source
 __global__ void combine_scales_kernel(const float* a, const float* b, float* out) { out[0] = a[1] * b[1]; }
+
+// operand copies of X / W for the projection GEMM of generated (cosine) features: tf32-rounded X always; fp16 copies
+// (KS_PRECISION_F16) or K-concatenated fp16 hi / lo copies (KS_PRECISION_F16X2) on request.  out.X, out.Wall, out.Wfull,
+// out.ldw, out.d_in, out.D, out.n_rows must be set.
+void prepare_generated_operands(Ctx& c, FeatSrc& out, int precision) {
+  const bool want_f16 = precision == KS_PRECISION_F16, want_x2 = precision == KS_PRECISION_F16X2;
+  const int64_t total = out.D;
+  out.zeros.alloc(sizeof(float) * static_cast<size_t>(round_up(std::max(out.D, out.d_in), 32) + 32));
+  KS_CUDA(cudaMemsetAsync(out.zeros.p, 0, out.zeros.bytes, c.st));
+  // GEMM operand copy of X rounded to tf32 (round-to-nearest instead of the MMA's truncation)
+  out.xop.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(out.n_rows, 1) * out.X->ld));
+  launch_center_round(out.X->d, out.X->ld, 0, out.zeros.as<float>(), out.xop.as<float>(), nullptr, out.X->ld, out.n_rows,
+                      static_cast<int>(out.X->cols), c.st);
+  c.launches += 1;
+  if ((want_f16 && c.proj_f16) || want_x2) {
+    // fp16 copies of X and W for the kind::f16 projection.  Each carries its own power-of-two scale (largest magnitude
+    // mapped into [2048, 4096]), so the input units do not matter; the product of the two inverse scales is applied to the
+    // fp32 accumulator in the epilogue.  Same 10-bit mantissa as the tf32 operands above.
+    out.pscale.alloc(sizeof(float) * 8);  // [0] 1/(sx*sw)  [1] maxbits x  [2] maxbits w  [4,5] x {s, 1/s}  [6,7] w {s, 1/s}
+    KS_CUDA(cudaMemsetAsync(out.pscale.p, 0, out.pscale.bytes, c.st));
+    float* ps = out.pscale.as<float>();
+    unsigned* mb = out.pscale.as<unsigned>();
+    launch_max_abs_f32(out.X->d, out.X->ld, out.n_rows, static_cast<int>(out.X->cols), mb + 1, c.st);
+    launch_max_abs_f32(out.Wfull, out.ldw, total, static_cast<int>(out.d_in), mb + 2, c.st);
+    launch_pow2_scale(mb + 1, 4096.f, ps + 4, c.st);
+    launch_pow2_scale(mb + 2, 4096.f, ps + 6, c.st);
+    combine_scales_kernel<<<1, 1, 0, c.st>>>(ps + 4, ps + 6, ps);
+    if (want_x2) {
+      out.ldx3 = out.ldw3 = round_up(3 * out.d_in, 64);
+      out.x3.alloc(2 * static_cast<size_t>(std::max<int64_t>(out.n_rows, 1) * out.ldx3));
+      out.w3.alloc(2 * static_cast<size_t>(total * out.ldw3));
+      launch_split_concat3(out.X->d, out.X->ld, out.n_rows, static_cast<int>(out.d_in), ps + 4, out.x3.p, out.ldx3, 0, c.st);
+      launch_split_concat3(out.Wfull, out.ldw, total, static_cast<int>(out.d_in), ps + 6, out.w3.p, out.ldw3, 1, c.st);
+      out.proj_x2 = true;
+    } else {
+      out.xop16.alloc(2 * static_cast<size_t>(std::max<int64_t>(out.n_rows, 1) * out.X->ld));
+      out.w16.alloc(2 * static_cast<size_t>(total * out.ldw));
+      launch_f32_to_f16_rows(out.X->d, out.X->ld, out.xop16.p, out.X->ld, out.n_rows, out.X->cols, c.st, ps + 4);
+      launch_f32_to_f16_rows(out.Wfull, out.ldw, out.w16.p, out.ldw, total, out.d_in, c.st, ps + 6);
+      out.proj16 = true;
+    }
+    c.launches += 7;
+  }
+}
 
 void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out, int precision) {
   const bool want_f16 = precision == KS_PRECISION_F16, want_x2 = precision == KS_PRECISION_F16X2;
@@ -365,59 +466,31 @@ void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, i
   out.D = total;
   CosRF& r0 = c.rf(rfs[0]);
   out.ldw = r0.ld;
+  const bool need_full = (want_f16 && c.proj_f16) || want_x2;
   if (n_rfs == 1) {
     out.Wall = r0.W;
+    out.Wfull = r0.Wfull;
     out.ball = r0.bias;
   } else {  // VectorCombiner: concatenate the gathered feature maps
     out.wcat.alloc(sizeof(float) * static_cast<size_t>(total * out.ldw));
+    if (need_full) out.wcat_full.alloc(out.wcat.bytes);
     out.bcat.alloc(sizeof(float) * static_cast<size_t>(total));
     int64_t off = 0;
     for (int i = 0; i < n_rfs; ++i) {
       CosRF& r = c.rf(rfs[i]);
       KS_CUDA(cudaMemcpyAsync(out.wcat.as<float>() + off * out.ldw, r.W, sizeof(float) * r.n_out * r.ld,
                               cudaMemcpyDeviceToDevice, c.st));
+      if (need_full)
+        KS_CUDA(cudaMemcpyAsync(out.wcat_full.as<float>() + off * out.ldw, r.Wfull, sizeof(float) * r.n_out * r.ld,
+                                cudaMemcpyDeviceToDevice, c.st));
       KS_CUDA(cudaMemcpyAsync(out.bcat.as<float>() + off, r.bias, sizeof(float) * r.n_out, cudaMemcpyDeviceToDevice, c.st));
       off += r.n_out;
     }
     out.Wall = out.wcat.as<float>();
+    out.Wfull = need_full ? out.wcat_full.as<float>() : nullptr;
     out.ball = out.bcat.as<float>();
   }
-  out.zeros.alloc(sizeof(float) * static_cast<size_t>(round_up(std::max(out.D, out.d_in), 32) + 32));
-  KS_CUDA(cudaMemsetAsync(out.zeros.p, 0, out.zeros.bytes, c.st));
-  // GEMM operand copy of X rounded to tf32 (round-to-nearest instead of the MMA's truncation)
-  out.xop.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(out.n_rows, 1) * out.X->ld));
-  launch_center_round(out.X->d, out.X->ld, 0, out.zeros.as<float>(), out.xop.as<float>(), nullptr, out.X->ld, out.n_rows,
-                      static_cast<int>(out.X->cols), c.st);
-  c.launches += 1;
-  if ((want_f16 && c.proj_f16) || want_x2) {
-    // fp16 copies of X and W for the kind::f16 projection.  Each carries its own power-of-two scale (largest magnitude
-    // mapped into [2048, 4096]), so the input units do not matter; the product of the two inverse scales is applied to the
-    // fp32 accumulator in the epilogue.  Same 10-bit mantissa as the tf32 operands above.
-    out.pscale.alloc(sizeof(float) * 8);  // [0] 1/(sx*sw)  [1] maxbits x  [2] maxbits w  [4,5] x {s, 1/s}  [6,7] w {s, 1/s}
-    KS_CUDA(cudaMemsetAsync(out.pscale.p, 0, out.pscale.bytes, c.st));
-    float* ps = out.pscale.as<float>();
-    unsigned* mb = out.pscale.as<unsigned>();
-    launch_max_abs_f32(out.X->d, out.X->ld, out.n_rows, static_cast<int>(out.X->cols), mb + 1, c.st);
-    launch_max_abs_f32(out.Wall, out.ldw, total, static_cast<int>(out.d_in), mb + 2, c.st);
-    launch_pow2_scale(mb + 1, 4096.f, ps + 4, c.st);
-    launch_pow2_scale(mb + 2, 4096.f, ps + 6, c.st);
-    combine_scales_kernel<<<1, 1, 0, c.st>>>(ps + 4, ps + 6, ps);
-    if (want_x2) {
-      out.ldx3 = out.ldw3 = round_up(3 * out.d_in, 64);
-      out.x3.alloc(2 * static_cast<size_t>(std::max<int64_t>(out.n_rows, 1) * out.ldx3));
-      out.w3.alloc(2 * static_cast<size_t>(total * out.ldw3));
-      launch_split_concat3(out.X->d, out.X->ld, out.n_rows, static_cast<int>(out.d_in), ps + 4, out.x3.p, out.ldx3, 0, c.st);
-      launch_split_concat3(out.Wall, out.ldw, total, static_cast<int>(out.d_in), ps + 6, out.w3.p, out.ldw3, 1, c.st);
-      out.proj_x2 = true;
-    } else {
-      out.xop16.alloc(2 * static_cast<size_t>(std::max<int64_t>(out.n_rows, 1) * out.X->ld));
-      out.w16.alloc(2 * static_cast<size_t>(total * out.ldw));
-      launch_f32_to_f16_rows(out.X->d, out.X->ld, out.xop16.p, out.X->ld, out.n_rows, out.X->cols, c.st, ps + 4);
-      launch_f32_to_f16_rows(out.Wall, out.ldw, out.w16.p, out.ldw, total, out.d_in, c.st, ps + 6);
-      out.proj16 = true;
-    }
-    c.launches += 7;
-  }
+  prepare_generated_operands(c, out, precision);
 }
 
 static void tmap16_or_throw(CUtensorMap* m, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
@@ -612,14 +685,22 @@ __global__ void sumsq_f64_kernel(const double* p, int64_t n, double* out) {
 }
 
 // ------------------------------------------------------------------------------------ BlockLS fit
-// Three-stream software pipeline.  Per block j the work splits into two parts that do NOT depend on the residual
-//   prep(j)   [stream st2]: shift estimate, slab S_j, G_j = S_j^T S_j, all-reduce
-//   factor(j) [stream st3]: H_j = G_j - N d d^T + lambda I, Cholesky (about 100 small, latency-bound cuSOLVER kernels)
+// Per block j the work splits into a part that does NOT depend on the residual
+//   proj(j)   slab S_j = round(features_j - m_j)                       tensor (projection GEMM) or HBM (materialised F)
+//   G(j)      G_j = S_j^T S_j, all-reduce                              tensor
+//   factor(j) H_j = G_j - N d d^T + lambda I, Cholesky                 fp64, ~100 small latency-bound kernels
 // and the residual-dependent chain
-//   main(j)   [stream st ]: Rr = tf32(R), C_j = S_j^T Rr, all-reduce, triangular solves, W_j += dW, R -= S_j dW.
-// prep / factor run up to two blocks ahead of main (three slab / G / H buffers); cross-stream dependencies are CUDA events
-// and there is no host synchronisation inside the loop.  With the rows sharded over several GPUs the per-block tensor
-// work shrinks but the Cholesky does not: keeping it off both other chains is what keeps the strong scaling going.
+//   C(j)      Rr = round(R), C_j = S_j^T Rr, all-reduce                tensor
+//   solve(j)  rhs, triangular solves, W_j += dW, pack dW               fp64, ~230 small kernels
+//   update(j) R -= S_j dW                                              tensor
+//
+// pipeline 1 (default): ONE stream carries every tensor-core kernel in the order C(j), G(j+1), proj(j+2), update(j); the
+// solve and factor chains run on their own higher-priority streams and hide under G(j+1) + proj(j+2).  Two tensor
+// kernels never share the SMs: each is written to own an SM (one CTA, ~200 KB of shared memory, all of TMEM), so running
+// two at once only splits the machine, thrashes L2 and stretches both (round 1 measured 40.4 ms per block for 29.3 ms of
+// isolated tensor work with the two-stream arrangement, i.e. worse than running everything back to back).
+// pipeline 0: the round-1 arrangement (residual chain on st, look-ahead tensor kernels on st2), kept for A/B runs.
+// Slabs, G and H are triple-buffered; cross-stream dependencies are CUDA events; no host synchronisation inside the loop.
 static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, int64_t nf_opt,
                            int precision = KS_PRECISION_TF32) {
   if (bs <= 0 || num_iter < 1) throw KsError{KS_ERR_INVALID, "blockSize must be > 0 and numIter >= 1"};
@@ -633,14 +714,28 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   const int bmax = static_cast<int>(std::min<int64_t>(bs, D));
   const int64_t lds = round_up(bmax, 32);
   const int64_t kpad = round_up(k, 32);
-  cudaStream_t S1 = c.st, S2 = c.st2, S3 = c.st3, S4 = c.st4;
+  const bool serial = c.pipeline != 0;
+  // stream roles (see the Ctx comment)
+  cudaStream_t S1 = c.st, S2 = c.st2, S3 = c.st3, S4 = c.st4, S5 = c.st5;
+  cudaStream_t ST = S2;                       // projection + G-Gram (both pipelines)
+  cudaStream_t SR = serial ? S2 : S1;         // C-Gram and update: the residual chain's tensor kernels
+  cudaStream_t SS = S1;                       // solve chain
+  cudaStream_t SF = S3;                       // factor chain
+  cudaStream_t SG = serial ? S4 : S2;         // all-reduce of G
+  ncclComm_t commG = serial ? c.comm3 : c.comm2;
   const auto host_t0 = std::chrono::steady_clock::now();
   c.spans.clear();
   const int64_t launches0 = c.launches;
-  cudaEvent_t ev0 = c.get_event(), ev1 = c.get_event(), ev_init = c.get_event();
+  auto new_event = [&]() {
+    cudaEvent_t e = c.get_event();
+    c.fit_events.push_back(e);
+    return e;
+  };
+  cudaEvent_t ev0 = new_event(), ev1 = new_event(), ev_init = new_event();
   KS_CUDA(cudaStreamSynchronize(S2));
   KS_CUDA(cudaStreamSynchronize(S3));
   KS_CUDA(cudaStreamSynchronize(S4));
+  KS_CUDA(cudaStreamSynchronize(S5));
   KS_CUDA(cudaEventRecord(ev0, S1));
 
   // ---- label mean (StandardScaler on labels, BlockLinearMapper.scala:215) + global row count
@@ -669,31 +764,43 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   scale_f64_to_f32_kernel<<<(k + 255) / 256, 256, 0, S1>>>(ysum.as<double>(), 1.0 / n_total_d, nullptr,
                                                           model->intercept.as<double>(), k);
   c.launches += 1;
+  auto block_cols = [&](int j, int64_t* c0) {
+    *c0 = static_cast<int64_t>(j) * bs;
+    return static_cast<int>(std::min<int64_t>(D, *c0 + bs) - *c0);
+  };
+  for (int j = 0; j < nb; ++j) {
+    int64_t c0;
+    const int b = block_cols(j, &c0);
+    model->brows.push_back(b);
+    auto W = std::make_unique<DevBuf>();
+    W->alloc(sizeof(double) * static_cast<size_t>(b) * k);
+    auto mean = std::make_unique<DevBuf>();
+    mean->alloc(sizeof(double) * b);
+    model->W.push_back(std::move(W));
+    model->mean.push_back(std::move(mean));
+  }
+  if (c.host_mirror) model_alloc_host(*model);
 
-  // ---- residual R = Y - mean (fp32 master) and Rr = its tf32-rounded copy (the Gram kernel's B operand)
-  // look-ahead depth of prep / factor over main: 2 blocks normally; with the owner-computes-inverse scheme the factor chain
-  // of a block is ~30 ms on its owner, so `world` of them must be in flight at once (N_loc shrinks with world, so do the slabs)
-  const bool use_inv = c.world >= c.inv_min_world;
-  const bool shard_solve = !use_inv && !c.custom_solve && c.world > 1 && c.shard_solve && k >= c.world;
-  const int NBUF = use_inv ? c.world + 2 : 3;
-  // fp16 operand mode (KS_PRECISION_F16): the slab, the residual operand and the increment operand are fp16 and the three
-  // big GEMMs run as kind::f16 -- same 10-bit mantissa as tf32 at twice the MMA rate and half the slab bytes.  Only for
-  // generated cosine features (|value| <= 2: no range problem); the residual and the increments are scaled by device-chosen
-  // powers of two.  Materialised feature matrices have arbitrary scale and keep the tf32 path.
-  // Split-operand mode (KS_PRECISION_F16X2, experimental): every fp16 operand v is carried as hi + lo (hi = fp16(v),
-  // lo = fp16(v - hi): 21 significant bits) and every product keeps hi*hi + hi*lo + lo*hi, using the same kernels three
-  // times (the projection once, on operands concatenated along K).  Modelled rel-Frobenius(W) ~ 2e-7 instead of 7e-4
-  // (tests/test_precision_model.py) at ~3x the fp16 tensor work.
-  const bool x2 = precision == KS_PRECISION_F16X2 && !src.F && src.proj_x2;
-  const bool f16 = (precision == KS_PRECISION_F16 || x2) && !src.F;
+  // ---- operand modes
+  // KS_PRECISION_F16: the slab, the residual operand and the increment operand are fp16 and the three big GEMMs run as
+  //   kind::f16 -- same 10-bit mantissa as tf32 at twice the MMA rate and half the slab bytes.  Only for generated cosine
+  //   features (|value| <= 2: no range problem); the residual and the increments are scaled by device-chosen powers of two.
+  //   Materialised feature matrices have arbitrary scale and keep the tf32 path.
+  // KS_PRECISION_F16X2 (the parity mode): every MMA operand v is carried as hi + lo (hi = round(v), lo = round(v - hi): 21+
+  //   significant bits) and every product keeps hi*hi + hi*lo + lo*hi, using the same kernels three times (the projection
+  //   once, on operands concatenated along K).  Generated features: fp16 pairs (kind::f16); materialised features: tf32
+  //   pairs (kind::tf32, no range limits).
+  const bool x2 = precision == KS_PRECISION_F16X2 && (src.F || src.proj_x2);
+  const bool f16 = !src.F && (precision == KS_PRECISION_F16 || x2);
   const size_t es = f16 ? 2 : 4;  // bytes per slab / operand element
   const int64_t x2_chunk = 2048;  // short accumulation chains: the tensor core's fp32 accumulate truncates (~2^-25 per MMA step)
-  DevBuf r_f32, r_tf32, cm, rhs, dwb, rsum, bop, cbias, samp, fsum, scales, sf32, r_lo, bop_lo;
+  const int NBUF = 3;
+  DevBuf r_f32, r_op, cm, rhs, rsum, bop, cbias, samp, fsum, scales, sf32, r_lo, bop_lo;
   std::unique_ptr<DevBuf[]> slab_lo;
   std::unique_ptr<DevBuf[]> slab(new DevBuf[NBUF]), gbuf(new DevBuf[NBUF]), Hbuf(new DevBuf[NBUF]), ssum(new DevBuf[NBUF]);
   r_f32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * kpad));
-  r_tf32.alloc(f16 ? r_f32.bytes / 2 : r_f32.bytes);
-  if (x2) r_lo.alloc(r_tf32.bytes);
+  r_op.alloc(f16 ? r_f32.bytes / 2 : r_f32.bytes);
+  if (x2) r_lo.alloc(r_op.bytes);
   launch_init_residual(Y.d, Y.ld, model->intercept.as<double>(), r_f32.as<float>(), kpad, n_loc, k, S1);
   c.launches += 1;
   // scales: [0] max|R0| bits, [1] max|dW| bits (per block), then float pairs {2^e, 2^-e}: [2,3] residual, [4,5] increment
@@ -721,13 +828,12 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   }
   cm.alloc(sizeof(float) * c_elems);
   rhs.alloc(sizeof(double) * static_cast<size_t>(bmax) * k);
-  dwb.alloc(rhs.bytes);
   rsum.alloc(sizeof(double) * kpad);
   bop.alloc(es * static_cast<size_t>(kpad) * lds);
   if (x2) {
     slab_lo.reset(new DevBuf[NBUF]);
     for (int i = 0; i < NBUF; ++i) slab_lo[i].alloc(slab[i].bytes);
-    sf32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));  // unrounded block before the split
+    if (!src.F) sf32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));  // unrounded block before the split
     bop_lo.alloc(bop.bytes);
   }
   cbias.alloc(sizeof(float) * kpad);
@@ -746,287 +852,280 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   }
   KS_CUDA(cudaEventRecord(ev_init, S1));
   KS_CUDA(cudaStreamWaitEvent(S2, ev_init, 0));
+  KS_CUDA(cudaStreamWaitEvent(S3, ev_init, 0));
 
   struct Step { int it, j; };
   std::vector<Step> steps;
   for (int it = 0; it < num_iter; ++it)
     for (int j = 0; j < nb; ++j) steps.push_back({it, j});
   const int T = static_cast<int>(steps.size());
-  std::vector<cudaEvent_t> ev_slab(T), ev_fact(T), ev_upd(T), ev_g(T), ev_inv(T), ev_solved(T);
-  const bool exclusive_solve = c.world >= c.exclusive_solve_min_world;
+  std::vector<cudaEvent_t> ev_slab(T), ev_fact(T), ev_upd(T), ev_gdone(T), ev_g(T), ev_c(T), ev_solved(T);
   for (int t = 0; t < T; ++t) {
-    ev_solved[t] = c.get_event();
-    ev_g[t] = c.get_event();
-    ev_inv[t] = c.get_event();
-    ev_slab[t] = c.get_event();
-    ev_fact[t] = c.get_event();
-    ev_upd[t] = c.get_event();
+    ev_slab[t] = new_event();
+    ev_fact[t] = new_event();
+    ev_upd[t] = new_event();
+    ev_gdone[t] = new_event();
+    ev_g[t] = new_event();
+    ev_c[t] = new_event();
+    ev_solved[t] = new_event();
   }
   int info_slot = 0;
   double flops = 0;
+  const bool shard_solve = !c.custom_solve && c.world > 1 && c.shard_solve && k >= c.world;
 
-  auto block_cols = [&](int j, int64_t* c0) {
-    *c0 = static_cast<int64_t>(j) * bs;
-    return static_cast<int>(std::min<int64_t>(D, *c0 + bs) - *c0);
-  };
-
-  // ---------------- prep(t): everything that does not depend on the residual, on stream S2
-  auto prep = [&](int t) {
+  // ---------------- proj(t): shift estimate (first sweep) + slab of step t, on ST
+  auto do_proj = [&](int t) {
     const int it = steps[t].it, j = steps[t].j, buf = t % NBUF;
     int64_t c0;
     const int b = block_cols(j, &c0);
-    if (t >= NBUF) KS_CUDA(cudaStreamWaitEvent(S2, ev_upd[t - NBUF], 0));  // slab / G / H buffers of step t-NBUF are free
-    c.span_begin(PH_FEATURIZE, S2);
+    c.span_begin(PH_FEATURIZE, ST);
     if (it == 0) {
       shifts[j] = std::make_unique<DevBuf>();
       shifts[j]->alloc(sizeof(float) * lds);
-      KS_CUDA(cudaMemsetAsync(shifts[j]->p, 0, shifts[j]->bytes, S2));
+      KS_CUDA(cudaMemsetAsync(shifts[j]->p, 0, shifts[j]->bytes, ST));
       if (src.F) {
-        scale_f64_to_f32_kernel<<<(b + 255) / 256, 256, 0, S2>>>(fsum.as<double>() + c0, 1.0 / n_total_d,
+        scale_f64_to_f32_kernel<<<(b + 255) / 256, 256, 0, ST>>>(fsum.as<double>() + c0, 1.0 / n_total_d,
                                                                  shifts[j]->as<float>(), nullptr, b);
         c.launches += 1;
       } else {
         // mean estimate from the first sample_rows rows of every rank; exactness is restored by the rank-1 correction
         // with delta below, the estimate only has to be close enough to avoid cancellation
         const int64_t ns = std::min<int64_t>(n_loc, c.sample_rows);
-        KS_CUDA(cudaMemsetAsync(samp.p, 0, samp.bytes, S2));
-        KS_CUDA(cudaMemsetAsync(ssum[buf].p, 0, ssum[buf].bytes, S2));
-        if (x2) produce_slab(c, src, c0, b, src.zeros.as<float>(), sf32.p, lds, 0, ns, /*round_out=*/false, ssum[buf].as<float>(), S2,
+        KS_CUDA(cudaMemsetAsync(samp.p, 0, samp.bytes, ST));
+        KS_CUDA(cudaMemsetAsync(ssum[buf].p, 0, ssum[buf].bytes, ST));
+        if (x2) produce_slab(c, src, c0, b, src.zeros.as<float>(), sf32.p, lds, 0, ns, /*round_out=*/false, ssum[buf].as<float>(), ST,
                              false, true);
         else produce_slab(c, src, c0, b, src.zeros.as<float>(), slab[buf].p, lds, 0, ns, /*round_out=*/false,
-                          ssum[buf].as<float>(), S2, f16);
-        launch_f32_to_f64_rows(ssum[buf].as<float>(), lds, samp.as<double>(), bmax, 1, b, S2);  // 1 x b "matrix"
+                          ssum[buf].as<float>(), ST, f16);
+        launch_f32_to_f64_rows(ssum[buf].as<float>(), lds, samp.as<double>(), bmax, 1, b, ST);  // 1 x b "matrix"
         c.launches += 1;
-        set_f64_kernel<<<1, 1, 0, S2>>>(samp.as<double>() + bmax, static_cast<double>(ns));
+        set_f64_kernel<<<1, 1, 0, ST>>>(samp.as<double>() + bmax, static_cast<double>(ns));
         c.launches += 1;
-        c.allreduce_f64(samp.as<double>(), bmax + 1, /*prep=*/true);
-        launch_divide_by_count(samp.as<double>(), samp.as<double>() + bmax, shifts[j]->as<float>(), nullptr, b, S2);
+        c.allreduce_on(samp.p, static_cast<size_t>(bmax + 1), true, c.comm2, ST);
+        launch_divide_by_count(samp.as<double>(), samp.as<double>() + bmax, shifts[j]->as<float>(), nullptr, b, ST);
         c.launches += 1;
         flops += 2.0 * static_cast<double>(ns) * src.d_in * b;
       }
     }
-    KS_CUDA(cudaMemsetAsync(ssum[buf].p, 0, ssum[buf].bytes, S2));
-    if (x2) {
-      produce_slab(c, src, c0, b, shifts[j]->as<float>(), sf32.p, lds, 0, n_loc, /*round_out=*/false, nullptr, S2, false, true);
-      launch_split_rows16(sf32.as<float>(), lds, slab[buf].p, slab_lo[buf].p, lds, n_loc, b, it == 0 ? ssum[buf].as<float>() : nullptr,
-                          S2);
+    KS_CUDA(cudaMemsetAsync(ssum[buf].p, 0, ssum[buf].bytes, ST));
+    float* cs = it == 0 ? ssum[buf].as<float>() : nullptr;
+    if (x2 && src.F) {  // materialised features: tf32 hi / lo planes straight from F
+      launch_center_round(src.F->d, src.F->ld, static_cast<int>(c0), shifts[j]->as<float>(), slab[buf].as<float>(), cs, lds, n_loc, b,
+                          ST, slab_lo[buf].as<float>());
       c.launches += 1;
-      if (!src.F) flops += 4.0 * static_cast<double>(n_loc) * src.d_in * b;  // two extra product terms of the projection
+    } else if (x2) {
+      produce_slab(c, src, c0, b, shifts[j]->as<float>(), sf32.p, lds, 0, n_loc, /*round_out=*/false, nullptr, ST, false, true);
+      launch_split_rows16(sf32.as<float>(), lds, slab[buf].p, slab_lo[buf].p, lds, n_loc, b, cs, ST);
+      c.launches += 1;
+      flops += 4.0 * static_cast<double>(n_loc) * src.d_in * b;  // two extra product terms of the projection
     } else {
-      produce_slab(c, src, c0, b, shifts[j]->as<float>(), slab[buf].p, lds, 0, n_loc, true,
-                   it == 0 ? ssum[buf].as<float>() : nullptr, S2, f16);
+      produce_slab(c, src, c0, b, shifts[j]->as<float>(), slab[buf].p, lds, 0, n_loc, true, cs, ST, f16);
     }
     if (!src.F) flops += 2.0 * static_cast<double>(n_loc) * src.d_in * b;
-    c.span_end(S2);
-    KS_CUDA(cudaEventRecord(ev_slab[t], S2));
+    c.span_end(ST);
+    KS_CUDA(cudaEventRecord(ev_slab[t], ST));
   };
-  // ---------------- prepB(t): Gram + factorization of block t (enqueued after main(t-1), see the loop below)
-  auto prepB = [&](int t) {
+  // ---------------- gram(t): G of step t on ST, its all-reduce on SG, the factorisation on SF
+  auto do_gram = [&](int t) {
     const int it = steps[t].it, j = steps[t].j, buf = t % NBUF;
     int64_t c0;
     const int b = block_cols(j, &c0);
-    if (it == 0) {
-      // strong-scaling regime: start this block's Gram only once the critical chain has finished the previous block's
-      // triangular solves -- ~100 small latency-bound kernels that take 2x longer when they share the SMs with it
-      if (exclusive_solve && t >= 1) KS_CUDA(cudaStreamWaitEvent(S2, ev_solved[t - 1], 0));
-      c.span_begin(PH_GRAM, S2);  // G part of the Gram
-      KS_CUDA(cudaMemsetAsync(gbuf[buf].p, 0, gbuf[buf].bytes, S2));
-      if (x2) {  // one launch: upper tiles of S_hi^T S_hi and all tiles of S_hi^T S_lo (the "C" slot with kcols = b)
-        launch_gram_block(c, slab[buf].p, lds, n_loc, b, slab_lo[buf].p, lds, b, gbuf[buf].as<float>(), ldg,
-                          gbuf[buf].as<float>() + g_elems, ldg, true, true, S2, true, x2_chunk);
-        flops += 4.0 * n_loc * static_cast<double>(b) * b;
-      } else {
-        launch_gram_block(c, slab[buf].p, lds, n_loc, b, nullptr, 0, 0, gbuf[buf].as<float>(), ldg, nullptr, 0, true,
-                          false, S2, f16);
-      }
-      flops += 2.0 * n_loc * static_cast<double>(b) * b;
-      c.span_end(S2);
-      c.span_begin(PH_ALLREDUCE, S2);
-      c.allreduce_f32(gbuf[buf].as<float>(), g_elems * (x2 ? 2 : 1), true);
-      c.allreduce_f32(ssum[buf].as<float>(), static_cast<size_t>(b), true);
-      c.span_end(S2);
-      KS_CUDA(cudaEventRecord(ev_g[t], S2));
-      // ---- factor(t)
-      deltas[j] = std::make_unique<DevBuf>();
-      deltas[j]->alloc(sizeof(double) * b);
-      auto mean = std::make_unique<DevBuf>();
-      mean->alloc(sizeof(double) * b);
-      double* Hj;
-      if (cache_factors) {
-        factors[j] = std::make_unique<DevBuf>();
-        factors[j]->alloc(sizeof(double) * static_cast<size_t>(b) * b);
-        Hj = factors[j]->as<double>();
-      } else {
-        Hj = Hbuf[buf].as<double>();
-      }
-      auto W = std::make_unique<DevBuf>();
-      W->alloc(sizeof(double) * static_cast<size_t>(b) * k);
-      if (use_inv) {
-        // The latency-bound Cholesky + explicit inverse of block j run on ONE rank (j % world) on its factor stream S3; the
-        // inverse is broadcast on a separate stream S4 (a rank waiting for somebody else's inverse must not stall its own
-        // factor work).  The factor chains of `world` consecutive blocks thus proceed in parallel on different GPUs and the
-        // critical chain's solve becomes a single fp64 GEMM on every rank.
-        const int owner = j % c.world;
-        KS_CUDA(cudaStreamWaitEvent(S4, ev_g[t], 0));
-        launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), mean->as<double>(), b, S4);
-        KS_CUDA(cudaMemsetAsync(W->p, 0, W->bytes, S4));
-        if (c.rank == owner) {
-          KS_CUDA(cudaStreamWaitEvent(S3, ev_g[t], 0));
-          c.span_begin(PH_SOLVE, S3);
-          launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), nullptr, b, S3);
-          launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S3,
-                              x2 ? gbuf[buf].as<float>() + g_elems : nullptr);
-          c.launches += 2;
-          c.potrf(Hj, b, info_slot++, S3);
-          c.potri(Hj, b, info_slot++, S3);
-          c.span_end(S3);
-          KS_CUDA(cudaEventRecord(ev_inv[t], S3));
-          KS_CUDA(cudaStreamWaitEvent(S4, ev_inv[t], 0));
-        }
-        c.span_begin(PH_ALLREDUCE, S4);
-        KS_NCCL(nccl_api().Broadcast(Hj, Hj, static_cast<size_t>(b) * b, ncclFloat64, owner, c.comm3, S4));
-        c.span_end(S4);
-        c.launches += 2;
-        KS_CUDA(cudaEventRecord(ev_fact[t], S4));
-      } else {
-        KS_CUDA(cudaStreamWaitEvent(S3, ev_g[t], 0));
-        c.span_begin(PH_SOLVE, S3);
-        launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), mean->as<double>(), b, S3);
-        launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, S3,
-                              x2 ? gbuf[buf].as<float>() + g_elems : nullptr);
-        c.launches += 2;
-        c.potrf(Hj, b, info_slot++, S3);
-        KS_CUDA(cudaMemsetAsync(W->p, 0, W->bytes, S3));
-        c.span_end(S3);
-        KS_CUDA(cudaEventRecord(ev_fact[t], S3));
-      }
-      model->brows.push_back(b);
-      model->W.push_back(std::move(W));
-      model->mean.push_back(std::move(mean));
-      flops += static_cast<double>(b) * b * b / 3.0;
-    } else {
-      KS_CUDA(cudaEventRecord(ev_fact[t], S2));
+    if (it != 0) {  // later sweeps reuse the cached factor
+      KS_CUDA(cudaEventRecord(ev_fact[t], ST));
+      return;
     }
+    c.span_begin(PH_GRAM, ST);
+    KS_CUDA(cudaMemsetAsync(gbuf[buf].p, 0, gbuf[buf].bytes, ST));
+    if (x2) {  // one launch: upper tiles of S_hi^T S_hi and all tiles of S_hi^T S_lo (the "C" slot with kcols = b)
+      launch_gram_block(c, slab[buf].p, lds, n_loc, b, slab_lo[buf].p, lds, b, gbuf[buf].as<float>(), ldg,
+                        gbuf[buf].as<float>() + g_elems, ldg, true, true, ST, f16, x2_chunk);
+      flops += 4.0 * n_loc * static_cast<double>(b) * b;
+    } else {
+      launch_gram_block(c, slab[buf].p, lds, n_loc, b, nullptr, 0, 0, gbuf[buf].as<float>(), ldg, nullptr, 0, true, false, ST, f16);
+    }
+    flops += 2.0 * n_loc * static_cast<double>(b) * b;
+    c.span_end(ST);
+    KS_CUDA(cudaEventRecord(ev_gdone[t], ST));
+    if (c.world > 1) {
+      if (SG != ST) KS_CUDA(cudaStreamWaitEvent(SG, ev_gdone[t], 0));
+      c.span_begin(PH_ALLREDUCE, SG);
+      c.allreduce_on(gbuf[buf].p, g_elems * (x2 ? 2 : 1), false, commG, SG);
+      c.allreduce_on(ssum[buf].p, static_cast<size_t>(b), false, commG, SG);
+      c.span_end(SG);
+      KS_CUDA(cudaEventRecord(ev_g[t], SG));
+    } else {
+      KS_CUDA(cudaEventRecord(ev_g[t], ST));
+    }
+    // ---- factor(t)
+    deltas[j] = std::make_unique<DevBuf>();
+    deltas[j]->alloc(sizeof(double) * b);
+    double* Hj;
+    if (cache_factors) {
+      factors[j] = std::make_unique<DevBuf>();
+      factors[j]->alloc(sizeof(double) * static_cast<size_t>(b) * b);
+      Hj = factors[j]->as<double>();
+    } else {
+      Hj = Hbuf[buf].as<double>();
+    }
+    KS_CUDA(cudaStreamWaitEvent(SF, ev_g[t], 0));
+    c.span_begin(PH_SOLVE, SF);
+    launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), model->mean[j]->as<double>(), b, SF);
+    launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, SF,
+                        x2 ? gbuf[buf].as<float>() + g_elems : nullptr);
+    c.launches += 2;
+    c.potrf(Hj, b, info_slot++, SF);
+    KS_CUDA(cudaMemsetAsync(model->W[j]->p, 0, model->W[j]->bytes, SF));
+    c.span_end(SF);
+    KS_CUDA(cudaEventRecord(ev_fact[t], SF));
+    flops += static_cast<double>(b) * b * b / 3.0;
   };
-
-  // ---------------- main(t): the residual-dependent chain, on stream S1
-  auto mainstep = [&](int t) {
-    const int it = steps[t].it, j = steps[t].j, buf = t % NBUF;
+  // ---------------- cgram(t): operand copy of R + C = S^T R on SR
+  auto do_cgram = [&](int t) {
+    const int j = steps[t].j, buf = t % NBUF;
     int64_t c0;
     const int b = block_cols(j, &c0);
-    c.span_begin(PH_OTHER);
-    KS_CUDA(cudaMemsetAsync(cm.p, 0, sizeof(float) * c_elems, S1));
-    KS_CUDA(cudaMemsetAsync(rsum.p, 0, rsum.bytes, S1));
-    if (f16) launch_round_colsum16(r_f32.as<float>(), r_tf32.p, kpad, n_loc, k, rsum.as<double>(), rscale, S1, x2 ? r_lo.p : nullptr);
-    else launch_round_colsum(r_f32.as<float>(), r_tf32.as<float>(), kpad, n_loc, k, rsum.as<double>(), S1);
+    c.span_begin(PH_OTHER, SR);
+    KS_CUDA(cudaMemsetAsync(cm.p, 0, sizeof(float) * c_elems, SR));
+    KS_CUDA(cudaMemsetAsync(rsum.p, 0, rsum.bytes, SR));
+    if (f16) launch_round_colsum16(r_f32.as<float>(), r_op.p, kpad, n_loc, k, rsum.as<double>(), rscale, SR, x2 ? r_lo.p : nullptr);
+    else launch_round_colsum(r_f32.as<float>(), r_op.as<float>(), kpad, n_loc, k, rsum.as<double>(), SR, x2 ? r_lo.as<float>() : nullptr);
     c.launches += 1;
-    c.span_end();
-    KS_CUDA(cudaStreamWaitEvent(S1, ev_slab[t], 0));
-    c.span_begin(PH_UPDATE);  // A^T R part of the Gram (accounted with the residual chain)
-    launch_gram_block(c, slab[buf].p, lds, n_loc, b, r_tf32.p, kpad, k, nullptr, 0, cm.as<float>(), ldc,
-                      false, true, S1, f16, x2 ? x2_chunk : 0);
+    c.span_end(SR);
+    if (SR != ST) KS_CUDA(cudaStreamWaitEvent(SR, ev_slab[t], 0));
+    c.span_begin(PH_UPDATE, SR);  // A^T R part of the Gram (accounted with the residual chain)
+    launch_gram_block(c, slab[buf].p, lds, n_loc, b, r_op.p, kpad, k, nullptr, 0, cm.as<float>(), ldc, false, true, SR, f16,
+                      x2 ? x2_chunk : 0);
     if (x2) {  // + S_lo^T R_hi + S_hi^T R_lo, reduce-added into the same C
-      launch_gram_block(c, slab_lo[buf].p, lds, n_loc, b, r_tf32.p, kpad, k, nullptr, 0, cm.as<float>(), ldc, false, true, S1, true,
+      launch_gram_block(c, slab_lo[buf].p, lds, n_loc, b, r_op.p, kpad, k, nullptr, 0, cm.as<float>(), ldc, false, true, SR, f16,
                         x2_chunk);
-      launch_gram_block(c, slab[buf].p, lds, n_loc, b, r_lo.p, kpad, k, nullptr, 0, cm.as<float>(), ldc, false, true, S1, true,
+      launch_gram_block(c, slab[buf].p, lds, n_loc, b, r_lo.p, kpad, k, nullptr, 0, cm.as<float>(), ldc, false, true, SR, f16,
                         x2_chunk);
       flops += 4.0 * n_loc * static_cast<double>(b) * k;
     }
     flops += 2.0 * n_loc * static_cast<double>(b) * k;
-    c.span_end();
-    c.span_begin(PH_ALLREDUCE);
+    c.span_end(SR);
+    KS_CUDA(cudaEventRecord(ev_c[t], SR));
+  };
+  // ---------------- solve(t): all-reduce of C, rhs, triangular solves, W += dW, operand of the update, on SS
+  auto do_solve = [&](int t) {
+    const int it = steps[t].it, j = steps[t].j, buf = t % NBUF;
+    int64_t c0;
+    const int b = block_cols(j, &c0);
+    if (SS != SR) KS_CUDA(cudaStreamWaitEvent(SS, ev_c[t], 0));
+    c.span_begin(PH_ALLREDUCE, SS);
     c.allreduce_f32(cm.as<float>(), c_elems);
     c.allreduce_f64(rsum.as<double>(), k);
-    c.span_end();
-    KS_CUDA(cudaStreamWaitEvent(S1, ev_fact[t], 0));
-    c.span_begin(PH_SOLVE);
+    c.span_end(SS);
+    KS_CUDA(cudaStreamWaitEvent(SS, ev_fact[t], 0));
+    c.span_begin(PH_SOLVE, SS);
     double* Hj = cache_factors ? factors[j]->as<double>() : Hbuf[buf].as<double>();
     launch_build_rhs(cm.as<float>(), ldc, deltas[j]->as<double>(), rsum.as<double>(), n_total_d, lam,
-                     it > 0 ? model->W[j]->as<double>() : nullptr, rhs.as<double>(), b, k, S1, f16 ? rscale + 1 : nullptr);
+                     it > 0 ? model->W[j]->as<double>() : nullptr, rhs.as<double>(), b, k, SS, f16 ? rscale + 1 : nullptr);
     c.launches += 1;
-    const double* dw_ptr;
-    if (use_inv) {
-      c.symm_solve(Hj, b, rhs.as<double>(), k, dwb.as<double>(), S1);
-      dw_ptr = dwb.as<double>();
-    } else if (c.custom_solve) {
-      KS_CUDA(launch_chol_solve(Hj, b, rhs.as<double>(), k, S1));
+    if (c.custom_solve) {
+      KS_CUDA(launch_chol_solve(Hj, b, rhs.as<double>(), k, SS));
       c.launches += 1;
-      dw_ptr = rhs.as<double>();
     } else if (shard_solve) {
       // Column-sharded solve: the right-hand sides are independent, so rank r solves columns [k r / world, k (r+1) / world)
       // in place (column-major: a contiguous slice) and one grouped broadcast per rank hands every slice to everybody.
       // All ranks end up with the same bytes, so the model stays bit-identical across ranks.
       auto col0 = [&](int r) { return static_cast<int64_t>(k) * r / c.world; };
       const int64_t m0 = col0(c.rank), m1 = col0(c.rank + 1);
-      c.potrs(Hj, b, rhs.as<double>() + m0 * b, static_cast<int>(m1 - m0), info_slot++, S1);
+      c.potrs(Hj, b, rhs.as<double>() + m0 * b, static_cast<int>(m1 - m0), info_slot++, SS);
       KS_NCCL(nccl_api().GroupStart());
       for (int r = 0; r < c.world; ++r) {
         double* slice = rhs.as<double>() + col0(r) * b;
-        KS_NCCL(nccl_api().Broadcast(slice, slice, static_cast<size_t>(col0(r + 1) - col0(r)) * b, ncclFloat64, r, c.comm, S1));
+        KS_NCCL(nccl_api().Broadcast(slice, slice, static_cast<size_t>(col0(r + 1) - col0(r)) * b, ncclFloat64, r, c.comm, SS));
       }
       KS_NCCL(nccl_api().GroupEnd());
       c.launches += 1;
-      dw_ptr = rhs.as<double>();
     } else {
-      c.potrs(Hj, b, rhs.as<double>(), k, info_slot++, S1);
-      dw_ptr = rhs.as<double>();
+      c.potrs(Hj, b, rhs.as<double>(), k, info_slot++, SS);
     }
-    KS_CUDA(cudaEventRecord(ev_solved[t], S1));
+    const double* dw_ptr = rhs.as<double>();
     if (f16) {
-      KS_CUDA(cudaMemsetAsync(maxbits + 1, 0, sizeof(unsigned), S1));
-      launch_max_abs_f64(dw_ptr, static_cast<int64_t>(b) * k, maxbits + 1, S1);
-      launch_pow2_scale(maxbits + 1, 8192.f, dwscale, S1);
+      KS_CUDA(cudaMemsetAsync(maxbits + 1, 0, sizeof(unsigned), SS));
+      launch_max_abs_f64(dw_ptr, static_cast<int64_t>(b) * k, maxbits + 1, SS);
+      launch_pow2_scale(maxbits + 1, 8192.f, dwscale, SS);
       launch_pack_update16(dw_ptr, model->W[j]->as<double>(), deltas[j]->as<double>(), bop.p, static_cast<int>(lds),
-                           cbias.as<float>(), b, k, static_cast<int>(kpad), dwscale, S1, x2 ? bop_lo.p : nullptr);
+                           cbias.as<float>(), b, k, static_cast<int>(kpad), dwscale, SS, x2 ? bop_lo.p : nullptr);
       c.launches += 2;
     } else {
-      launch_pack_update(dw_ptr, model->W[j]->as<double>(), deltas[j]->as<double>(), bop.as<float>(), nullptr,
-                         static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), S1);
+      launch_pack_update(dw_ptr, model->W[j]->as<double>(), deltas[j]->as<double>(), bop.as<float>(), x2 ? bop_lo.as<float>() : nullptr,
+                         static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), SS);
     }
     c.launches += 1;
     flops += 2.0 * static_cast<double>(b) * b * k;
-    c.span_end();
-    c.span_begin(PH_UPDATE);
+    c.span_end(SS);
+    KS_CUDA(cudaEventRecord(ev_solved[t], SS));
+    if (it == num_iter - 1 && model->host_valid) {  // W_j and mean_j are final: mirror them to the host while the fit goes on
+      KS_CUDA(cudaStreamWaitEvent(S5, ev_solved[t], 0));
+      model_block_to_host(*model, j, S5);
+    }
+  };
+  // ---------------- update(t): R -= S dW on SR
+  auto do_update = [&](int t) {
+    const int j = steps[t].j, buf = t % NBUF;
+    int64_t c0;
+    const int b = block_cols(j, &c0);
+    if (SR != SS) KS_CUDA(cudaStreamWaitEvent(SR, ev_solved[t], 0));
+    c.span_begin(PH_UPDATE, SR);
     launch_update(c, slab[buf].p, lds, n_loc, b, bop.p, lds, k, r_f32.as<float>(), kpad, cbias.as<float>(),
-                  EPI_UPDATE, /*reduce=*/true, S1, f16, f16 ? dwscale + 1 : nullptr);
+                  EPI_UPDATE, /*reduce=*/true, SR, f16, f16 ? dwscale + 1 : nullptr);
     if (x2) {  // - S_lo dW_hi - S_hi dW_lo (the constant delta^T dW is applied once, above)
-      launch_update(c, slab_lo[buf].p, lds, n_loc, b, bop.p, lds, k, r_f32.as<float>(), kpad, nullptr, EPI_UPDATE, true, S1, true,
-                    dwscale + 1);
-      launch_update(c, slab[buf].p, lds, n_loc, b, bop_lo.p, lds, k, r_f32.as<float>(), kpad, nullptr, EPI_UPDATE, true, S1, true,
-                    dwscale + 1);
+      launch_update(c, slab_lo[buf].p, lds, n_loc, b, bop.p, lds, k, r_f32.as<float>(), kpad, nullptr, EPI_UPDATE, true, SR, f16,
+                    f16 ? dwscale + 1 : nullptr);
+      launch_update(c, slab[buf].p, lds, n_loc, b, bop_lo.p, lds, k, r_f32.as<float>(), kpad, nullptr, EPI_UPDATE, true, SR, f16,
+                    f16 ? dwscale + 1 : nullptr);
       flops += 4.0 * n_loc * static_cast<double>(b) * k;
     }
     flops += 2.0 * n_loc * static_cast<double>(b) * k;
-    c.span_end();
-    KS_CUDA(cudaEventRecord(ev_upd[t], S1));
+    c.span_end(SR);
+    KS_CUDA(cudaEventRecord(ev_upd[t], SR));
   };
 
-  // Enqueue order: a stream-wait on an event that has not been recorded yet counts as complete, so every wait must be
-  // enqueued after the corresponding record: prep(t) [featurize] after main(t - NBUF + 1), prepB(t) [Gram, factor] after main(t-1).
-  for (int t = 0; t < std::min(T, NBUF - 1); ++t) prep(t);
-  prepB(0);
-  for (int t = 0; t < T; ++t) {
-    mainstep(t);
-    if (t + 1 < T) prepB(t + 1);
-    if (t + NBUF - 1 < T) prep(t + NBUF - 1);
+  // Enqueue order: a stream-wait on an event that has not been recorded yet counts as complete, so every wait is enqueued
+  // after the corresponding record.
+  if (serial) {
+    // tensor stream: proj(0) proj(1) G(0) | C(t) G(t+1) proj(t+2) update(t) | ...   (slab (t+2)%3 was last read by
+    // update(t-1), G buffer (t+1)%3 by factor(t-2): both precede in stream / event order)
+    for (int t = 0; t < std::min(T, 2); ++t) do_proj(t);
+    do_gram(0);
+    for (int t = 0; t < T; ++t) {
+      do_cgram(t);
+      do_solve(t);
+      if (t + 1 < T) do_gram(t + 1);
+      if (t + 2 < T) do_proj(t + 2);
+      do_update(t);
+    }
+  } else {
+    // proj(t) after update(t - NBUF) released its buffers; G + factor of step t+1 after the chain of step t was enqueued
+    for (int t = 0; t < std::min(T, NBUF - 1); ++t) do_proj(t);
+    do_gram(0);
+    for (int t = 0; t < T; ++t) {
+      do_cgram(t);
+      do_solve(t);
+      do_update(t);
+      if (t + 1 < T) do_gram(t + 1);
+      if (t + NBUF - 1 < T) {
+        if (t >= 1) KS_CUDA(cudaStreamWaitEvent(ST, ev_upd[t - 1], 0));  // step t-1 was the last reader of that slab buffer
+        do_proj(t + NBUF - 1);
+      }
+    }
   }
+  KS_CUDA(cudaStreamWaitEvent(S1, ev_upd[T - 1], 0));
   KS_CUDA(cudaStreamWaitEvent(S1, ev_fact[T - 1], 0));
+  if (model->host_valid) {
+    model_intercept_to_host(*model, S5);
+    cudaEvent_t ev_copy = new_event();
+    KS_CUDA(cudaEventRecord(ev_copy, S5));
+    KS_CUDA(cudaStreamWaitEvent(S1, ev_copy, 0));  // total_ms ends with the whole model on the host
+  }
   KS_CUDA(cudaEventRecord(ev1, S1));
   c.check_async("BlockLeastSquaresEstimator.fit");
   c.check_infos(info_slot);
   float total_ms = 0;
   cudaEventElapsedTime(&total_ms, ev0, ev1);
-  c.event_pool.push_back(ev0);
-  c.event_pool.push_back(ev1);
-  c.event_pool.push_back(ev_init);
-  for (int t = 0; t < T; ++t) {
-    c.event_pool.push_back(ev_g[t]);
-    c.event_pool.push_back(ev_inv[t]);
-    c.event_pool.push_back(ev_solved[t]);
-    c.event_pool.push_back(ev_slab[t]);
-    c.event_pool.push_back(ev_fact[t]);
-    c.event_pool.push_back(ev_upd[t]);
-  }
   double ms[PH_COUNT];
   c.timeline_origin = getenv("KS_TIMELINE") ? ev0 : nullptr;
   c.collect_spans(ms);
@@ -1035,14 +1134,17 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     FILE* f = fopen((std::string(getenv("KS_TIMELINE")) + "." + std::to_string(c.rank)).c_str(), "w");
     if (f) { fputs(c.timeline_json.c_str(), f); fclose(f); }
   }
+  for (cudaEvent_t e : c.fit_events) c.event_pool.push_back(e);
+  c.fit_events.clear();
   std::ostringstream js;
   js << "{\"solver\":\"blockls\",\"n_local\":" << n_loc << ",\"n_total\":" << static_cast<int64_t>(n_total_d) << ",\"d\":" << D
      << ",\"k\":" << k << ",\"block_size\":" << bs << ",\"num_blocks\":" << nb << ",\"num_iter\":" << num_iter
      << ",\"world\":" << c.world << ",\"total_ms\":" << total_ms << ",\"featurize_ms\":" << ms[PH_FEATURIZE]
      << ",\"gram_ms\":" << ms[PH_GRAM] << ",\"allreduce_ms\":" << ms[PH_ALLREDUCE] << ",\"solve_ms\":" << ms[PH_SOLVE]
      << ",\"update_ms\":" << ms[PH_UPDATE] << ",\"other_ms\":" << ms[PH_OTHER] << ",\"local_flops\":" << flops
-     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"" << (x2 ? "f16x2" : f16 ? "f16" : "tf32x1") << "\",\"streams\":3,\"solve\":\"" << (use_inv ? "inverse-owner" : shard_solve ? "potrs-column-sharded" : "potrs")
-     << "\",\"host_ms\":"
+     << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"" << (x2 ? (f16 ? "f16x2" : "tf32x2") : f16 ? "f16" : "tf32x1")
+     << "\",\"pipeline\":" << (serial ? 1 : 0) << ",\"host_mirror\":" << (model->host_valid ? 1 : 0) << ",\"solve\":\""
+     << (c.custom_solve ? "custom" : shard_solve ? "potrs-column-sharded" : "potrs") << "\",\"host_ms\":"
      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count() << "}";
   c.stats_json = js.str();
   return c.add(std::move(model));
@@ -1059,7 +1161,9 @@ static std::unique_ptr<Matrix> new_matrix(int64_t rows, int64_t cols) {
   return m;
 }
 
-static std::unique_ptr<Matrix> apply_model(Ctx& c, Model& md, FeatSrc& src, int last_block, bool use_means) {
+// BlockLinearMapper.apply.  precision KS_PRECISION_F16X2 (the context default): slab and weights are carried as tf32 hi + lo
+// pairs and every block costs three GEMMs (hi*hi + lo*hi + hi*lo); otherwise one tf32 GEMM per block.
+static std::unique_ptr<Matrix> apply_model(Ctx& c, Model& md, FeatSrc& src, int last_block, bool use_means, int precision) {
   const int nb = static_cast<int>(md.brows.size());
   if (last_block < 0 || last_block >= nb) last_block = nb - 1;
   int64_t dsum = 0;
@@ -1073,9 +1177,16 @@ static std::unique_ptr<Matrix> apply_model(Ctx& c, Model& md, FeatSrc& src, int 
   for (auto r : md.brows) bmax = std::max<int>(bmax, static_cast<int>(r));
   const int64_t lds = round_up(std::max(bmax, 1), 32);
   const int64_t kpad = round_up(k, 32);
-  DevBuf slab, bop, cbias, shift;
-  slab.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));
+  const bool x2 = precision == KS_PRECISION_F16X2 && (src.F || src.proj_x2);
+  DevBuf slab, slab_lo, sf32, bop, bop_lo, cbias, shift;
+  const size_t slab_bytes = sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds);
+  slab.alloc(slab_bytes);
   bop.alloc(sizeof(float) * static_cast<size_t>(kpad) * lds);
+  if (x2) {
+    slab_lo.alloc(slab_bytes);
+    bop_lo.alloc(bop.bytes);
+    if (!src.F) sf32.alloc(slab_bytes);
+  }
   cbias.alloc(sizeof(float) * kpad);
   shift.alloc(sizeof(float) * lds);
   int64_t c0 = 0;
@@ -1086,13 +1197,29 @@ static std::unique_ptr<Matrix> apply_model(Ctx& c, Model& md, FeatSrc& src, int 
       launch_f64_to_f32_vec(md.mean[j]->as<double>(), shift.as<float>(), b, c.st);
       c.launches += 1;
     }
-    produce_slab(c, src, c0, b, shift.as<float>(), slab.as<float>(), lds, 0, n_loc);
-    // the fp32 rounding of the mean is compensated in the bias: cbias = intercept - (mean - fp32(mean)) . W  ~ intercept
-    launch_pack_apply(md.W[j]->as<double>(), nullptr, (j == 0 && md.has_intercept) ? md.intercept.as<double>() : nullptr,
-                      bop.as<float>(), static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), c.st);
+    if (x2 && src.F) {
+      launch_center_round(src.F->d, src.F->ld, static_cast<int>(c0), shift.as<float>(), slab.as<float>(), nullptr, lds, n_loc, b, c.st,
+                          slab_lo.as<float>());
+      c.launches += 1;
+    } else if (x2) {
+      produce_slab(c, src, c0, b, shift.as<float>(), sf32.p, lds, 0, n_loc, /*round_out=*/false, nullptr, c.st, false, true);
+      launch_center_round(sf32.as<float>(), lds, 0, src.zeros.as<float>(), slab.as<float>(), nullptr, lds, n_loc, b, c.st,
+                          slab_lo.as<float>());
+      c.launches += 1;
+    } else {
+      produce_slab(c, src, c0, b, shift.as<float>(), slab.as<float>(), lds, 0, n_loc);
+    }
+    // the fp32 rounding of the mean is compensated in the bias: cbias = intercept - (mean - fp32(mean)) . W
+    launch_pack_apply(md.W[j]->as<double>(), (use_means && md.has_mean) ? md.mean[j]->as<double>() : nullptr, shift.as<float>(),
+                      (j == 0 && md.has_intercept) ? md.intercept.as<double>() : nullptr, bop.as<float>(),
+                      x2 ? bop_lo.as<float>() : nullptr, static_cast<int>(lds), cbias.as<float>(), b, k, static_cast<int>(kpad), c.st);
     c.launches += 1;
     launch_update(c, slab.as<float>(), lds, n_loc, b, bop.as<float>(), lds, k, out->d, out->ld, cbias.as<float>(), EPI_APPLY,
                   /*reduce=*/j > 0);
+    if (x2) {
+      launch_update(c, slab_lo.as<float>(), lds, n_loc, b, bop.as<float>(), lds, k, out->d, out->ld, nullptr, EPI_APPLY, true);
+      launch_update(c, slab.as<float>(), lds, n_loc, b, bop_lo.as<float>(), lds, k, out->d, out->ld, nullptr, EPI_APPLY, true);
+    }
     c0 += md.block_size;
   }
   c.check_async("BlockLinearMapper.apply");
@@ -1115,6 +1242,21 @@ static Ctx* find_ctx(int64_t h) {
   return it == g_ctxs.end() ? nullptr : it->second.get();
 }
 
+// An exception that unwinds a fit returns its workspace to the memory pool while kernels that use it may still be queued on
+// the context's streams.  Nothing may be handed out of the pool before those have drained: wait for the whole device
+// (the context is single-threaded, so no allocation can have happened in between), then recycle the fit's events.
+static void after_error(Ctx& c) {
+  cudaDeviceSynchronize();
+  cudaGetLastError();
+  for (cudaEvent_t e : c.fit_events) c.event_pool.push_back(e);
+  c.fit_events.clear();
+  for (auto& sp : c.spans) {
+    c.event_pool.push_back(sp.a);
+    c.event_pool.push_back(sp.b);
+  }
+  c.spans.clear();
+}
+
 template <class Fn>
 static int32_t guard(int64_t ctx, Fn&& fn) {
   Ctx* c = find_ctx(ctx);
@@ -1129,10 +1271,11 @@ static int32_t guard(int64_t ctx, Fn&& fn) {
     return KS_OK;
   } catch (const KsError& e) {
     c->err = e.msg;
-    cudaGetLastError();
+    after_error(*c);
     return e.code;
   } catch (const std::exception& e) {
     c->err = std::string("exception: ") + e.what();
+    after_error(*c);
     return KS_ERR_INVALID;
   }
 }
@@ -1188,14 +1331,16 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
     if (const char* e = getenv("KS_EPI_MULTI")) c->epi_multi = atoi(e) != 0;
     if (const char* e = getenv("KS_SHARD_SOLVE")) c->shard_solve = atoi(e) != 0;
     if (const char* e = getenv("KS_PROJ_F16")) c->proj_f16 = atoi(e) != 0;
-    if (const char* e = getenv("KS_PRECISION")) c->precision = (atoi(e) == 1 || !strcmp(e, "f16")) ? KS_PRECISION_F16 : KS_PRECISION_TF32;
+    if (const char* e = getenv("KS_PRECISION"))
+      c->precision = (atoi(e) == 1 || !strcmp(e, "f16")) ? KS_PRECISION_F16 : (atoi(e) == 2 || !strcmp(e, "f16x2") || !strcmp(e, "parity")) ? KS_PRECISION_F16X2 : KS_PRECISION_TF32;
     if (const char* e = getenv("KS_CUSTOM_SOLVE")) c->custom_solve = atoi(e) != 0;
     if (const char* e = getenv("KS_RESERVE_SMS")) c->reserve_sms = std::max(0, std::min(140, atoi(e)));
-    if (const char* e = getenv("KS_INV_MIN_WORLD")) c->inv_min_world = std::max(1, atoi(e));
-    if (const char* e = getenv("KS_EXCL_SOLVE_MIN_WORLD")) c->exclusive_solve_min_world = std::max(1, atoi(e));
+    if (const char* e = getenv("KS_PIPELINE")) c->pipeline = atoi(e) != 0;
+    if (const char* e = getenv("KS_HOST_MIRROR")) c->host_mirror = atoi(e) != 0;
     KS_CUDA(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, prio_least));
     KS_CUDA(cudaStreamCreateWithPriority(&c->st3, cudaStreamNonBlocking, prio_mid));
     KS_CUDA(cudaStreamCreateWithPriority(&c->st4, cudaStreamNonBlocking, prio_mid));
+    KS_CUDA(cudaStreamCreateWithPriority(&c->st5, cudaStreamNonBlocking, prio_mid));
     if (world_size > 1) {
       if (!nccl_id) throw KsError{KS_ERR_INVALID, "nccl_id required for world_size > 1"};
       ncclUniqueId id;
@@ -1234,14 +1379,21 @@ KS_API int32_t ks_ctx_destroy(int64_t ctx) {
   if (c->st2) cudaStreamSynchronize(c->st2);
   if (c->st3) cudaStreamSynchronize(c->st3);
   if (c->st4) cudaStreamSynchronize(c->st4);
+  if (c->st5) cudaStreamSynchronize(c->st5);
   c->matrices.clear();
   c->rfs.clear();
   c->models.clear();
   c->tile_cache.clear();
   for (auto e : c->event_pool) cudaEventDestroy(e);
+  for (auto& ln : c->lanes) {
+    if (ln->s) cudaStreamSynchronize(ln->s);
+    if (ln->h) solver_api().Destroy(ln->h);
+    ln->work.release();
+    if (ln->s) cudaStreamDestroy(ln->s);
+  }
+  c->lanes.clear();
   if (c->solver) solver_api().Destroy(c->solver);
   if (c->solver2) solver_api().Destroy(c->solver2);
-  if (c->blas) blas_api().Destroy(c->blas);
   if (c->comm3 && c->comm3 != c->comm) nccl_api().CommDestroy(c->comm3);
   if (c->comm2 && c->comm2 != c->comm) nccl_api().CommDestroy(c->comm2);
   if (c->comm) nccl_api().CommDestroy(c->comm);
@@ -1251,13 +1403,17 @@ KS_API int32_t ks_ctx_destroy(int64_t ctx) {
   if (c->st2) cudaStreamDestroy(c->st2);
   if (c->st3) cudaStreamDestroy(c->st3);
   if (c->st4) cudaStreamDestroy(c->st4);
+  if (c->st5) cudaStreamDestroy(c->st5);
   c.reset();
   bool last;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     last = g_ctxs.empty();
   }
-  if (last) pool_release_all();
+  if (last) {
+    pool_release_all();
+    host_pool_release_all();
+  }
   return KS_OK;
 }
 
@@ -1279,11 +1435,12 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     else if (n == "epi_multi") c.epi_multi = value != 0;
     else if (n == "shard_solve") c.shard_solve = value != 0;
     else if (n == "proj_f16") c.proj_f16 = value != 0;
-    else if (n == "precision" && (value == KS_PRECISION_TF32 || value == KS_PRECISION_F16)) c.precision = static_cast<int>(value);
+    else if (n == "precision" && (value == KS_PRECISION_TF32 || value == KS_PRECISION_F16 || value == KS_PRECISION_F16X2)) c.precision = static_cast<int>(value);
     else if (n == "custom_solve") c.custom_solve = value != 0;
     else if (n == "reserve_sms" && value >= 0 && value < 148) c.reserve_sms = static_cast<int>(value);
-    else if (n == "inv_min_world" && value >= 1) c.inv_min_world = static_cast<int>(value);
-    else if (n == "exclusive_solve_min_world" && value >= 1) c.exclusive_solve_min_world = static_cast<int>(value);
+    else if (n == "pipeline") c.pipeline = value != 0;
+    else if (n == "solve_lanes" && value >= 1 && value <= 16) c.solve_lanes = static_cast<int>(value);
+    else if (n == "host_mirror") c.host_mirror = value != 0;
     else if (n == "timing") c.timing = value != 0;
     else throw KsError{KS_ERR_INVALID, "unknown option or bad value: " + n};
   });
@@ -1412,13 +1569,16 @@ KS_API int32_t ks_cosine_rf_create(int64_t ctx, const double* W_colmajor, const 
     r->ld = round_up(n_in, kPadCols);
     r->wbuf.alloc(sizeof(float) * static_cast<size_t>(n_out * r->ld));
     r->bbuf.alloc(sizeof(float) * static_cast<size_t>(n_out));
+    r->wfbuf.alloc(r->wbuf.bytes);
     r->W = r->wbuf.as<float>();
+    r->Wfull = r->wfbuf.as<float>();
     r->bias = r->bbuf.as<float>();
     DevBuf stage;
     stage.alloc(sizeof(double) * static_cast<size_t>(n_out * n_in + n_out));
     KS_CUDA(cudaMemcpyAsync(stage.p, W_colmajor, sizeof(double) * n_out * n_in, cudaMemcpyHostToDevice, c.st));
     KS_CUDA(cudaMemcpyAsync(stage.as<double>() + n_out * n_in, b, sizeof(double) * n_out, cudaMemcpyHostToDevice, c.st));
     launch_w_to_operand(stage.as<double>(), n_out, n_in, r->W, r->ld, c.st);
+    launch_w_to_operand(stage.as<double>(), n_out, n_in, r->Wfull, r->ld, c.st, /*round=*/false);
     launch_f64_to_f32_vec(stage.as<double>() + n_out * n_in, r->bias, n_out, c.st);
     c.launches += 2;
     c.check_async("cosine_rf_create");
@@ -1431,10 +1591,12 @@ KS_API int32_t ks_cosine_rf_apply(int64_t ctx, int64_t rf, int64_t x_in, int64_t
   return guard(ctx, [&](Ctx& c) {
     if (!out_features) throw KsError{KS_ERR_INVALID, "null output"};
     FeatSrc src;
-    make_feat_src(c, 0, x_in, &rf, 1, src);
+    make_feat_src(c, 0, x_in, &rf, 1, src, c.precision);
     auto out = new_matrix(src.n_rows, src.D);
     KS_CUDA(cudaMemsetAsync(out->d, 0, out->buf.bytes, c.st));
-    produce_slab(c, src, 0, src.D, src.zeros.as<float>(), out->d, out->ld, 0, src.n_rows, /*round_out=*/false);
+    // parity mode: split fp16 projection operands (hi*hi + lo*hi + hi*lo in one GEMM of depth 3 d_in); else tf32 operands
+    produce_slab(c, src, 0, src.D, src.zeros.as<float>(), out->d, out->ld, 0, src.n_rows, /*round_out=*/false, nullptr, nullptr, false,
+                 src.proj_x2);
     c.check_async("CosineRandomFeatures.apply");
     *out_features = c.add(std::move(out));
   });
@@ -1446,14 +1608,19 @@ KS_API int32_t ks_cosine_rf_destroy(int64_t ctx, int64_t rf) {
 }
 
 // ---------------------------------------------------------------- estimators
+// the per-call precision_mode is authoritative; KS_PRECISION_DEFAULT means "the context's setting" (option "precision")
+static int resolve_precision(Ctx& c, int32_t precision_mode) {
+  if (precision_mode == KS_PRECISION_DEFAULT) return c.precision;
+  if (precision_mode != KS_PRECISION_TF32 && precision_mode != KS_PRECISION_F16 && precision_mode != KS_PRECISION_F16X2)
+    throw KsError{KS_ERR_INVALID, "unsupported precision_mode"};
+  return precision_mode;
+}
 KS_API int32_t ks_blockls_fit(int64_t ctx, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, int64_t labels,
                        int32_t block_size, int32_t num_iter, double lambda, int64_t num_features_or_0, int32_t precision_mode,
                        int64_t* out_model) {
   return guard(ctx, [&](Ctx& c) {
     if (!out_model) throw KsError{KS_ERR_INVALID, "null out_model"};
-    if (precision_mode != KS_PRECISION_TF32 && precision_mode != KS_PRECISION_F16 && precision_mode != KS_PRECISION_F16X2)
-      throw KsError{KS_ERR_INVALID, "unsupported precision_mode"};
-    const int prec = (c.precision == KS_PRECISION_F16 && precision_mode == KS_PRECISION_TF32) ? KS_PRECISION_F16 : precision_mode;
+    const int prec = resolve_precision(c, precision_mode);
     FeatSrc src;
     make_feat_src(c, features, x_in, rfs, n_rfs, src, prec);
     *out_model = fit_blockls(c, src, c.matrix(labels), block_size, num_iter, lambda, num_features_or_0, prec);
@@ -1465,11 +1632,10 @@ KS_API int32_t ks_blockwls_fit(int64_t ctx, int64_t features, int64_t x_in, cons
                         int32_t precision_mode, int64_t* out_model) {
   return guard(ctx, [&](Ctx& c) {
     if (!out_model) throw KsError{KS_ERR_INVALID, "null out_model"};
-    if (precision_mode != KS_PRECISION_TF32)
-      throw KsError{KS_ERR_INVALID, "unsupported precision_mode (the weighted solver computes in tf32 only)"};
+    const int prec = resolve_precision(c, precision_mode);
     FeatSrc src;
-    make_feat_src(c, features, x_in, rfs, n_rfs, src);
-    *out_model = fit_bwls(c, src, c.matrix(labels), block_size, num_iter, lambda, mixture_weight, num_features_or_0);
+    make_feat_src(c, features, x_in, rfs, n_rfs, src, prec);
+    *out_model = fit_bwls(c, src, c.matrix(labels), block_size, num_iter, lambda, mixture_weight, num_features_or_0, prec);
   });
 }
 
@@ -1478,8 +1644,9 @@ KS_API int32_t ks_linear_map_fit(int64_t ctx, int64_t features, int64_t labels, 
     if (!out_model) throw KsError{KS_ERR_INVALID, "null out_model"};
     FeatSrc src;
     make_feat_src(c, features, 0, nullptr, 0, src);
-    // one block spanning every feature, one pass: exactly (A^T A [+ lambda I]) \ A^T y on centred data
-    *out_model = fit_blockls(c, src, c.matrix(labels), static_cast<int>(src.D), 1, has_lambda ? lambda : 0.0, 0);
+    // one block spanning every feature, one pass: exactly (A^T A [+ lambda I]) \ A^T y on centred data; the operand mode is the
+    // context's ("precision" option; the default is the split-operand parity mode)
+    *out_model = fit_blockls(c, src, c.matrix(labels), static_cast<int>(src.D), 1, has_lambda ? lambda : 0.0, 0, c.precision);
   });
 }
 
@@ -1533,10 +1700,33 @@ KS_API int32_t ks_model_get_block(int64_t ctx, int64_t model, int32_t j, double*
   return guard(ctx, [&](Ctx& c) {
     Model& m = c.model(model);
     if (j < 0 || j >= static_cast<int>(m.brows.size())) throw KsError{KS_ERR_INVALID, "block index out of range"};
+    if (has_mean) *has_mean = m.has_mean ? 1 : 0;
+    if (m.host_valid) {  // the fit already mirrored the block into pinned host memory
+      const uint8_t* h = static_cast<const uint8_t*>(m.host.p);
+      if (W_out) memcpy(W_out, h + m.host_w_off[j], sizeof(double) * m.brows[j] * m.k);
+      if (mean_out && m.has_mean) memcpy(mean_out, h + m.host_mean_off[j], sizeof(double) * m.brows[j]);
+      return;
+    }
     if (W_out) KS_CUDA(cudaMemcpyAsync(W_out, m.W[j]->p, sizeof(double) * m.brows[j] * m.k, cudaMemcpyDeviceToHost, c.st));
     if (mean_out && m.has_mean) KS_CUDA(cudaMemcpyAsync(mean_out, m.mean[j]->p, sizeof(double) * m.brows[j], cudaMemcpyDeviceToHost, c.st));
-    if (has_mean) *has_mean = m.has_mean ? 1 : 0;
     KS_CUDA(cudaStreamSynchronize(c.st));
+  });
+}
+KS_API int32_t ks_model_host_view(int64_t ctx, int64_t model, int32_t j, const double** W_ptr, const double** mean_ptr,
+                                  const double** intercept_ptr) {
+  return guard(ctx, [&](Ctx& c) {
+    Model& m = c.model(model);
+    if (j < 0 || j >= static_cast<int>(m.brows.size())) throw KsError{KS_ERR_INVALID, "block index out of range"};
+    if (!m.host_valid) {  // models that were not fitted with the mirror on (or came from the host): mirror now
+      model_alloc_host(m);
+      for (int q = 0; q < static_cast<int>(m.brows.size()); ++q) model_block_to_host(m, q, c.st);
+      model_intercept_to_host(m, c.st);
+      KS_CUDA(cudaStreamSynchronize(c.st));
+    }
+    const uint8_t* h = static_cast<const uint8_t*>(m.host.p);
+    if (W_ptr) *W_ptr = reinterpret_cast<const double*>(h + m.host_w_off[j]);
+    if (mean_ptr) *mean_ptr = m.has_mean ? reinterpret_cast<const double*>(h + m.host_mean_off[j]) : nullptr;
+    if (intercept_ptr) *intercept_ptr = m.has_intercept ? reinterpret_cast<const double*>(h + m.host_b_off) : nullptr;
   });
 }
 KS_API int32_t ks_model_get_intercept(int64_t ctx, int64_t model, double* b_out, int32_t* has_intercept) {
@@ -1553,8 +1743,8 @@ KS_API int32_t ks_model_apply(int64_t ctx, int64_t model, int64_t features, int6
   return guard(ctx, [&](Ctx& c) {
     if (!out) throw KsError{KS_ERR_INVALID, "null output"};
     FeatSrc src;
-    make_feat_src(c, features, x_in, rfs, n_rfs, src);
-    *out = c.add(apply_model(c, c.model(model), src, -1, true));
+    make_feat_src(c, features, x_in, rfs, n_rfs, src, c.precision);
+    *out = c.add(apply_model(c, c.model(model), src, -1, true, c.precision));
   });
 }
 KS_API int32_t ks_model_apply_partial(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
@@ -1562,8 +1752,8 @@ KS_API int32_t ks_model_apply_partial(int64_t ctx, int64_t model, int64_t featur
   return guard(ctx, [&](Ctx& c) {
     if (!out) throw KsError{KS_ERR_INVALID, "null output"};
     FeatSrc src;
-    make_feat_src(c, features, x_in, rfs, n_rfs, src);
-    *out = c.add(apply_model(c, c.model(model), src, last_block, true));
+    make_feat_src(c, features, x_in, rfs, n_rfs, src, c.precision);
+    *out = c.add(apply_model(c, c.model(model), src, last_block, true, c.precision));
   });
 }
 KS_API int32_t ks_model_apply_argmax(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
@@ -1571,8 +1761,8 @@ KS_API int32_t ks_model_apply_argmax(int64_t ctx, int64_t model, int64_t feature
   return guard(ctx, [&](Ctx& c) {
     if (!host_out) throw KsError{KS_ERR_INVALID, "null output"};
     FeatSrc src;
-    make_feat_src(c, features, x_in, rfs, n_rfs, src);
-    auto y = apply_model(c, c.model(model), src, -1, true);
+    make_feat_src(c, features, x_in, rfs, n_rfs, src, c.precision);
+    auto y = apply_model(c, c.model(model), src, -1, true, c.precision);
     DevBuf idx;
     idx.alloc(sizeof(int32_t) * static_cast<size_t>(std::max<int64_t>(y->rows, 1)));
     launch_argmax_rows(y->d, y->ld, y->rows, static_cast<int>(y->cols), idx.as<int32_t>(), c.st);
@@ -1588,10 +1778,10 @@ KS_API int32_t ks_model_confusion_matrix(int64_t ctx, int64_t model, int64_t fea
     Model& m = c.model(model);
     Matrix& L = c.matrix(labels);
     FeatSrc src;
-    make_feat_src(c, features, x_in, rfs, n_rfs, src);
+    make_feat_src(c, features, x_in, rfs, n_rfs, src, c.precision);
     if (L.rows != src.n_rows || L.cols != m.k) throw KsError{KS_ERR_INVALID, "labels shape mismatch"};
     const int k = static_cast<int>(m.k);
-    auto y = apply_model(c, m, src, -1, true);
+    auto y = apply_model(c, m, src, -1, true, c.precision);
     DevBuf pred, act, counts;
     pred.alloc(sizeof(int32_t) * static_cast<size_t>(std::max<int64_t>(y->rows, 1)));
     act.alloc(pred.bytes);
@@ -1616,9 +1806,9 @@ KS_API int32_t ks_model_cost(int64_t ctx, int64_t model, int64_t features, int64
     Model& m = c.model(model);
     Matrix& L = c.matrix(labels);
     FeatSrc src;
-    make_feat_src(c, features, x_in, rfs, n_rfs, src);
+    make_feat_src(c, features, x_in, rfs, n_rfs, src, c.precision);
     if (L.rows != src.n_rows || L.cols != m.k) throw KsError{KS_ERR_INVALID, "labels shape mismatch"};
-    auto y = apply_model(c, m, src, -1, /*use_means=*/false);  // computeCost applies no feature scalers (:149-156)
+    auto y = apply_model(c, m, src, -1, /*use_means=*/false, c.precision);  // computeCost applies no feature scalers (:149-156)
     DevBuf acc;  // [0] squared error, [1] row count, [2] ||W||^2
     acc.alloc(sizeof(double) * 3);
     KS_CUDA(cudaMemsetAsync(acc.p, 0, acc.bytes, c.st));

@@ -58,6 +58,28 @@ struct DevBuf {
   T* as() const { return static_cast<T*>(p); }
 };
 
+// pinned host memory from a per-process caching pool (cudaHostAlloc of 0.5 GB costs ~0.2 s)
+void* host_pool_alloc(size_t bytes);
+void host_pool_free(void* p, size_t bytes);
+struct HostBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  HostBuf() = default;
+  HostBuf(const HostBuf&) = delete;
+  HostBuf& operator=(const HostBuf&) = delete;
+  ~HostBuf() { release(); }
+  void release() {
+    if (p) host_pool_free(p, bytes);
+    p = nullptr;
+    bytes = 0;
+  }
+  void alloc(size_t n) {
+    release();
+    p = host_pool_alloc(n ? n : 16);
+    bytes = n ? n : 16;
+  }
+};
+
 struct Matrix {  // fp32 row-major, ld % 32 == 0, padding columns are zero
   DevBuf buf;
   float* d = nullptr;
@@ -65,8 +87,9 @@ struct Matrix {  // fp32 row-major, ld % 32 == 0, padding columns are zero
 };
 
 struct CosRF {
-  DevBuf wbuf, bbuf;
+  DevBuf wbuf, wfbuf, bbuf;
   float* W = nullptr;     // [n_out][ld] tf32-rounded, K-major GEMM operand
+  float* Wfull = nullptr; // [n_out][ld] fp32(W) unrounded: source of the fp16 / split operands (rounding once, not twice)
   float* bias = nullptr;  // [n_out]
   int64_t n_out = 0, n_in = 0, ld = 0;
 };
@@ -79,6 +102,12 @@ struct Model {  // BlockLinearMapper state (K/nodes/learning/BlockLinearMapper.s
   std::vector<std::unique_ptr<DevBuf>> mean;  // rows_j fp64 (if has_mean)
   DevBuf intercept;                           // k fp64
   bool has_mean = false, has_intercept = false;
+  // Pinned host mirror written by async D2H copies while the fit is still running (block j's W_j / mean_j are final as soon
+  // as its last update is packed): "all W_j, intercept on host"  costs no extra time after the fit.
+  HostBuf host;                               // [W_0 | mean_0 | W_1 | mean_1 | ... | intercept]
+  std::vector<size_t> host_w_off, host_mean_off;
+  size_t host_b_off = 0;
+  bool host_valid = false;
 };
 
 struct SolverApi {
@@ -89,18 +118,7 @@ struct SolverApi {
   cusolverStatus_t (*DpotrfBufferSize)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, int*) = nullptr;
   cusolverStatus_t (*Dpotrf)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, double*, int, int*) = nullptr;
   cusolverStatus_t (*Dpotrs)(cusolverDnHandle_t, cublasFillMode_t, int, int, const double*, int, double*, int, int*) = nullptr;
-  cusolverStatus_t (*DpotriBufferSize)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, int*) = nullptr;
-  cusolverStatus_t (*Dpotri)(cusolverDnHandle_t, cublasFillMode_t, int, double*, int, double*, int, int*) = nullptr;
 };
-struct BlasApi {  // cuBLAS, one plain library call: the fp64 symmetric product H^-1 * rhs
-  void* lib = nullptr;
-  cublasStatus_t (*Create)(cublasHandle_t*) = nullptr;
-  cublasStatus_t (*Destroy)(cublasHandle_t) = nullptr;
-  cublasStatus_t (*SetStream)(cublasHandle_t, cudaStream_t) = nullptr;
-  cublasStatus_t (*Dsymm)(cublasHandle_t, cublasSideMode_t, cublasFillMode_t, int, int, const double*, const double*, int,
-                          const double*, int, const double*, double*, int) = nullptr;
-};
-BlasApi& blas_api();
 struct NcclApi {
   void* lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -121,28 +139,41 @@ enum Phase { PH_FEATURIZE = 0, PH_GRAM, PH_ALLREDUCE, PH_SOLVE, PH_UPDATE, PH_OT
 struct Ctx {
   int device = 0, rank = 0, world = 1;
   int num_sms = 148;
-  cudaStream_t st = nullptr;   // main stream: residual-dependent chain (A^T R, triangular solves, update)
-  cudaStream_t st2 = nullptr;  // prep stream: featurize + Gram of the blocks AHEAD (independent of the residual)
-  cudaStream_t st3 = nullptr;  // factor stream: fp64 assembly + Cholesky of the blocks ahead
-  cudaStream_t st4 = nullptr;  // broadcast stream of the owner-computed inverses (so a broadcast never blocks a rank's own factor work)
+  // Stream roles of the pipelined fit (engine.cu::fit_blockls), pipeline = 1 (default):
+  //   st  (highest priority) solve chain: all-reduce of C, rhs assembly, triangular solves, operand packing
+  //   st2 (lowest priority)  ALL tensor-core kernels in one order: C(j), G(j+1), proj(j+2), update(j) -- never two at once
+  //   st3 (mid)              factor chain: fp64 system assembly + Cholesky of the block ahead
+  //   st4 (mid)              all-reduce of G
+  //   st5 (mid)              D2H copies of finished model blocks into the pinned host mirror
+  // pipeline = 0 is the round-1 arrangement (residual chain incl. its tensor kernels on st, look-ahead tensor kernels on st2).
+  cudaStream_t st = nullptr, st2 = nullptr, st3 = nullptr, st4 = nullptr, st5 = nullptr;
   ncclComm_t comm = nullptr;   // collectives issued on st
   ncclComm_t comm2 = nullptr;  // collectives issued on st2 (split of comm; falls back to comm)
-  ncclComm_t comm3 = nullptr;  // broadcasts of the per-block inverse issued on st3
-  int inv_min_world = 1 << 30; // experimental: from this world size on, block j's Cholesky + explicit inverse run on rank
-                               // j % world only and are broadcast (off by default: cusolverDnDpotri is ~25 ms per 4096^2
-                               // block and its fp64 work slows the tensor kernels more than the shorter solve gains)
+  ncclComm_t comm3 = nullptr;  // collectives issued on st4 (pipeline 1: all-reduce of G)
+  int pipeline = 1;
+  int host_mirror = 1;  // fits mirror the model into pinned host memory while they run
   int shard_solve = 1;  // world > 1: every rank runs the triangular solves for its k / world right-hand sides only and the
                         // columns of dW are gathered (grouped ncclBroadcast, 32 MB at b = 4096, k = 1000) -- the solve is the
                         // serial term of the strong-scaling curve and its cost is proportional to the number of columns
-  int exclusive_solve_min_world = 1 << 30;  // experimental: from this world size on the look-ahead Gram waits for the
-                                            // critical chain's triangular solves (4.4 ms alone, ~11 ms contended); measured
-                                            // neutral at 4 GPUs (332 vs 338 ms) because it serialises Gram and solve
   cusolverDnHandle_t solver = nullptr;   // triangular solves (main stream)
-  cublasHandle_t blas = nullptr;         // H^-1 * rhs on the main stream
   cudaStream_t solver_stream = nullptr, solver2_stream = nullptr;  // streams the handles are currently bound to
   cusolverDnHandle_t solver2 = nullptr;  // factorizations (factor stream): a handle's internal cuBLAS workspace is per stream
   DevBuf solver_work;
   int solver_lwork = 0;
+  // independent small factorisations (the per-class systems of the weighted solver) run on several lanes at once
+  struct SolveLane {
+    cudaStream_t s = nullptr;
+    cusolverDnHandle_t h = nullptr;
+    DevBuf work;
+    int lwork = 0;
+  };
+  std::vector<std::unique_ptr<SolveLane>> lanes;
+  int solve_lanes = 4;
+  void ensure_lanes(int n);
+  // Cholesky factorisation of H (n x n, lower) + solve of nrhs right-hand sides in place, on lane q; status -> dev_info[slot]
+  void lane_potrf_potrs(int q, double* H, int n, double* B, int nrhs, int info_slot);
+  // *flag (device, fp64) = number of non-zero entries among dev_info[0, used); the slots are cleared
+  void infos_to_flag(int used, double* flag, cudaStream_t s);
   DevBuf dev_info;  // int[kMaxInfo]
   std::string err;
   std::string stats_json;
@@ -151,8 +182,7 @@ struct Ctx {
   int gram_pair = 1;  // CTA-pair (cta_group::2) Gram kernel
   int epi_multi = 1;  // CTA-pair kernels: 8 rotating epilogue staging buffers per warp (0: one buffer, store-and-wait)
   int proj_f16 = 1;   // fp16 mode: the projection GEMM X W^T runs with fp16 operands too (0: tf32 operands, fp16 slab)
-  int precision = 0;  // KS_PRECISION_TF32 (0) or KS_PRECISION_F16 (1: fp16 slab / residual / increment operands, kind::f16;
-                      // BlockLeastSquares on generated (cosine) features only, everything else stays tf32)
+  int precision = KS_PRECISION_F16X2;  // what KS_PRECISION_DEFAULT resolves to: the split-operand parity mode
   int reserve_sms = 8; // SMs the persistent look-ahead kernel leaves to the critical chain
   int custom_solve = 0; // experimental: 1 = chol_solve_kernel (single launch; 10.8 ms at b=4096,k=1000 vs 4.4 ms for
                         // cusolverDnDpotrs alone / ~11 ms when potrs shares the SMs), 0 = cusolverDnDpotrs
@@ -181,14 +211,12 @@ struct Ctx {
   void collect_spans(double out_ms[PH_COUNT]);
   void allreduce_f32(float* p, size_t n, bool prep = false);
   void allreduce_f64(double* p, size_t n, bool prep = false);
+  void allreduce_on(void* p, size_t n, bool f64, ncclComm_t cm, cudaStream_t s);
+  std::vector<cudaEvent_t> fit_events;  // events of the fit in flight (returned to event_pool when it ends, also on error)
   void allreduce_max_u32(unsigned* p, size_t n);
   void ensure_solver();
   void potrf(double* H, int n, int info_slot, cudaStream_t s);
   void potrs(const double* H, int n, double* B, int nrhs, int info_slot, cudaStream_t s);
-  // H (Cholesky factor, lower) -> lower triangle of H^-1, in place (cusolverDnDpotri); latency-bound, runs on the factor stream
-  void potri(double* H, int n, int info_slot, cudaStream_t s);
-  // out (n x nrhs) = sym(Hinv, lower) * B   (cublasDsymm): the whole solve of the critical chain is ONE fp64 GEMM
-  void symm_solve(const double* Hinv, int n, const double* B, int nrhs, double* out, cudaStream_t s);
   void check_infos(int used_slots);
   void check_async(const char* what);
 };
@@ -207,8 +235,9 @@ struct FeatSrc {
   DevBuf x3, w3;
   int64_t ldx3 = 0, ldw3 = 0;
   bool proj_x2 = false;
-  DevBuf wcat, bcat;
+  DevBuf wcat, wcat_full, bcat;
   float* Wall = nullptr;
+  float* Wfull = nullptr;  // unrounded fp32 weights (same layout as Wall)
   float* ball = nullptr;
   int64_t ldw = 0, d_in = 0;
   int64_t D = 0, n_rows = 0;
@@ -216,6 +245,7 @@ struct FeatSrc {
 };
 void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs, FeatSrc& out,
                    int precision = 0);  // KS_PRECISION_*: which operand copies of X / W to prepare
+void prepare_generated_operands(Ctx& c, FeatSrc& out, int precision);
 // slab[rows x lds] = round_tf32(features[row_begin : row_begin+rows, c0 : c0+cols] - shift)   (shift may be the zero vector)
 // colsum (optional, fp32[cols], must be zeroed): receives the column sums of the stored slab
 // out16: the slab is fp16 (lds in fp16 elements), generated features only
@@ -233,6 +263,11 @@ void launch_update(Ctx& c, const void* slab, int64_t lds, int64_t rows, int b, c
                    float* out, int64_t ldo, const float* cbias, int epi, bool reduce, cudaStream_t st = nullptr,
                    bool f16 = false, const float* acc_scale_ptr = nullptr);
 
-int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, double w, int64_t nf_opt);
+int64_t fit_bwls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter, double lam, double w, int64_t nf_opt,
+                 int precision = KS_PRECISION_TF32);
+// allocates the pinned mirror of a model whose brows / k / has_mean are set; enqueue_block_to_host copies block j (async, stream s)
+void model_alloc_host(Model& m);
+void model_block_to_host(Model& m, int j, cudaStream_t s);
+void model_intercept_to_host(Model& m, cudaStream_t s);
 
 }  // namespace ks

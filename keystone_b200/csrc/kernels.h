@@ -73,10 +73,11 @@ void launch_init_residual(const float* Y, int64_t ldy, const double* ymean, floa
                           cudaStream_t st);
 // Rr[:, :k] = tf32_rn(R[:, :k]) (the Gram's MN-major operand), Rr[:, k] = 1 (ones column), Rr[:, > k] = 0, and
 // sums[c] += column sums of R (fp64; must be zeroed) -- one pass over R per block
-void launch_round_colsum(const float* R, float* Rr, int64_t ld, int64_t rows, int k, double* sums, cudaStream_t st);
+void launch_round_colsum(const float* R, float* Rr, int64_t ld, int64_t rows, int k, double* sums, cudaStream_t st,
+                         float* Rlo = nullptr);  // Rlo (split-operand mode): tf32(R - Rr)
 // slab[:, :cols] = tf32(F[:, c0:c0+cols] - shift); if colsum != null, colsum[c] += column sums of the slab (fp32 atomics)
 void launch_center_round(const float* F, int64_t ldf, int c0, const float* shift, float* slab, float* colsum, int64_t lds,
-                         int64_t rows, int cols, cudaStream_t st);
+                         int64_t rows, int cols, cudaStream_t st, float* slab_lo = nullptr);  // slab_lo: tf32(v - slab), split mode
 // out[i] = float(sums[i] / *count) (and out64 if non-null); the count lives on the device (no host round trip)
 void launch_divide_by_count(const double* sums, const double* count, float* out, double* out64, int n, cudaStream_t st);
 // delta[i] = double(ssum[i]) / n_total ; mean[i] = shift[i] + delta[i]
@@ -90,9 +91,9 @@ void launch_build_rhs(const float* C, int ldc, const double* delta, const double
 // Wmodel += dW;  Bop_hi/lo [kpad x ldb] = split(dW^T);  cbias[c] = sum_f delta[f] dW[f][c]
 void launch_pack_update(const double* dW, double* Wmodel, const double* delta, float* bop_hi, float* bop_lo, int ldb,
                         float* cbias, int b, int k, int kpad, cudaStream_t st);
-// Bop [kpad x ldb] = split(W^T) for apply; cbias[c] = (add_intercept ? intercept[c] : 0) - sum_f mean[f] W[f][c]
-void launch_pack_apply(const double* W, const double* mean_or_null, const double* intercept_or_null, float* bop_hi,
-                       int ldb, float* cbias, int b, int k, int kpad, cudaStream_t st);
+// Bop hi (/ lo) [kpad x ldb] = split(W^T) for apply; cbias[c] = (intercept ? intercept[c] : 0) - sum_f (mean[f] - shift32[f]) W[f][c]
+void launch_pack_apply(const double* W, const double* mean_or_null, const float* shift32, const double* intercept_or_null,
+                       float* bop_hi, float* bop_lo, int ldb, float* cbias, int b, int k, int kpad, cudaStream_t st);
 void launch_argmax_rows(const float* Y, int64_t ld, int64_t rows, int k, int32_t* out, cudaStream_t st);
 // counts[actual * k + predicted] += 1 over n samples (counts must be zeroed); out-of-range classes are skipped
 void launch_confusion(const int32_t* pred, const int32_t* act, int64_t n, int k, unsigned long long* counts, cudaStream_t st);
@@ -101,7 +102,8 @@ void launch_sq_err(const float* Y, int64_t ldy, const float* L, int64_t ldl, int
 void launch_fill_f32(float* p, int64_t n, float v, cudaStream_t st);
 void launch_normal_f32(float* dst, int64_t ld, int64_t rows, int cols, uint64_t seed, int64_t row_offset, float mean,
                        float stddev, cudaStream_t st);
-void launch_w_to_operand(const double* W_colmajor, int64_t n_out, int64_t n_in, float* dst, int64_t ld, cudaStream_t st);
+void launch_w_to_operand(const double* W_colmajor, int64_t n_out, int64_t n_in, float* dst, int64_t ld, cudaStream_t st,
+                         bool round = true);  // round: tf32 round-to-nearest (MMA operand); false: plain fp32
 void launch_f64_to_f32_vec(const double* src, float* dst, int64_t n, cudaStream_t st);
 // ---- fp16 operand path: device-chosen power-of-two scales (scale[0] = 2^e, scale[1] = 2^-e) and fp16 operand packers
 void launch_max_abs_f32(const float* p, int64_t ld, int64_t rows, int cols, unsigned* maxbits, cudaStream_t st);

@@ -127,6 +127,18 @@ class MaxClassifier(Transformer):
 
 
 # ------------------------------------------------------------------------------------------
+class _HostView:
+    """Array-interface holder for a block of the model's pinned host mirror; numpy keeps it (and through it the mapper that
+    owns the memory) alive as the array's base."""
+
+    def __init__(self, owner, ptr: int, shape, order: str):
+        self.owner = owner
+        strides = None
+        if order == "F" and len(shape) == 2:
+            strides = (8, 8 * shape[0])
+        self.__array_interface__ = {"version": 3, "shape": tuple(shape), "typestr": "<f8", "data": (ptr, True), "strides": strides}
+
+
 class BlockLinearMapper(Transformer):
     """Fitted model: xs (per-block (rows_j x k) matrices), blockSize, optional intercept and feature means."""
 
@@ -156,15 +168,20 @@ class BlockLinearMapper(Transformer):
         return cls(ctx, h.value)
 
     # ---- model state (fp64, Breeze layouts) ----
+    # The fit mirrors every finished block into pinned host memory while it is still running (ks_model_host_view); the
+    # arrays below are read-only views of that mirror (no copy) and keep this mapper alive through their base object.
+    def _view(self, ptr: int, shape, order: str) -> np.ndarray:
+        holder = _HostView(self, ptr, shape, order)
+        return np.asarray(holder)
+
     def _block(self, j: int):
         rows = C.c_int64(0)
         check(self.ctx.handle, lib().ks_model_block_rows(self.ctx.handle, self.handle, j, C.byref(rows)))
-        W = np.empty((rows.value, self.k), dtype=np.float64, order="F")
-        mean = np.empty(rows.value, dtype=np.float64)
-        has = C.c_int32(0)
-        check(self.ctx.handle, lib().ks_model_get_block(self.ctx.handle, self.handle, j, W.ctypes.data_as(C.c_void_p),
-                                                         mean.ctypes.data_as(C.c_void_p), C.byref(has)))
-        return W, (mean if has.value else None)
+        wp, mp = C.c_void_p(0), C.c_void_p(0)
+        check(self.ctx.handle, lib().ks_model_host_view(self.ctx.handle, self.handle, j, C.byref(wp), C.byref(mp), None))
+        W = self._view(wp.value, (rows.value, self.k), "F")
+        mean = self._view(mp.value, (rows.value,), "C") if mp.value else None
+        return W, mean
 
     @property
     def xs(self) -> List[np.ndarray]:
@@ -179,10 +196,9 @@ class BlockLinearMapper(Transformer):
 
     @property
     def b_opt(self) -> Optional[np.ndarray]:
-        b = np.empty(self.k, dtype=np.float64)
-        has = C.c_int32(0)
-        check(self.ctx.handle, lib().ks_model_get_intercept(self.ctx.handle, self.handle, b.ctypes.data_as(C.c_void_p), C.byref(has)))
-        return b if has.value else None
+        bp = C.c_void_p(0)
+        check(self.ctx.handle, lib().ks_model_host_view(self.ctx.handle, self.handle, 0, None, None, C.byref(bp)))
+        return self._view(bp.value, (self.k,), "C") if bp.value else None
 
     # ---- apply ----
     def apply(self, data):
@@ -243,12 +259,13 @@ class LinearMapper(BlockLinearMapper):
 
 class BlockLeastSquaresEstimator(LabelEstimator, WeightedNode):
     def __init__(self, block_size: int, num_iter: int, lam: float = 0.0, num_features_opt: Optional[int] = None,
-                 ctx: Optional[Context] = None, precision: str = "tf32"):
-        """precision: "tf32" (default) or "f16" -- fp16 operands for the three big GEMMs when the features are generated
-        cosine features (KS_PRECISION_F16 in include/keystone_b200.h); same mantissa, twice the tensor-core rate."""
+                 ctx: Optional[Context] = None, precision: str = "default"):
+        """precision (KS_PRECISION_* of include/keystone_b200.h): "default" = the context's setting (initially the parity mode),
+        "f16x2" / "parity" = split operands (hi + lo per MMA operand, >= 21 bits), "f16" = fp16 operands for the three big
+        GEMMs on generated cosine features (10-bit mantissa, the fastest), "tf32" = one tf32 MMA per product."""
         self.block_size, self.num_iter, self.lam, self.num_features_opt, self.ctx = block_size, num_iter, lam, num_features_opt, ctx
-        if precision not in ("tf32", "f16", "f16x2"):
-            raise ValueError("precision must be 'tf32', 'f16' or 'f16x2' (experimental split-operand mode)")
+        if precision not in _capi.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_capi.PRECISIONS)}")
         self.precision = precision
         self.weight = 3 * num_iter + 1  # BlockLinearMapper.scala:204
 
@@ -259,10 +276,7 @@ class BlockLeastSquaresEstimator(LabelEstimator, WeightedNode):
         f, x, rfs, n = feature_source_args(ds)
         h = C.c_int64(0)
         check(ctx.handle, lib().ks_blockls_fit(ctx.handle, f, x, rfs, n, lb.handle, self.block_size, self.num_iter, self.lam,
-                                                self.num_features_opt or 0,
-                                                {"tf32": _capi.KS_PRECISION_TF32, "f16": _capi.KS_PRECISION_F16,
-                                                 "f16x2": _capi.KS_PRECISION_F16X2}[self.precision],
-                                                C.byref(h)))
+                                                self.num_features_opt or 0, _capi.PRECISIONS[self.precision], C.byref(h)))
         return BlockLinearMapper(ctx, h.value)
 
     def cost(self, n: int, d: int, k: int, sparsity: float, num_machines: int, cpu_weight: float, mem_weight: float,
@@ -276,9 +290,12 @@ class BlockLeastSquaresEstimator(LabelEstimator, WeightedNode):
 
 class BlockWeightedLeastSquaresEstimator(LabelEstimator, WeightedNode):
     def __init__(self, block_size: int, num_iter: int, lam: float, mixture_weight: float,
-                 num_features_opt: Optional[int] = None, ctx: Optional[Context] = None):
+                 num_features_opt: Optional[int] = None, ctx: Optional[Context] = None, precision: str = "default"):
         self.block_size, self.num_iter, self.lam, self.mixture_weight = block_size, num_iter, lam, mixture_weight
         self.num_features_opt, self.ctx = num_features_opt, ctx
+        if precision not in _capi.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_capi.PRECISIONS)}")
+        self.precision = precision
         self.weight = 3 * num_iter + 1  # BlockWeightedLeastSquares.scala:44
 
     def fit(self, data, labels) -> BlockLinearMapper:
@@ -288,11 +305,15 @@ class BlockWeightedLeastSquaresEstimator(LabelEstimator, WeightedNode):
         f, x, rfs, n = feature_source_args(ds)
         h = C.c_int64(0)
         check(ctx.handle, lib().ks_blockwls_fit(ctx.handle, f, x, rfs, n, lb.handle, self.block_size, self.num_iter, self.lam,
-                                                 self.mixture_weight, self.num_features_opt or 0, _capi.KS_PRECISION_TF32, C.byref(h)))
+                                                 self.mixture_weight, self.num_features_opt or 0, _capi.PRECISIONS[self.precision],
+                                                 C.byref(h)))
         return BlockLinearMapper(ctx, h.value)
 
 
 class LinearMapEstimator(LabelEstimator):
+    """Exact centred normal equations; computes in the context's precision (``ctx.set_option("precision", ...)``, initially the
+    split-operand parity mode)."""
+
     def __init__(self, lam: Optional[float] = None, ctx: Optional[Context] = None):
         self.lam, self.ctx = lam, ctx
 

@@ -1,11 +1,14 @@
 """GPU parity tests (run with -m gpu on the B200 box): every call goes through the C ABI and is compared with the
 fp64 CPU oracle on the same seeded inputs.
 
-Tolerances (stated once, used everywhere below).  The MMA operands are tf32 (10-bit mantissa, round-to-nearest)
-with fp32 accumulation and the reduced system is solved in fp64:
-  * Gram / A^T B entries: |err| <= 2e-3 * sqrt(N) * rms(a) * rms(b)   (random-walk bound of the input rounding)
-  * cosine features: max abs err <= 5e-3 (the reference's own tolerance is 1e-2, CosineRandomFeaturesSuite.scala:33-35)
-  * fitted weights: rel-Frobenius(W) <= 5e-3 on well-conditioned problems; predictions max-abs <= 5e-3 * max|y|
+Tolerances (stated once, used everywhere below).  The reference computes in fp64 and its suites assert 1e-8 .. 1e-4
+(LinearMapperSuite.scala:28-33, BlockWeightedLeastSquaresSuite.scala:115-140, BlockLinearMapperSuite.scala:40-52).
+  * parity mode (KS_PRECISION_F16X2, the library default: every MMA operand carried as hi + lo, fp32 accumulation in the
+    tensor core, reduced systems assembled and solved in fp64):
+      fitted weights rel-Frobenius(W) <= W_TOL = 5e-5; predictions max-abs <= 1e-4 * max|y|; cosine features <= 2e-5
+  * fast modes (one 10-bit-mantissa MMA per product: "f16" on generated features, "tf32"):
+      fitted weights rel-Frobenius(W) <= W_TOL_FAST = 1.5e-3 (measured 7e-4 at N = 32768); predictions max-abs <= 5e-3
+  * Gram kernel alone, operands exactly representable: 5e-5 * sum|a||b| (the tensor core's fp32 accumulation truncates)
 """
 import json
 import os
@@ -18,7 +21,8 @@ from oracle import keystone_oracle as ko
 
 pytestmark = pytest.mark.gpu
 
-W_TOL = 5e-3
+W_TOL = 5e-5        # parity mode
+W_TOL_FAST = 1.5e-3  # 10-bit operand modes
 
 
 def round_tf32(x):
@@ -82,20 +86,29 @@ def test_cosine_random_features(ctx):
     out = rf(ctx.matrix(X)).to_numpy()
     ref = ko.cosine_random_features(X, W, b)
     assert out.shape == ref.shape
-    assert np.abs(out - ref).max() < 5e-3, np.abs(out - ref).max()
+    assert np.abs(out - ref).max() < 2e-5, np.abs(out - ref).max()     # reference's own tolerance: 1e-2 (CosineRandomFeaturesSuite.scala:33-35)
     one = rf(X[3])
-    assert np.abs(one - ref[3]).max() < 5e-3
+    assert np.abs(one - ref[3]).max() < 2e-5
+    ctx.set_option("precision", 0)                                       # one tf32 MMA per product
+    try:
+        assert np.abs(rf(ctx.matrix(X)).to_numpy() - ref).max() < 5e-3
+    finally:
+        ctx.set_option("precision", 2)
 
 
-def _fit_compare(ctx, F, Y, bs, iters, lam, tol=W_TOL):
-    model = ks.BlockLeastSquaresEstimator(bs, iters, lam).fit(ctx.matrix(F), ctx.matrix(Y))
+def _fit_compare(ctx, F, Y, bs, iters, lam, tol=W_TOL, precision="default"):
+    model = ks.BlockLeastSquaresEstimator(bs, iters, lam, precision=precision).fit(ctx.matrix(F), ctx.matrix(Y))
+    assert ctx.last_fit_stats()["mma"] == {"default": "tf32x2", "tf32": "tf32x1", "f16": "tf32x1"}[precision]
+    # the device stores fp32 inputs: the oracle sees the same values
+    F = np.asarray(F, dtype=np.float32).astype(np.float64)
+    Y = np.asarray(Y, dtype=np.float32).astype(np.float64)
     xs, b0, mus = ko.block_ls_fit(F, Y, bs, iters, lam)
     Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
     rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
     assert [x.shape for x in model.xs] == [x.shape for x in xs]
     assert rel < tol, rel
-    assert np.abs(model.b_opt - b0).max() < 1e-5
-    assert np.abs(np.concatenate(model.feature_means) - np.concatenate(mus)).max() < 1e-4
+    assert np.abs(model.b_opt - b0).max() < 1e-6
+    assert np.abs(np.concatenate(model.feature_means) - np.concatenate(mus)).max() < 1e-6 * max(1.0, np.abs(np.concatenate(mus)).max())
     return model, xs, b0, mus, rel
 
 
@@ -105,10 +118,12 @@ def test_blockls_fit_materialized(ctx):
     F = rng.standard_normal((n, d)) + 0.5 * rng.standard_normal(d)   # non-zero column means
     Y = ko.class_label_indicators(rng.integers(0, k, n), k)
     model, xs, b0, mus, rel = _fit_compare(ctx, F, Y, 256, 1, 1.0)
+    F32 = F.astype(np.float32).astype(np.float64)
     pred = model(ctx.matrix(F)).to_numpy()
-    ref = ko.block_linear_apply(F, xs, 256, b0, mus)
-    assert np.abs(pred - ref).max() < 5e-3, np.abs(pred - ref).max()
-    assert (model.apply_argmax(ctx.matrix(F)) == np.argmax(ref, 1)).mean() > 0.995
+    ref = ko.block_linear_apply(F32, xs, 256, b0, mus)
+    assert np.abs(pred - ref).max() < 1e-4, np.abs(pred - ref).max()
+    assert (model.apply_argmax(ctx.matrix(F)) == np.argmax(ref, 1)).mean() > 0.9995
+    _fit_compare(ctx, F, Y, 256, 1, 1.0, tol=W_TOL_FAST, precision="tf32")
 
 
 def test_blockls_fit_multi_pass_and_ragged(ctx):
@@ -118,6 +133,7 @@ def test_blockls_fit_multi_pass_and_ragged(ctx):
     Y = rng.standard_normal((n, k))
     _fit_compare(ctx, F, Y, 128, 3, 0.5)        # blocks 128,128,44 ; 3 sweeps
     _fit_compare(ctx, F, Y, 300, 1, 0.0)        # nb = 1, lambda = 0 : LinearMapEstimator case
+    _fit_compare(ctx, F, Y, 128, 3, 0.5, tol=W_TOL_FAST, precision="tf32")
 
 
 def test_blockls_fit_reference_fixture(ctx, golden_dir):
@@ -129,6 +145,24 @@ def test_blockls_fit_reference_fixture(ctx, golden_dir):
     W = np.concatenate(model.xs, 0)
     assert np.linalg.norm(W - np.array(g["W"])) / np.linalg.norm(g["W"]) < W_TOL
     assert np.abs(model.b_opt - np.array(g["intercept"])).max() < 1e-6
+
+
+@pytest.mark.parametrize("bs,iters", [(4, 1), (5, 2), (12, 3)])
+def test_blockls_pinned_by_weighted_solver_with_zero_mixture_weight(ctx, golden_dir, bs, iters):
+    """The identity that pins the BlockLS arithmetic to in-repo reference code (tests/test_oracle_golden.py, same name):
+    trainWithL2 with mixtureWeight = 0 (K/nodes/learning/BlockWeightedLeastSquares.scala:216-273) == BlockLS with lambda * N,
+    here through the two GPU solvers: ks_blockwls_fit(w = 0) vs ks_blockls_fit(lambda N)."""
+    A = np.loadtxt(os.path.join(golden_dir, "aMat.csv"), delimiter=",")
+    B = np.loadtxt(os.path.join(golden_dir, "bMat.csv"), delimiter=",")
+    n, lam = A.shape[0], 0.1
+    mw = ks.BlockWeightedLeastSquaresEstimator(bs, iters, lam, 0.0).fit(ctx.matrix(A), ctx.matrix(B))
+    ml = ks.BlockLeastSquaresEstimator(bs, iters, lam * n).fit(ctx.matrix(A), ctx.matrix(B))
+    Ww, Wl = np.concatenate(mw.xs, 0), np.concatenate(ml.xs, 0)
+    assert np.linalg.norm(Ww - Wl) / np.linalg.norm(Wl) < 2 * W_TOL
+    folded = ml.b_opt - sum(mu @ x for mu, x in zip(ml.feature_means, ml.xs))
+    assert np.abs(mw.b_opt - folded).max() < 1e-4
+    xs, ybar, mus = ko.block_ls_fit(A, B, bs, iters, lam * n)          # and both against the oracle
+    assert np.linalg.norm(Wl - np.concatenate(xs, 0)) / np.linalg.norm(np.concatenate(xs, 0)) < W_TOL
 
 
 def test_blockls_fit_cosine_features_regenerated(ctx):
@@ -143,6 +177,7 @@ def test_blockls_fit_cosine_features_regenerated(ctx):
     feats = ks.Pipeline.gather(rfs).andThen(ks.VectorCombiner())(x)
     y = ctx.labels_from_classes(cls, k)
     model = ks.BlockLeastSquaresEstimator(n_out, 1, 2.0).fit(feats, y)
+    assert ctx.last_fit_stats()["mma"] == "f16x2"
     Xd = X.astype(np.float32).astype(np.float64)
     F = np.concatenate([ko.cosine_random_features(Xd, W, b) for W, b in params], 1)
     Y = ko.class_label_indicators(cls, k)
@@ -152,10 +187,15 @@ def test_blockls_fit_cosine_features_regenerated(ctx):
     assert rel < W_TOL, rel
     pred = model(feats).to_numpy()
     ref = ko.block_linear_apply(F, xs, n_out, b0, mus)
-    assert np.abs(pred - ref).max() < 5e-3
+    assert np.abs(pred - ref).max() < 1e-4
     # computeCost (no centring; BlockLinearMapper.scala:142-187)
     cost = model.compute_cost(feats, y, 2.0)
-    assert abs(cost - ko.compute_cost(F, Y, 2.0, xs, n_out, b0)) / cost < 2e-3
+    assert abs(cost - ko.compute_cost(F, Y, 2.0, xs, n_out, b0)) / cost < 1e-5
+    # the tf32 one-MMA mode on the same problem
+    m32 = ks.BlockLeastSquaresEstimator(n_out, 1, 2.0, precision="tf32").fit(feats, y)
+    assert ctx.last_fit_stats()["mma"] == "tf32x1"
+    W32 = np.concatenate(m32.xs, 0)
+    assert np.linalg.norm(W32 - Wr) / np.linalg.norm(Wr) < W_TOL_FAST
     # block size different from the feature-map width (blocks straddle maps)
     m2 = ks.BlockLeastSquaresEstimator(200, 1, 2.0).fit(feats, y)
     xs2, _, _ = ko.block_ls_fit(F, Y, 200, 1, 2.0)
@@ -167,7 +207,7 @@ def test_blockls_fit_cosine_features_regenerated(ctx):
 def ctx16(ctx):
     ctx.set_option("precision", 1)
     yield ctx
-    ctx.set_option("precision", 0)
+    ctx.set_option("precision", 2)
 
 
 @pytest.mark.parametrize("n,m,kc", [(777, 200, 70), (64, 64, 64), (5000, 640, 257), (130, 1030, 5)])
@@ -215,7 +255,7 @@ def test_blockls_fit_f16_matches_oracle(ctx, bs, iters):
     xs, b0, mus = ko.block_ls_fit(F, Y, bs, iters, 2.0)
     Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
     rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
-    assert rel < W_TOL, rel
+    assert rel < W_TOL_FAST, rel
     # the means are those of the generated features (tf32 projection, 10-bit slab): measured 1.2e-4 at N = 4000 in both modes,
     # shrinking like 1/sqrt(N) (4.2e-5 at N = 32768, tools/accuracy_probe.py)
     assert np.abs(np.concatenate(model.feature_means) - np.concatenate(mus)).max() < 5e-4
@@ -237,7 +277,7 @@ def test_blockls_fit_f16_label_scale_invariance(ctx):
         xs, b0, mus = ko.block_ls_fit(F, Y.astype(np.float32).astype(np.float64), 256, 1, 1.0)
         Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
         rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
-        assert rel < W_TOL, (scale, rel)
+        assert rel < W_TOL_FAST, (scale, rel)
 
 
 def test_blockls_fit_f16_input_scale_invariance(ctx):
@@ -260,18 +300,13 @@ def test_blockls_fit_f16_input_scale_invariance(ctx):
         xs, _, _ = ko.block_ls_fit(F, Y, n_out, 1, 1.0)
         Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
         rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
-        assert rel < W_TOL, (sx, rel)
+        assert rel < W_TOL_FAST, (sx, rel)
 
 
-EXPERIMENTAL = pytest.mark.skipif(os.environ.get("KS_TEST_EXPERIMENTAL") != "1",
-                                  reason="split-operand mode: written without GPU access, enable with KS_TEST_EXPERIMENTAL=1")
-
-
-@EXPERIMENTAL
 @pytest.mark.parametrize("bs,iters", [(256, 1), (200, 2)])
 def test_blockls_fit_f16x2_split_operands(ctx, bs, iters):
-    """KS_PRECISION_F16X2: same problem as the fp16 test, tolerance 100x tighter (model: 2e-7, tests/test_precision_model.py;
-    the tensor core's truncating fp32 accumulation is expected to leave ~1e-6)."""
+    """KS_PRECISION_F16X2 (parity mode): same problem as the fp16 test, tolerance 30x tighter (model of the device arithmetic:
+    2e-7, tests/test_precision_model.py; the tensor core's truncating fp32 accumulation leaves ~1e-6)."""
     n, k = 4000, 10
     feats, F, cls = _cosine_problem(ctx, 4, n, 44, 256, k, 3)
     y = ctx.labels_from_classes(cls, k)
@@ -281,8 +316,24 @@ def test_blockls_fit_f16x2_split_operands(ctx, bs, iters):
     xs, b0, mus = ko.block_ls_fit(F, Y, bs, iters, 2.0)
     Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
     rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
-    assert rel < 5e-5, rel
+    assert rel < W_TOL, rel
     assert np.abs(np.concatenate(model.feature_means) - np.concatenate(mus)).max() < 5e-6
+
+
+def test_blockls_parity_mode_scale_invariance(ctx):
+    """The split fp16 operands carry device-chosen power-of-two scales (labels, inputs): magnitudes far outside fp16's range
+    must not change the relative accuracy of the parity mode."""
+    n, k = 3000, 4
+    feats, F, cls = _cosine_problem(ctx, 9, n, 30, 256, k, 2)
+    rng = np.random.default_rng(10)
+    Y0 = rng.standard_normal((n, k))
+    for scale in (1e-6, 1.0, 1e5):
+        Y = Y0 * scale
+        model = ks.BlockLeastSquaresEstimator(256, 1, 1.0).fit(feats, ctx.matrix(Y))
+        xs, b0, mus = ko.block_ls_fit(F, Y.astype(np.float32).astype(np.float64), 256, 1, 1.0)
+        Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
+        rel = np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)
+        assert rel < W_TOL, (scale, rel)
 
 
 def test_blockls_f16_falls_back_to_tf32_for_materialized_features(ctx):
@@ -293,17 +344,19 @@ def test_blockls_f16_falls_back_to_tf32_for_materialized_features(ctx):
     assert ctx.last_fit_stats()["mma"] == "tf32x1"
     xs, _, _ = ko.block_ls_fit(F.astype(np.float32).astype(np.float64), Y, 128, 1, 1.0)
     Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
-    assert np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr) < W_TOL
+    assert np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr) < W_TOL_FAST
 
 
 def test_linear_map_estimator_known_answer(ctx):
-    """T/nodes/learning/LinearMapperSuite.scala:13-36 through the GPU path."""
+    """T/nodes/learning/LinearMapperSuite.scala:13-36 through the GPU path.  The reference asserts 1e-8 in fp64; the device
+    stores its inputs in fp32 (2^-24 relative), so the recoverable accuracy of the planted model is ~1e-6."""
     rng = np.random.default_rng(42)
-    A = rng.standard_normal((128, 5))
+    A = rng.standard_normal((128, 5)).astype(np.float32).astype(np.float64)   # exactly representable inputs
     x = np.array([5.0, 4.0, 3.0, 2.0, -1.0])[:, None]
     mapper = ks.LinearMapEstimator().fit(ctx.matrix(A), ctx.matrix(A @ x))
-    assert np.abs(mapper.x - x).max() < 5e-3
-    assert abs(mapper(np.array([2.0, -3.0, 2.0, 3.0, 5.0]))[0] - 5.0) < 2e-2
+    assert ctx.last_fit_stats()["mma"] == "tf32x2"
+    assert np.abs(mapper.x - x).max() < 1e-5, np.abs(mapper.x - x).max()
+    assert abs(mapper(np.array([2.0, -3.0, 2.0, 3.0, 5.0]))[0] - 5.0) < 1e-4
 
 
 def test_block_linear_mapper_equals_linear_mapper(ctx):
@@ -318,7 +371,9 @@ def test_block_linear_mapper_equals_linear_mapper(ctx):
     o1, o2 = blm(x).to_numpy(), lm(x).to_numpy()
     ref = X @ mat + b
     scale = np.abs(ref).max()
-    assert np.abs(o1 - ref).max() < 2e-3 * scale and np.abs(o2 - ref).max() < 2e-3 * scale
+    # the reference asserts 1e-4 absolute on this shape (BlockLinearMapperSuite.scala:40-52); fp32 inputs: compare against them
+    ref = X.astype(np.float32).astype(np.float64) @ mat + b
+    assert np.abs(o1 - ref).max() < 1e-5 * scale and np.abs(o2 - ref).max() < 1e-5 * scale
     seen = []
     blm.applyAndEvaluate(x, lambda part: seen.append(part.to_numpy()))
     assert len(seen) == 5 and np.abs(seen[-1] - o1).max() < 1e-5 * scale
@@ -334,8 +389,9 @@ def test_error_paths(ctx):
 
 
 # ---- BlockWeightedLeastSquaresEstimator on the device (T/nodes/learning/BlockWeightedLeastSquaresSuite.scala) ----
-def _bwls_compare(ctx, A, B, bs, iters, lam=0.1, w=0.3, tol=W_TOL):
-    model = ks.BlockWeightedLeastSquaresEstimator(bs, iters, lam, w).fit(ctx.matrix(A), ctx.matrix(B))
+def _bwls_compare(ctx, A, B, bs, iters, lam=0.1, w=0.3, tol=W_TOL, precision="default"):
+    model = ks.BlockWeightedLeastSquaresEstimator(bs, iters, lam, w, precision=precision).fit(ctx.matrix(A), ctx.matrix(B))
+    assert ctx.last_fit_stats()["mma"] == ("tf32x2" if precision == "default" else "tf32x1")
     xs, fb = ko.bwls_fit(A, B, bs, iters, lam, w)
     Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
     assert [x.shape for x in model.xs] == [x.shape for x in xs]
@@ -353,13 +409,14 @@ def test_bwls_reference_fixture(ctx, golden_dir):
     model, Wg, Wr, fb = _bwls_compare(ctx, A, B, 4, 10)
     g = ko.compute_gradient(A, B, 0.1, 0.3, Wg, model.b_opt)
     g_ref = ko.compute_gradient(A, B, 0.1, 0.3, Wr, fb)
-    # the reference bound is 1e-2 and the fp64 oracle sits at 8.1e-3; tf32 operands may add a few 1e-4
-    assert np.linalg.norm(g) < np.linalg.norm(g_ref) + 2e-3
+    # the reference bound is 1e-2 and the fp64 oracle sits at 8.1e-3
+    assert np.linalg.norm(g) < np.linalg.norm(g_ref) + 1e-4
+    _bwls_compare(ctx, A, B, 4, 10, tol=5e-3, precision="tf32")
     model5, W5, _, _ = _bwls_compare(ctx, A, B, 5, 10)
     assert np.linalg.norm(ko.compute_gradient(A, B, 0.1, 0.3, W5, model5.b_opt)) < 1e-1
     # predictions through BlockLinearMapper.apply (no scalers, intercept = finalB)
     pred = model(ctx.matrix(A)).to_numpy()
-    assert np.abs(pred - (A @ Wr + fb)).max() < 5e-3
+    assert np.abs(pred - (A @ Wr + fb)).max() < 1e-4
 
 
 def test_bwls_group_by_classes_and_degenerate_cases(ctx, golden_dir):
@@ -394,10 +451,10 @@ def test_bwls_larger_problem_cosine_features(ctx):
     F = np.concatenate([ko.cosine_random_features(Xd, W, b) for W, b in params], 1)
     xs, fb = ko.bwls_fit(F, ko.class_label_indicators(cls, k), n_out, 2, 0.01, 0.25)
     Wg, Wr = np.concatenate(model.xs, 0), np.concatenate(xs, 0)
-    assert np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr) < 2e-2    # lambda = 0.01 on n_c as small as 150: conditioning ~1e3
+    assert np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr) < 5e-4    # lambda = 0.01 on n_c as small as 150: conditioning ~1e3
     pred = model(feats).to_numpy()
     ref = F @ Wr + fb
-    assert np.abs(pred - ref).max() < 2e-2
+    assert np.abs(pred - ref).max() < 5e-4
 
 
 @pytest.mark.parametrize("n,k", [(4096, 1000), (300, 37), (128, 8), (5, 3), (1000, 1)])
@@ -420,7 +477,6 @@ def test_chol_solve_kernel(ctx, n, k):
     print(f"chol_solve n={n} k={k}: kernel {out[0][1]:.3f} ms, cusolver potrs {out[1][1]:.3f} ms")
 
 
-@EXPERIMENTAL
 def test_device_confusion_matrix_matches_oracle(ctx):
     """ks_model_confusion_matrix: apply -> MaxClassifier -> counts on the device vs the oracle's confusion matrix of the same
     predictions (integer counts: exact)."""
