@@ -111,6 +111,18 @@ KS_API int32_t ks_cosine_rf_create(int64_t ctx, const double* W_colmajor, const 
 KS_API int32_t ks_cosine_rf_apply(int64_t ctx, int64_t rf, int64_t x_in, int64_t* out_features);
 KS_API int32_t ks_cosine_rf_destroy(int64_t ctx, int64_t rf);
 
+/* RandomSignNode(signs) andThen PaddedFFT() [andThen LinearRectifier(maxVal, alpha)] as one dense feature map
+ * (K/nodes/stats/RandomSignNode.scala:11-24, PaddedFFT.scala:13-21, LinearRectifier.scala:12-17; the featurizer of
+ * K/pipelines/images/mnist/MnistRandomFFT.scala:40-44): out[f] = max(maxVal, sum_n x[n] signs[n] cos(2 pi f n / P) - alpha),
+ * f < P / 2, P = nextPositivePowerOfTwo(n_in).  signs may be NULL (all +1); rectify = 0: no rectifier.  The handle is a feature-map
+ * handle like CosineRandomFeatures': ks_cosine_rf_apply materialises it, the fits regenerate it block by block, and
+ * ks_cosine_rf_destroy releases it.  Maps gathered into one feature source must be of one kind. */
+KS_API int32_t ks_padded_fft_create(int64_t ctx, const double* signs_or_null, int64_t n_in, int32_t rectify, double max_val,
+                                    double alpha, int64_t* out_rf);
+/* Elementwise nodes on a materialised batch: op 0: out = x .* colvec (RandomSignNode.apply), op 1: out = max(a, x - b)
+ * (LinearRectifier.apply); returns a new matrix. */
+KS_API int32_t ks_matrix_map(int64_t ctx, int64_t m, int32_t op, const double* colvec_or_null, double a, double b, int64_t* out_m);
+
 /* ---- feature source shared by fit / apply -------------------------------------------------
  * Either `features` (a materialised N x D matrix; VectorSplitter blocks are column ranges of it,
  * K/nodes/util/VectorSplitter.scala:15-25) or `x_in` + `rfs[n_rfs]` (the gather of

@@ -14,11 +14,14 @@ from .nodes import (  # noqa: F401
     CosineRandomFeatures,
     LinearMapEstimator,
     LinearMapper,
+    LinearRectifier,
     MaxClassifier,
+    PaddedFFT,
+    RandomSignNode,
     VectorCombiner,
     VectorSplitter,
 )
-from .evaluation import (  # noqa: F401  (experimental: the row after the solver)
+from .evaluation import (  # noqa: F401
     BinaryClassificationMetrics,
     MulticlassClassifierEvaluator,
     MulticlassMetrics,

@@ -427,6 +427,44 @@ void launch_w_to_operand(const double* W_colmajor, int64_t n_out, int64_t n_in, 
   w_to_operand_kernel<<<grid_for(n_out * ld, 256), 256, 0, st>>>(W_colmajor, n_out, n_in, dst, ld, round);
 }
 
+// PaddedFFT (K/nodes/stats/PaddedFFT.scala:13-21): Re(FFT(pad(x))) [f] = sum_n x[n] cos(2 pi f n / P); with RandomSignNode
+// (K/nodes/stats/RandomSignNode.scala:11-16) in front, x[n] carries the sign s[n]: a fixed (P/2) x n_in matrix
+__global__ void fft_real_matrix_kernel(const double* __restrict__ signs, int64_t n_in, int64_t P, float* __restrict__ dst,
+                                       float* __restrict__ dst_full, int64_t ld) {
+  const int64_t total = (P / 2) * ld;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t f = i / ld, n = i - f * ld;
+    float v = 0.f;
+    if (n < n_in) {
+      const int64_t q = (f * n) % P;                       // exact phase reduction in integers
+      v = static_cast<float>((signs ? signs[n] : 1.0) * cospi(2.0 * static_cast<double>(q) / static_cast<double>(P)));
+    }
+    dst[i] = round_tf32_aux(v);
+    dst_full[i] = v;
+  }
+}
+void launch_fft_real_matrix(const double* signs, int64_t n_in, int64_t P, float* dst, float* dst_full, int64_t ld, cudaStream_t st) {
+  fft_real_matrix_kernel<<<grid_for((P / 2) * ld, 256), 256, 0, st>>>(signs, n_in, P, dst, dst_full, ld);
+}
+
+__global__ void matrix_map_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t ld, int64_t rows, int cols, int op,
+                                  const float* __restrict__ colvec, float a, float b) {
+  const int64_t total = rows * ld;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % ld);
+    float v = 0.f;
+    if (c < cols) v = op == 0 ? src[i] * colvec[c] : fmaxf(a, src[i] - b);
+    dst[i] = v;
+  }
+}
+void launch_matrix_map(const float* src, float* dst, int64_t ld, int64_t rows, int cols, int op, const float* colvec, float a, float b,
+                       cudaStream_t st) {
+  if (rows == 0) return;
+  matrix_map_kernel<<<grid_for(rows * ld, 256), 256, 0, st>>>(src, dst, ld, rows, cols, op, colvec, a, b);
+}
+
 // ------------------------------------------------------------------ MaxClassifier (K/nodes/util/MaxClassifier.scala:9-11)
 __global__ void argmax_rows_kernel(const float* __restrict__ Y, int64_t ld, int64_t rows, int k, int32_t* __restrict__ out) {
   const int lane = threadIdx.x & 31;

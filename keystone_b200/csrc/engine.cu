@@ -460,9 +460,13 @@ void make_feat_src(Ctx& c, int64_t features, int64_t x_in, const int64_t* rfs, i
   int64_t total = 0;
   for (int i = 0; i < n_rfs; ++i) {
     CosRF& r = c.rf(rfs[i]);
-    if (r.n_in != out.d_in) throw KsError{KS_ERR_INVALID, "CosineRandomFeatures input dimension does not match x_in"};
+    if (r.n_in != out.d_in) throw KsError{KS_ERR_INVALID, "feature map input dimension does not match x_in"};
+    if (r.kind != c.rf(rfs[0]).kind || r.rect_floor != c.rf(rfs[0]).rect_floor)
+      throw KsError{KS_ERR_INVALID, "gathered feature maps must be of one kind (all cosine, or all rectified with the same maxVal)"};
     total += r.n_out;
   }
+  out.kind = c.rf(rfs[0]).kind;
+  out.rect_floor = c.rf(rfs[0]).rect_floor;
   out.D = total;
   CosRF& r0 = c.rf(rfs[0]);
   out.ldw = r0.ld;
@@ -549,7 +553,8 @@ void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* s
   k.p.M = static_cast<int>(rows);
   k.p.N = static_cast<int>(cols);
   k.p.K = static_cast<int>(kdepth);
-  k.p.flags = round_out ? 0 : KM_FLAG_NO_ROUND;
+  k.p.flags = (round_out ? 0 : KM_FLAG_NO_ROUND) | (src.kind == 1 ? KM_FLAG_RECT : 0);
+  k.p.rect_floor = src.rect_floor;
   k.epi = EPI_COS;
   k.pair = 0;
   // the projection kernel is persistent (one CTA per SM for its whole duration); on the look-ahead stream leave a few SMs
@@ -790,14 +795,16 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   //   significant bits) and every product keeps hi*hi + hi*lo + lo*hi, using the same kernels three times (the projection
   //   once, on operands concatenated along K).  Generated features: fp16 pairs (kind::f16); materialised features: tf32
   //   pairs (kind::tf32, no range limits).
+  // fp16 slabs only for cosine features (|value| <= 2); rectified linear features have the scale of their input
   const bool x2 = precision == KS_PRECISION_F16X2 && (src.F || src.proj_x2);
-  const bool f16 = !src.F && (precision == KS_PRECISION_F16 || x2);
+  const bool f16 = !src.F && src.kind == 0 && (precision == KS_PRECISION_F16 || x2);
   const size_t es = f16 ? 2 : 4;  // bytes per slab / operand element
   const int64_t x2_chunk = 2048;  // short accumulation chains: the tensor core's fp32 accumulate truncates (~2^-25 per MMA step)
   const int NBUF = 3;
   DevBuf r_f32, r_op, cm, rhs, rsum, bop, cbias, samp, fsum, scales, sf32, r_lo, bop_lo;
   std::unique_ptr<DevBuf[]> slab_lo;
   std::unique_ptr<DevBuf[]> slab(new DevBuf[NBUF]), gbuf(new DevBuf[NBUF]), Hbuf(new DevBuf[NBUF]), ssum(new DevBuf[NBUF]);
+  std::unique_ptr<DevBuf[]> Dbuf(new DevBuf[NBUF]);  // inverted diagonal tiles of the factors (operand of the library's own solve)
   r_f32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * kpad));
   r_op.alloc(f16 ? r_f32.bytes / 2 : r_f32.bytes);
   if (x2) r_lo.alloc(r_op.bytes);
@@ -825,6 +832,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     gbuf[i].alloc(sizeof(float) * g_elems * (x2 ? 2 : 1));  // x2: S_hi^T S_hi (upper tiles) followed by the full S_hi^T S_lo
     ssum[i].alloc(sizeof(float) * lds);
     if (!cache_factors) Hbuf[i].alloc(sizeof(double) * static_cast<size_t>(bmax) * bmax);
+    if (!cache_factors && c.custom_solve) Dbuf[i].alloc(sizeof(double) * chol_solve_dinv_doubles(bmax));
   }
   cm.alloc(sizeof(float) * c_elems);
   rhs.alloc(sizeof(double) * static_cast<size_t>(bmax) * k);
@@ -838,7 +846,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   }
   cbias.alloc(sizeof(float) * kpad);
   samp.alloc(sizeof(double) * (bmax + 1));  // sample column sums + sample row count (generated features)
-  std::vector<std::unique_ptr<DevBuf>> factors(nb), deltas(nb), shifts(nb);
+  std::vector<std::unique_ptr<DevBuf>> factors(nb), dinvs(nb), deltas(nb), shifts(nb);
 
   // ---- exact column means for materialised features (one pass over F for all blocks)
   if (src.F) {
@@ -871,7 +879,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   }
   int info_slot = 0;
   double flops = 0;
-  const bool shard_solve = !c.custom_solve && c.world > 1 && c.shard_solve && k >= c.world;
+  const bool shard_solve = c.world > 1 && c.shard_solve && k >= c.world;
 
   // ---------------- proj(t): shift estimate (first sweep) + slab of step t, on ST
   auto do_proj = [&](int t) {
@@ -915,7 +923,9 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       c.launches += 1;
     } else if (x2) {
       produce_slab(c, src, c0, b, shifts[j]->as<float>(), sf32.p, lds, 0, n_loc, /*round_out=*/false, nullptr, ST, false, true);
-      launch_split_rows16(sf32.as<float>(), lds, slab[buf].p, slab_lo[buf].p, lds, n_loc, b, cs, ST);
+      if (f16) launch_split_rows16(sf32.as<float>(), lds, slab[buf].p, slab_lo[buf].p, lds, n_loc, b, cs, ST);
+      else launch_center_round(sf32.as<float>(), lds, 0, src.zeros.as<float>(), slab[buf].as<float>(), cs, lds, n_loc, b, ST,
+                               slab_lo[buf].as<float>());  // tf32 pairs
       c.launches += 1;
       flops += 4.0 * static_cast<double>(n_loc) * src.d_in * b;  // two extra product terms of the projection
     } else {
@@ -960,12 +970,19 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     deltas[j] = std::make_unique<DevBuf>();
     deltas[j]->alloc(sizeof(double) * b);
     double* Hj;
+    double* Dj = nullptr;
     if (cache_factors) {
       factors[j] = std::make_unique<DevBuf>();
       factors[j]->alloc(sizeof(double) * static_cast<size_t>(b) * b);
       Hj = factors[j]->as<double>();
+      if (c.custom_solve) {
+        dinvs[j] = std::make_unique<DevBuf>();
+        dinvs[j]->alloc(sizeof(double) * chol_solve_dinv_doubles(b));
+        Dj = dinvs[j]->as<double>();
+      }
     } else {
       Hj = Hbuf[buf].as<double>();
+      if (c.custom_solve) Dj = Dbuf[buf].as<double>();
     }
     KS_CUDA(cudaStreamWaitEvent(SF, ev_g[t], 0));
     c.span_begin(PH_SOLVE, SF);
@@ -974,6 +991,10 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
                         x2 ? gbuf[buf].as<float>() + g_elems : nullptr);
     c.launches += 2;
     c.potrf(Hj, b, info_slot++, SF);
+    if (Dj) {  // inverses of the factor's 64 x 64 diagonal tiles: the in-tile substitutions of the solve become DMMA products
+      KS_CUDA(launch_tri_inv_tiles(Hj, b, Dj, SF));
+      c.launches += 1;
+    }
     KS_CUDA(cudaMemsetAsync(model->W[j]->p, 0, model->W[j]->bytes, SF));
     c.span_end(SF);
     KS_CUDA(cudaEventRecord(ev_fact[t], SF));
@@ -1022,16 +1043,22 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     launch_build_rhs(cm.as<float>(), ldc, deltas[j]->as<double>(), rsum.as<double>(), n_total_d, lam,
                      it > 0 ? model->W[j]->as<double>() : nullptr, rhs.as<double>(), b, k, SS, f16 ? rscale + 1 : nullptr);
     c.launches += 1;
-    if (c.custom_solve) {
-      KS_CUDA(launch_chol_solve(Hj, b, rhs.as<double>(), k, SS));
-      c.launches += 1;
-    } else if (shard_solve) {
+    const double* Dj = !c.custom_solve ? nullptr : cache_factors ? dinvs[j]->as<double>() : Dbuf[buf].as<double>();
+    auto solve_cols = [&](double* cols, int ncols) {  // (L L^T)^-1 on `ncols` right-hand sides, in place
+      if (c.custom_solve) {
+        KS_CUDA(launch_chol_solve(Hj, Dj, b, cols, ncols, SS));  // one launch, runs beside the look-ahead Gram (solve_kernels.cu)
+        c.launches += 1;
+      } else {
+        c.potrs(Hj, b, cols, ncols, info_slot++, SS);
+      }
+    };
+    if (shard_solve) {
       // Column-sharded solve: the right-hand sides are independent, so rank r solves columns [k r / world, k (r+1) / world)
       // in place (column-major: a contiguous slice) and one grouped broadcast per rank hands every slice to everybody.
       // All ranks end up with the same bytes, so the model stays bit-identical across ranks.
       auto col0 = [&](int r) { return static_cast<int64_t>(k) * r / c.world; };
       const int64_t m0 = col0(c.rank), m1 = col0(c.rank + 1);
-      c.potrs(Hj, b, rhs.as<double>() + m0 * b, static_cast<int>(m1 - m0), info_slot++, SS);
+      solve_cols(rhs.as<double>() + m0 * b, static_cast<int>(m1 - m0));
       KS_NCCL(nccl_api().GroupStart());
       for (int r = 0; r < c.world; ++r) {
         double* slice = rhs.as<double>() + col0(r) * b;
@@ -1040,7 +1067,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       KS_NCCL(nccl_api().GroupEnd());
       c.launches += 1;
     } else {
-      c.potrs(Hj, b, rhs.as<double>(), k, info_slot++, SS);
+      solve_cols(rhs.as<double>(), k);
     }
     const double* dw_ptr = rhs.as<double>();
     if (f16) {
@@ -1087,16 +1114,19 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   // Enqueue order: a stream-wait on an event that has not been recorded yet counts as complete, so every wait is enqueued
   // after the corresponding record.
   if (serial) {
-    // tensor stream: proj(0) proj(1) G(0) | C(t) G(t+1) proj(t+2) update(t) | ...   (slab (t+2)%3 was last read by
-    // update(t-1), G buffer (t+1)%3 by factor(t-2): both precede in stream / event order)
+    // tensor stream: proj(0) proj(1) G(0) | C(t) G(t+1) update(t) proj(t+2) | ...   (slab (t+2)%3 was last read by
+    // update(t-1), G buffer (t+1)%3 by factor(t-2): both precede in stream / event order).  The solve of step t runs beside
+    // G(t+1): its CTAs fit on the SMs next to Gram CTAs (solve_kernels.cu), not next to the register-heavy projection kernel,
+    // which therefore comes after the update (pipeline = 2 puts it before, for A/B runs).
     for (int t = 0; t < std::min(T, 2); ++t) do_proj(t);
     do_gram(0);
     for (int t = 0; t < T; ++t) {
       do_cgram(t);
       do_solve(t);
       if (t + 1 < T) do_gram(t + 1);
-      if (t + 2 < T) do_proj(t + 2);
+      if (c.pipeline == 2 && t + 2 < T) do_proj(t + 2);
       do_update(t);
+      if (c.pipeline != 2 && t + 2 < T) do_proj(t + 2);
     }
   } else {
     // proj(t) after update(t - NBUF) released its buffers; G + factor of step t+1 after the chain of step t was enqueued
@@ -1143,8 +1173,8 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
      << ",\"gram_ms\":" << ms[PH_GRAM] << ",\"allreduce_ms\":" << ms[PH_ALLREDUCE] << ",\"solve_ms\":" << ms[PH_SOLVE]
      << ",\"update_ms\":" << ms[PH_UPDATE] << ",\"other_ms\":" << ms[PH_OTHER] << ",\"local_flops\":" << flops
      << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"" << (x2 ? (f16 ? "f16x2" : "tf32x2") : f16 ? "f16" : "tf32x1")
-     << "\",\"pipeline\":" << (serial ? 1 : 0) << ",\"host_mirror\":" << (model->host_valid ? 1 : 0) << ",\"solve\":\""
-     << (c.custom_solve ? "custom" : shard_solve ? "potrs-column-sharded" : "potrs") << "\",\"host_ms\":"
+     << "\",\"pipeline\":" << c.pipeline << ",\"host_mirror\":" << (model->host_valid ? 1 : 0) << ",\"solve\":\""
+     << (c.custom_solve ? "dmma-kernel" : "potrs") << (shard_solve ? "-column-sharded" : "") << "\",\"host_ms\":"
      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count() << "}";
   c.stats_json = js.str();
   return c.add(std::move(model));
@@ -1335,7 +1365,7 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
       c->precision = (atoi(e) == 1 || !strcmp(e, "f16")) ? KS_PRECISION_F16 : (atoi(e) == 2 || !strcmp(e, "f16x2") || !strcmp(e, "parity")) ? KS_PRECISION_F16X2 : KS_PRECISION_TF32;
     if (const char* e = getenv("KS_CUSTOM_SOLVE")) c->custom_solve = atoi(e) != 0;
     if (const char* e = getenv("KS_RESERVE_SMS")) c->reserve_sms = std::max(0, std::min(140, atoi(e)));
-    if (const char* e = getenv("KS_PIPELINE")) c->pipeline = atoi(e) != 0;
+    if (const char* e = getenv("KS_PIPELINE")) c->pipeline = std::max(0, std::min(2, atoi(e)));
     if (const char* e = getenv("KS_HOST_MIRROR")) c->host_mirror = atoi(e) != 0;
     KS_CUDA(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, prio_least));
     KS_CUDA(cudaStreamCreateWithPriority(&c->st3, cudaStreamNonBlocking, prio_mid));
@@ -1438,7 +1468,7 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     else if (n == "precision" && (value == KS_PRECISION_TF32 || value == KS_PRECISION_F16 || value == KS_PRECISION_F16X2)) c.precision = static_cast<int>(value);
     else if (n == "custom_solve") c.custom_solve = value != 0;
     else if (n == "reserve_sms" && value >= 0 && value < 148) c.reserve_sms = static_cast<int>(value);
-    else if (n == "pipeline") c.pipeline = value != 0;
+    else if (n == "pipeline" && value >= 0 && value <= 2) c.pipeline = static_cast<int>(value);
     else if (n == "solve_lanes" && value >= 1 && value <= 16) c.solve_lanes = static_cast<int>(value);
     else if (n == "host_mirror") c.host_mirror = value != 0;
     else if (n == "timing") c.timing = value != 0;
@@ -1585,6 +1615,61 @@ KS_API int32_t ks_cosine_rf_create(int64_t ctx, const double* W_colmajor, const 
     const int64_t id = c.next_id++;
     c.rfs[id] = std::move(r);
     *out_rf = id;
+  });
+}
+// RandomSignNode -> PaddedFFT [-> LinearRectifier] as ONE dense feature map (the real part of the FFT of a sign-flipped,
+// zero-padded real vector is a fixed cosine-matrix product): usable wherever a CosineRandomFeatures handle is.
+KS_API int32_t ks_padded_fft_create(int64_t ctx, const double* signs_or_null, int64_t n_in, int32_t rectify, double max_val,
+                                    double alpha, int64_t* out_rf) {
+  return guard(ctx, [&](Ctx& c) {
+    if (n_in <= 0 || !out_rf) throw KsError{KS_ERR_INVALID, "bad PaddedFFT arguments"};
+    int64_t P = 1;
+    while (P < n_in) P <<= 1;   // nextPositivePowerOfTwo (PaddedFFT.scala:20)
+    if (P < 2) P = 2;
+    auto r = std::make_unique<CosRF>();
+    r->n_out = P / 2;
+    r->n_in = n_in;
+    r->ld = round_up(n_in, kPadCols);
+    r->kind = 1;
+    r->rect_floor = rectify ? static_cast<float>(max_val) : -INFINITY;
+    r->wbuf.alloc(sizeof(float) * static_cast<size_t>(r->n_out * r->ld));
+    r->wfbuf.alloc(r->wbuf.bytes);
+    r->bbuf.alloc(sizeof(float) * static_cast<size_t>(r->n_out));
+    r->W = r->wbuf.as<float>();
+    r->Wfull = r->wfbuf.as<float>();
+    r->bias = r->bbuf.as<float>();
+    DevBuf sg;
+    if (signs_or_null) {
+      sg.alloc(sizeof(double) * static_cast<size_t>(n_in));
+      KS_CUDA(cudaMemcpyAsync(sg.p, signs_or_null, sizeof(double) * n_in, cudaMemcpyHostToDevice, c.st));
+    }
+    launch_fft_real_matrix(signs_or_null ? sg.as<double>() : nullptr, n_in, P, r->W, r->Wfull, r->ld, c.st);
+    launch_fill_f32(r->bias, r->n_out, rectify ? static_cast<float>(alpha) : 0.f, c.st);
+    c.launches += 2;
+    c.check_async("padded_fft_create");
+    const int64_t id = c.next_id++;
+    c.rfs[id] = std::move(r);
+    *out_rf = id;
+  });
+}
+// out = x .* colvec (op 0: RandomSignNode on a batch) or max(a, x - b) (op 1: LinearRectifier on a batch), as a new matrix
+KS_API int32_t ks_matrix_map(int64_t ctx, int64_t m, int32_t op, const double* colvec_or_null, double a, double b, int64_t* out_m) {
+  return guard(ctx, [&](Ctx& c) {
+    Matrix& in = c.matrix(m);
+    if (!out_m || (op != 0 && op != 1) || (op == 0 && !colvec_or_null)) throw KsError{KS_ERR_INVALID, "bad matrix_map arguments"};
+    auto out = new_matrix(in.rows, in.cols);
+    DevBuf cv64, cv32;
+    if (op == 0) {
+      cv64.alloc(sizeof(double) * static_cast<size_t>(in.cols));
+      cv32.alloc(sizeof(float) * static_cast<size_t>(in.cols));
+      KS_CUDA(cudaMemcpyAsync(cv64.p, colvec_or_null, sizeof(double) * in.cols, cudaMemcpyHostToDevice, c.st));
+      launch_f64_to_f32_vec(cv64.as<double>(), cv32.as<float>(), in.cols, c.st);
+    }
+    launch_matrix_map(in.d, out->d, in.ld, in.rows, static_cast<int>(in.cols), op, cv32.as<float>(), static_cast<float>(a),
+                      static_cast<float>(b), c.st);
+    c.launches += 2;
+    c.check_async("matrix_map");
+    *out_m = c.add(std::move(out));
   });
 }
 KS_API int32_t ks_cosine_rf_apply(int64_t ctx, int64_t rf, int64_t x_in, int64_t* out_features) {
@@ -1923,18 +2008,20 @@ KS_API int32_t ks_debug_chol_solve(int64_t ctx, const double* H_colmajor, int32_
                                    int32_t use_cusolver, double* X_out, double* out_ms) {
   return guard(ctx, [&](Ctx& c) {
     if (!H_colmajor || !B_colmajor || !X_out || n <= 0 || k <= 0) throw KsError{KS_ERR_INVALID, "bad arguments"};
-    DevBuf H, B;
+    DevBuf H, B, Dv;
     H.alloc(sizeof(double) * static_cast<size_t>(n) * n);
     B.alloc(sizeof(double) * static_cast<size_t>(n) * k);
+    Dv.alloc(sizeof(double) * chol_solve_dinv_doubles(n));
     KS_CUDA(cudaMemcpyAsync(H.p, H_colmajor, sizeof(double) * static_cast<size_t>(n) * n, cudaMemcpyHostToDevice, c.st));
     c.potrf(H.as<double>(), n, 0, c.st);
+    KS_CUDA(launch_tri_inv_tiles(H.as<double>(), n, Dv.as<double>(), c.st));
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
       KS_CUDA(cudaMemcpyAsync(B.p, B_colmajor, sizeof(double) * static_cast<size_t>(n) * k, cudaMemcpyHostToDevice, c.st));
       cudaEvent_t e0 = c.get_event(), e1 = c.get_event();
       KS_CUDA(cudaEventRecord(e0, c.st));
       if (use_cusolver) c.potrs(H.as<double>(), n, B.as<double>(), k, 1, c.st);
-      else KS_CUDA(launch_chol_solve(H.as<double>(), n, B.as<double>(), k, c.st));
+      else KS_CUDA(launch_chol_solve(H.as<double>(), Dv.as<double>(), n, B.as<double>(), k, c.st));
       KS_CUDA(cudaEventRecord(e1, c.st));
       c.check_async("debug_chol_solve");
       float ms = 0;

@@ -92,6 +92,10 @@ struct CosRF {
   float* Wfull = nullptr; // [n_out][ld] fp32(W) unrounded: source of the fp16 / split operands (rounding once, not twice)
   float* bias = nullptr;  // [n_out]
   int64_t n_out = 0, n_in = 0, ld = 0;
+  // kind 0: cos(x W^T + bias) (CosineRandomFeatures); kind 1: max(rect_floor, x W^T - bias) -- a dense linear node followed by
+  // LinearRectifier (K/nodes/stats/LinearRectifier.scala:12-17; bias holds alpha per column, rect_floor = -inf: no rectifier)
+  int kind = 0;
+  float rect_floor = 0.f;
 };
 
 struct Model {  // BlockLinearMapper state (K/nodes/learning/BlockLinearMapper.scala:22-33)
@@ -184,8 +188,8 @@ struct Ctx {
   int proj_f16 = 1;   // fp16 mode: the projection GEMM X W^T runs with fp16 operands too (0: tf32 operands, fp16 slab)
   int precision = KS_PRECISION_F16X2;  // what KS_PRECISION_DEFAULT resolves to: the split-operand parity mode
   int reserve_sms = 8; // SMs the persistent look-ahead kernel leaves to the critical chain
-  int custom_solve = 0; // experimental: 1 = chol_solve_kernel (single launch; 10.8 ms at b=4096,k=1000 vs 4.4 ms for
-                        // cusolverDnDpotrs alone / ~11 ms when potrs shares the SMs), 0 = cusolverDnDpotrs
+  int custom_solve = 1; // 1 = the library's DMMA solve kernel (one launch, co-resident with the look-ahead Gram CTAs:
+                        // solve_kernels.cu), 0 = cusolverDnDpotrs (~230 small launches that queue for SMs)
   int64_t sample_rows = 16384;
   int64_t next_id = 1;
   std::unordered_map<int64_t, std::unique_ptr<Matrix>> matrices;
@@ -238,6 +242,8 @@ struct FeatSrc {
   DevBuf wcat, wcat_full, bcat;
   float* Wall = nullptr;
   float* Wfull = nullptr;  // unrounded fp32 weights (same layout as Wall)
+  int kind = 0;            // feature-map kind of every gathered map (CosRF::kind; mixing kinds in one gather is rejected)
+  float rect_floor = 0.f;
   float* ball = nullptr;
   int64_t ldw = 0, d_in = 0;
   int64_t D = 0, n_rows = 0;

@@ -29,9 +29,10 @@ struct GramLaunch {
   int epi_multi = 1;       // CTA-pair kernel: rotate the epilogue through 8 staging buffers per warp (idle stage memory)
   int f16 = 0;             // 1: operands are fp16 (kind::f16, CTA-pair kernel, 64-row stages), 0: tf32
 };
-enum { KM_FLAG_NO_ROUND = 1, KM_FLAG_REDUCE = 2, KM_FLAG_EPI_MULTI = 4 };
+enum { KM_FLAG_NO_ROUND = 1, KM_FLAG_REDUCE = 2, KM_FLAG_EPI_MULTI = 4, KM_FLAG_RECT = 8 };
 struct KmParams {
-  const float* vec0;  // EPI_COS: bias;  EPI_UPDATE / EPI_APPLY: per-column constant
+  const float* vec0;  // EPI_COS: bias (KM_FLAG_RECT: alpha);  EPI_UPDATE / EPI_APPLY: per-column constant
+  float rect_floor = 0.f;   // KM_FLAG_RECT: the feature is max(rect_floor, acc - alpha) instead of cos(acc + bias)
   const float* vec1;  // EPI_COS: shift
   float* colsum;      // EPI_COS: if non-null, colsum[n] += sum over valid rows of the stored values (fp32 atomics)
   float acc_scale = 1.f;    // the accumulator is multiplied by this before the epilogue (undoes power-of-two operand scaling)
@@ -57,8 +58,11 @@ int make_tmap_any(CUtensorMap* out, const void* base, int64_t rows, int64_t cols
 cudaError_t launch_gram(const GramLaunch& g, cudaStream_t st);
 cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st);
 unsigned int read_wait_timeout_flag();
-// B (n x k, column-major, ld = n) <- (L L^T)^-1 B with L the lower triangle of a column-major n x n matrix (solve_kernels.cu)
-cudaError_t launch_chol_solve(const double* L, int n, double* B, int k, cudaStream_t st);
+// B (n x k, column-major, ld = n) <- (L L^T)^-1 B with L the lower triangle of a column-major n x n matrix and Dinv the inverses
+// of its 64 x 64 diagonal tiles (launch_tri_inv_tiles; chol_solve_dinv_doubles(n) doubles) -- solve_kernels.cu
+cudaError_t launch_chol_solve(const double* L, const double* Dinv, int n, double* B, int k, cudaStream_t st);
+cudaError_t launch_tri_inv_tiles(const double* L, int n, double* Dinv, cudaStream_t st);
+size_t chol_solve_dinv_doubles(int n);
 
 // ---- element-wise / reduction helpers (aux_kernels.cu) ----
 void launch_f64_to_f32_rows(const double* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int64_t cols,
@@ -105,6 +109,12 @@ void launch_normal_f32(float* dst, int64_t ld, int64_t rows, int cols, uint64_t 
 void launch_w_to_operand(const double* W_colmajor, int64_t n_out, int64_t n_in, float* dst, int64_t ld, cudaStream_t st,
                          bool round = true);  // round: tf32 round-to-nearest (MMA operand); false: plain fp32
 void launch_f64_to_f32_vec(const double* src, float* dst, int64_t n, cudaStream_t st);
+// PaddedFFT as a dense map: W[f][n] = signs[n] * cos(2 pi f n / P), f < P / 2, n < n_in (signs may be null = all ones), written
+// twice: tf32-rounded (dst) and plain fp32 (dst_full); both [P/2][ld]
+void launch_fft_real_matrix(const double* signs, int64_t n_in, int64_t P, float* dst, float* dst_full, int64_t ld, cudaStream_t st);
+// elementwise maps on a matrix: op 0: out = x * colvec[c];  op 1: out = max(a, x - b)
+void launch_matrix_map(const float* src, float* dst, int64_t ld, int64_t rows, int cols, int op, const float* colvec, float a, float b,
+                       cudaStream_t st);
 // ---- fp16 operand path: device-chosen power-of-two scales (scale[0] = 2^e, scale[1] = 2^-e) and fp16 operand packers
 void launch_max_abs_f32(const float* p, int64_t ld, int64_t rows, int cols, unsigned* maxbits, cudaStream_t st);
 void launch_max_abs_f64(const double* p, int64_t n, unsigned* maxbits, cudaStream_t st);

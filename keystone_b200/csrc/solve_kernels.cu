@@ -1,219 +1,178 @@
-// Multi-right-hand-side Cholesky solve  X = (L L^T)^{-1} B  in ONE kernel (fp64, CUDA cores).
+// Multi-right-hand-side Cholesky solve  X = (L L^T)^{-1} B  in ONE kernel on the fp64 tensor cores (DMMA m8n8k4).
 //
 // Replaces cusolverDnDpotrs on the critical chain of the block solver (the reference's `\` on the driver,
 // K/nodes/learning/BlockWeightedLeastSquares.scala:272, mlmatrix NormalEquations for BlockLS).  cuSOLVER runs the two
-// triangular solves as ~100 small dependent kernels: 5.5 ms alone and ~11 ms when it shares the SMs with the look-ahead
-// tensor work -- the dominant serial term of the strong-scaling curve (profiles/README.md).  Here every CTA owns 8
-// right-hand sides and performs the complete forward and backward substitution for them; L (the lower triangle, 67 MB
-// at b = 4096) is streamed from L2 once per pass per CTA and the kernel is a single launch.
+// triangular solves as ~230 small dependent kernels: 4.4 ms alone, but 26 ms when they share the GPU with the tensor-core
+// kernels of the look-ahead (profiles/README.md, round 2: every one of those launches waits for SMs that 140-microsecond Gram
+// CTAs or the persistent projection kernel are holding) -- the critical path of the whole fit.  This kernel is built to run
+// BESIDE them instead:
+//   * one launch; a CTA owns NC right-hand sides and performs the complete forward and backward substitution for them, so
+//     there is no inter-CTA dependency and no grid synchronisation;
+//   * no shared-memory tiles in the bulk loops and 10 KB in total: it fits next to a 209 KB Gram CTA on the same SM
+//     (registers and thread slots are free there), so its CTAs become resident at once instead of queueing for an SM;
+//   * all bulk arithmetic is DMMA (mma.sync.m8n8k4.f64) with operand fragments loaded straight from L2 in fully used
+//     32 / 64 B sectors; the in-tile substitutions are products with the pre-inverted 64 x 64 diagonal tiles (tri_inv_tiles,
+//     computed on the factor stream right after the Cholesky), i.e. DMMA as well -- no serial per-row dependency chains.
 //
-//   forward   for each 128-row tile I:  V = B_I - L[I, 0:i0] Y[0:i0]   (bulk, all 256 threads, 32-row chunks of Y in smem)
-//                                       Y_I = L[I,I]^{-1} V            (one warp per right-hand side, warp shuffles)
-//   backward  for each tile I (last to first): V = Y_I - L[i1:n, I]^T X[i1:n] ; X_I = L[I,I]^{-T} V
+//   forward   for each 64-row tile I:  V = B_I - L[I, 0:i0] Y[0:i0]      Y_I = inv(L_II) V
+//   backward  for each tile I (last to first): V = Y_I - L[i1:n, I]^T X[i1:n]      X_I = inv(L_II)^T V
 //
 // L: column-major n x n (ld = n), lower triangle valid (cusolverDnDpotrf, CUBLAS_FILL_MODE_LOWER).  B: column-major n x k.
+// Dinv: ceil(n / 64) tiles of 64 x 64 doubles, column-major inside a tile, zero above the diagonal and beyond n.
 #include "kernels.h"
 
 namespace ks {
 
 namespace {
-constexpr int TS = 128;      // tile size (rows of the diagonal tile)
-constexpr int NC = 8;        // right-hand sides per CTA == warps per CTA
-constexpr int CH = 32;       // rows of Y / X staged per chunk of the bulk update
-constexpr int LP = TS + 1;   // padded pitch (doubles) of transposed tiles in shared memory
+constexpr int TS = 64;  // tile rows
+constexpr int U = 16;   // k-steps (of 4) whose operand loads are in flight per warp (64 rows of the contraction)
 
-struct SolveSmem {
-  double diag[TS * LP];   // diagonal tile: forward  diag[q * LP + r] = L[i0 + r][i0 + q]  (r >= q)
-                          //                backward diag[q * LP + r] = L[i0 + q][i0 + r]  (r <= q)
-  double lt[CH * LP];     // backward bulk: lt[jj * LP + c] = L[j0 + jj][i0 + c]
-  double xs[CH * NC];     // staged chunk of already-solved rows: xs[jj * NC + c]
-  double v[TS * NC];      // tile right-hand side after the bulk update: v[r * NC + c]
-  double invd[TS];
-};
+__device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d[0]), "+d"(d[1])
+               : "d"(a), "d"(b));
+}
+
+// acc[g] (8 rows x 8 columns per n-group g) += A[8 x K] * Bm[K x 8 NG] over K = [k0, k1) (multiples of 4 * U), read from L2.
+//   A(m, kk)  = TRANS ? Aptr[kk + m * lda] : Aptr[m + kk * lda]     m = lane / 4, kk = lane % 4 (+ 4 per step)
+//   Bm(kk, c) = Bptr[kk + c * ldb]                                   kk = lane % 4, c = lane / 4 (+ 8 per n-group)
+// Rows kk >= krow_limit of A / Bm and A rows m >= mrow_limit read as zero (ragged edges).
+template <int NG, bool TRANS>
+__device__ __forceinline__ void bulk_dmma(double (&acc)[NG][2], const double* __restrict__ Aptr, size_t lda, int mrow_limit,
+                                          const double* Bptr, size_t ldb, const bool (&col_ok)[NG], int k0, int k1, int krow_limit,
+                                          int lane) {
+  const int m = lane >> 2, kq = lane & 3;
+  const bool m_ok = m < mrow_limit;
+  for (int kb = k0; kb < k1; kb += 4 * U) {
+    double a[U], b[U][NG];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int kk = kb + 4 * u + kq;
+      const bool ok = kk < krow_limit;
+      a[u] = (ok && m_ok) ? __ldg(TRANS ? Aptr + kk + static_cast<size_t>(m) * lda : Aptr + m + static_cast<size_t>(kk) * lda) : 0.0;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) b[u][g] = (ok && col_ok[g]) ? __ldcg(Bptr + kk + static_cast<size_t>(8 * g + m) * ldb) : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int g = 0; g < NG; ++g) dmma(acc[g], a[u], b[u][g]);
+  }
+}
 }  // namespace
 
+// 8 warps: warp w owns rows 8 w .. 8 w + 8 of the current 64-row tile.  Shared memory: the 64 x NC tile right-hand side only
+// (10 KB at NC = 16), registers ~130 x 256 threads: a CTA fits beside a Gram CTA (209 KB shared, 14 K registers) on one SM.
+template <int NC>
 __global__ void __launch_bounds__(256, 1)
-chol_solve_kernel(const double* __restrict__ L, int n, double* __restrict__ B, int k) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  SolveSmem& S = *reinterpret_cast<SolveSmem*>(smem_raw);
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int c0 = blockIdx.x * NC;            // first right-hand side of this CTA
-  const int row = t & (TS - 1);              // bulk update: tile row (forward) / tile column (backward)
-  const int half = t >> 7;                   // bulk update: right-hand sides [4*half, 4*half + 4)
-  const int ntiles = (n + TS - 1) / TS;
+chol_solve_kernel(const double* __restrict__ L, const double* __restrict__ Dinv, int n, double* B, int k) {
+  constexpr int NG = NC / 8;
+  constexpr int VP = NC + 4;                 // pitch of sV: conflict-free B-fragment reads (k * VP + c distinct mod 16)
+  __shared__ double sV[TS * VP];             // tile right-hand side after the bulk update (B operand of the diagonal product)
+  const int t = threadIdx.x, rg = t >> 5, lane = t & 31;
+  const int c0 = blockIdx.x * NC;
   const size_t ld = static_cast<size_t>(n);
-  const int my_col = c0 + warp;              // in-tile solve: the right-hand side owned by this warp
-  const bool col_ok = my_col < k;
+  const int ntiles = (n + TS - 1) / TS;
+  const int npad = ntiles * TS;
+  const int m = lane >> 2, cq = lane & 3;
+  bool col_ok[NG];
+#pragma unroll
+  for (int g = 0; g < NG; ++g) col_ok[g] = c0 + 8 * g + m < k;       // B-fragment column of this lane
+  double* Bc = B + static_cast<size_t>(c0) * ld;
 
-  // =========================================================== forward: L Y = B
-  for (int it = 0; it < ntiles; ++it) {
-    const int i0 = it * TS;
-    const int rows = min(TS, n - i0);
-    // ---- stage the diagonal tile (column q of the tile contiguous in r: coalesced global reads, conflict-free smem)
-    for (int idx = t; idx < TS * TS; idx += 256) {
-      const int q = idx / TS, r = idx - q * TS;
-      double val = 0.0;
-      if (r >= q && r < rows) val = L[(i0 + r) + (i0 + q) * ld];
-      S.diag[q * LP + r] = val;
-    }
-    // ---- bulk update  acc[row][c] = sum_{j < i0} L[i0 + row][j] * Y[j][c]
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    const bool row_ok = row < rows;
-    for (int j0 = 0; j0 < i0; j0 += CH) {
-      __syncthreads();
-      {  // stage Y[j0 .. j0+CH)[c0 .. c0+NC): 256 threads, one element each (coalesced along j for a fixed column)
-        const int jj = t & (CH - 1), c = t >> 5;
-        S.xs[jj * NC + c] = (c0 + c < k) ? B[(j0 + jj) + (c0 + c) * ld] : 0.0;
-      }
-      __syncthreads();
-      if (row_ok) {
-        const double* lp = L + (i0 + row) + j0 * ld;
-#pragma unroll 8
-        for (int jj = 0; jj < CH; ++jj) {
-          const double l = lp[jj * ld];
-          const double2 y01 = *reinterpret_cast<const double2*>(&S.xs[jj * NC + 4 * half]);
-          const double2 y23 = *reinterpret_cast<const double2*>(&S.xs[jj * NC + 4 * half + 2]);
-          acc[0] = fma(l, y01.x, acc[0]);
-          acc[1] = fma(l, y01.y, acc[1]);
-          acc[2] = fma(l, y23.x, acc[2]);
-          acc[3] = fma(l, y23.y, acc[3]);
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int step = 0; step < ntiles; ++step) {
+      const int it = pass == 0 ? step : ntiles - 1 - step;
+      const int i0 = it * TS;
+      const int r0 = i0 + 8 * rg;                                       // first row of this warp
+      double acc[NG][2];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) acc[g][0] = acc[g][1] = 0.0;
+      // ---- bulk update over the already solved rows: [0, i0) forward, [i0 + TS, npad) backward
+      if (pass == 0) bulk_dmma<NG, false>(acc, L + r0, ld, n - r0, Bc, ld, col_ok, 0, i0, n, lane);
+      else bulk_dmma<NG, true>(acc, L + static_cast<size_t>(r0) * ld, ld, n - r0, Bc, ld, col_ok, i0 + TS, npad, n, lane);
+      // ---- V = B_I - acc  (C fragment: row m, columns 2 cq, 2 cq + 1 of n-group g) -> shared
+#pragma unroll
+      for (int g = 0; g < NG; ++g)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int row = r0 + m, col = c0 + 8 * g + 2 * cq + e;
+          const double bv = (row < n && col < k) ? __ldcg(B + row + static_cast<size_t>(col) * ld) : 0.0;
+          sV[(8 * rg + m) * VP + 8 * g + 2 * cq + e] = bv - acc[g][e];
         }
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int col = c0 + 4 * half + c;
-      S.v[row * NC + 4 * half + c] = (row_ok && col < k) ? B[(i0 + row) + col * ld] - acc[c] : 0.0;
-    }
-    if (t < TS) {
-      const double d = S.diag[t * LP + t];
-      S.invd[t] = (t < rows && d != 0.0) ? 1.0 / d : 0.0;
-    }
-    __syncthreads();
-    // ---- in-tile forward substitution: warp w owns right-hand side w; lane holds rows lane, lane+32, lane+64, lane+96
-    {
-      double vr[4];
-#pragma unroll
-      for (int m = 0; m < 4; ++m) vr[m] = S.v[(lane + 32 * m) * NC + warp];
-      for (int q = 0; q < rows; ++q) {
-        const int m = q >> 5, src = q & 31;
-        double cand = vr[0];
-        if (m == 1) cand = vr[1];
-        else if (m == 2) cand = vr[2];
-        else if (m == 3) cand = vr[3];
-        const double yq = __shfl_sync(0xffffffffu, cand, src) * S.invd[q];
-        const double* dq = &S.diag[q * LP];
-#pragma unroll
-        for (int mm = 0; mm < 4; ++mm) {
-          const int r = lane + 32 * mm;
-          if (r == q) vr[mm] = yq;
-          else if (r > q) vr[mm] = fma(-dq[r], yq, vr[mm]);
-        }
-      }
-      if (col_ok) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int r = lane + 32 * m;
-          if (r < rows) B[(i0 + r) + my_col * ld] = vr[m];
-        }
-      }
-    }
-    __syncthreads();  // Y_I is visible to the whole CTA before the next tile stages it
-  }
-
-  // =========================================================== backward: L^T X = Y
-  for (int it = ntiles - 1; it >= 0; --it) {
-    const int i0 = it * TS;
-    const int rows = min(TS, n - i0);
-    const int i1 = i0 + TS;
-    // ---- stage the diagonal tile transposed: diag[q * LP + r] = L[i0 + q][i0 + r], r <= q
-    for (int idx = t; idx < TS * TS; idx += 256) {
-      const int r = idx / TS, q = idx - r * TS;  // q fastest: consecutive rows of L for a fixed column r -> coalesced
-      double val = 0.0;
-      if (r <= q && q < rows) val = L[(i0 + q) + (i0 + r) * ld];
-      S.diag[q * LP + r] = val;
-    }
-    // ---- bulk update  acc[col][c] = sum_{j >= i1} L[j][i0 + col] * X[j][c]
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int j0 = i1; j0 < n; j0 += CH) {
       __syncthreads();
+      // ---- in-tile solve as a product with the inverted diagonal tile (K = 64)
+      double y[NG][2];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) y[g][0] = y[g][1] = 0.0;
       {
-        const int jj = t & (CH - 1), c = t >> 5;
-        S.xs[jj * NC + c] = (j0 + jj < n && c0 + c < k) ? B[(j0 + jj) + (c0 + c) * ld] : 0.0;
-        // transposed chunk of L: thread reads 32 consecutive j of one tile column (256 B per warp)
+        const double* Dt = Dinv + static_cast<size_t>(it) * TS * TS;
 #pragma unroll
-        for (int m = 0; m < TS / 8; ++m) {
-          const int cc = (t >> 5) + 8 * m;
-          S.lt[jj * LP + cc] = (j0 + jj < n && cc < rows) ? L[(j0 + jj) + (i0 + cc) * ld] : 0.0;
+        for (int u = 0; u < TS / 4; ++u) {
+          const int kk = 4 * u + cq;
+          // forward: A(m, kk) = Dinv[8 rg + m][kk]; backward: A(m, kk) = Dinv[kk][8 rg + m]   (column-major tile)
+          const double a = pass == 0 ? __ldg(Dt + (8 * rg + m) + kk * TS) : __ldg(Dt + kk + (8 * rg + m) * TS);
+#pragma unroll
+          for (int g = 0; g < NG; ++g) dmma(y[g], a, sV[kk * VP + 8 * g + m]);
         }
       }
-      __syncthreads();
-#pragma unroll 8
-      for (int jj = 0; jj < CH; ++jj) {
-        const double l = S.lt[jj * LP + row];
-        const double2 x01 = *reinterpret_cast<const double2*>(&S.xs[jj * NC + 4 * half]);
-        const double2 x23 = *reinterpret_cast<const double2*>(&S.xs[jj * NC + 4 * half + 2]);
-        acc[0] = fma(l, x01.x, acc[0]);
-        acc[1] = fma(l, x01.y, acc[1]);
-        acc[2] = fma(l, x23.x, acc[2]);
-        acc[3] = fma(l, x23.y, acc[3]);
-      }
-    }
-    __syncthreads();
-    const bool row_ok = row < rows;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int col = c0 + 4 * half + c;
-      S.v[row * NC + 4 * half + c] = (row_ok && col < k) ? B[(i0 + row) + col * ld] - acc[c] : 0.0;
-    }
-    if (t < TS) {
-      const double d = S.diag[t * LP + t];
-      S.invd[t] = (t < rows && d != 0.0) ? 1.0 / d : 0.0;
-    }
-    __syncthreads();
-    // ---- in-tile backward substitution: x_q = v_q / L_qq ; v_r -= L[q][r] x_q for r < q
-    {
-      double vr[4];
+      for (int g = 0; g < NG; ++g)
 #pragma unroll
-      for (int m = 0; m < 4; ++m) vr[m] = S.v[(lane + 32 * m) * NC + warp];
-      for (int q = rows - 1; q >= 0; --q) {
-        const int m = q >> 5, src = q & 31;
-        double cand = vr[0];
-        if (m == 1) cand = vr[1];
-        else if (m == 2) cand = vr[2];
-        else if (m == 3) cand = vr[3];
-        const double xq = __shfl_sync(0xffffffffu, cand, src) * S.invd[q];
-        const double* dq = &S.diag[q * LP];
-#pragma unroll
-        for (int mm = 0; mm < 4; ++mm) {
-          const int r = lane + 32 * mm;
-          if (r == q) vr[mm] = xq;
-          else if (r < q) vr[mm] = fma(-dq[r], xq, vr[mm]);
+        for (int e = 0; e < 2; ++e) {
+          const int row = r0 + m, col = c0 + 8 * g + 2 * cq + e;
+          if (row < n && col < k) B[row + static_cast<size_t>(col) * ld] = y[g][e];
         }
-      }
-      if (col_ok) {
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          const int r = lane + 32 * m;
-          if (r < rows) B[(i0 + r) + my_col * ld] = vr[m];
-        }
-      }
+      __syncthreads();  // the solved rows are visible to every warp of the CTA (they are read back through L2) before the next tile
     }
-    __syncthreads();
   }
 }
 
-cudaError_t launch_chol_solve(const double* L, int n, double* B, int k, cudaStream_t st) {
-  if (n <= 0 || k <= 0) return cudaSuccess;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(sizeof(SolveSmem)));
-    if (e != cudaSuccess) return e;
-    attr_done = true;
+// Inverse of every 64 x 64 diagonal tile of the Cholesky factor (lower triangular): one CTA per tile, thread j builds column j
+// of the inverse by forward substitution.  Output tile it: Dinv[it][r + 64 c], zero above the diagonal and for rows / columns >= n.
+__global__ void __launch_bounds__(TS)
+tri_inv_tiles_kernel(const double* __restrict__ L, int n, double* __restrict__ Dinv) {
+  __shared__ double sL[TS][TS + 1];
+  const int it = blockIdx.x, j = threadIdx.x, i0 = it * TS;
+  const size_t ld = static_cast<size_t>(n);
+  for (int c = 0; c < TS; ++c) {
+    const int r = j;
+    sL[r][c] = (i0 + r < n && i0 + c < n && r >= c) ? L[(i0 + r) + (i0 + c) * ld] : (r == c ? 1.0 : 0.0);
   }
-  chol_solve_kernel<<<(k + NC - 1) / NC, 256, sizeof(SolveSmem), st>>>(L, n, B, k);
+  __syncthreads();
+  double x[TS];
+#pragma unroll
+  for (int r = 0; r < TS; ++r) x[r] = 0.0;
+  const bool live = i0 + j < n;
+#pragma unroll
+  for (int r = 0; r < TS; ++r) {
+    if (r >= j) {
+      double s = (r == j) ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < TS; ++q)
+        if (q < r && q >= j) s -= sL[r][q] * x[q];
+      x[r] = s / sL[r][r];
+    }
+  }
+  double* out = Dinv + static_cast<size_t>(it) * TS * TS + static_cast<size_t>(j) * TS;
+#pragma unroll
+  for (int r = 0; r < TS; ++r) out[r] = (live && r >= j && i0 + r < n) ? x[r] : 0.0;
+}
+
+size_t chol_solve_dinv_doubles(int n) { return static_cast<size_t>((n + TS - 1) / TS) * TS * TS; }
+
+cudaError_t launch_tri_inv_tiles(const double* L, int n, double* Dinv, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  tri_inv_tiles_kernel<<<(n + TS - 1) / TS, TS, 0, st>>>(L, n, Dinv);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chol_solve(const double* L, const double* Dinv, int n, double* B, int k, cudaStream_t st) {
+  if (n <= 0 || k <= 0) return cudaSuccess;
+  // 16 right-hand sides per CTA halve the L2 traffic for L (every CTA streams the whole factor twice); with few columns (the
+  // column-sharded multi-GPU solve) 8 per CTA keep more SMs busy
+  if (k > 8 * 96) chol_solve_kernel<16><<<(k + 15) / 16, 256, 0, st>>>(L, Dinv, n, B, k);
+  else chol_solve_kernel<8><<<(k + 7) / 8, 256, 0, st>>>(L, Dinv, n, B, k);
   return cudaGetLastError();
 }
 

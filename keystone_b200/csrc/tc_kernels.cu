@@ -513,7 +513,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (EPI == EPI_COS) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float val = cos_reduced(__uint_as_float(v[i]) * ascale + v0s[c0 + i]) - v1s[c0 + i];
+            const float z = __uint_as_float(v[i]) * ascale;
+            // cosine random feature, or (KM_FLAG_RECT) a rectified linear feature max(floor, z - alpha): PaddedFFT + LinearRectifier
+            const float val = ((p.flags & KM_FLAG_RECT) ? fmaxf(p.rect_floor, z - v0s[c0 + i]) : cos_reduced(z + v0s[c0 + i])) - v1s[c0 + i];
             // the value summed into colsum must be exactly the stored one: tf32 rounding here; the fp16 slab is rounded once,
             // by the packed conversion of the staging step, and its column sums are taken from the staged halfs
             o[i] = OUT16 ? val : ((p.flags & KM_FLAG_NO_ROUND) ? val : round_tf32(val));

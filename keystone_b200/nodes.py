@@ -83,6 +83,121 @@ class CosineRandomFeatures(Transformer):
             pass
 
 
+class _FeatureMapHandle:
+    """Owns a dense feature-map handle of the library (PaddedFFT / rectified maps; same handle space as CosineRandomFeatures)."""
+
+    def __init__(self, ctx: Context, handle: int):
+        self.ctx, self.handle = ctx, handle
+
+    def __del__(self):
+        try:
+            if self.handle and self.ctx.handle:
+                lib().ks_cosine_rf_destroy(self.ctx.handle, self.handle)
+        except Exception:
+            pass
+
+
+class _SignedInput(Dataset):
+    """Lazy ``x .* signs`` (RandomSignNode output): fused into the PaddedFFT map that consumes it."""
+
+    def __init__(self, x: DeviceMatrix, signs: np.ndarray):
+        self.ctx, self.x, self.signs = x.ctx, x, signs
+        self.rows, self.cols = x.rows, x.cols
+
+    def materialize(self) -> DeviceMatrix:
+        h = C.c_int64(0)
+        check(self.ctx.handle, lib().ks_matrix_map(self.ctx.handle, self.x.handle, 0, self.signs.ctypes.data_as(C.c_void_p), 0.0, 0.0,
+                                                    C.byref(h)))
+        return DeviceMatrix(self.ctx, h.value, self.rows, self.cols)
+
+    def to_numpy(self, dtype=np.float64) -> np.ndarray:
+        return self.materialize().to_numpy(dtype)
+
+
+class _FFTFeatures(LazyFeatures):
+    """Lazy PaddedFFT output (optionally of a sign-flipped input): a LazyFeatures whose single map is the FFT cosine matrix;
+    a following LinearRectifier swaps the map for the rectified one."""
+
+    def __init__(self, x: DeviceMatrix, signs: Optional[np.ndarray], rectifier=None):
+        ctx = x.ctx
+        self.signs, self.rectifier = signs, rectifier
+        h = C.c_int64(0)
+        sp = None if signs is None else signs.ctypes.data_as(C.c_void_p)
+        rect, mx, al = (0, 0.0, 0.0) if rectifier is None else (1, float(rectifier[0]), float(rectifier[1]))
+        check(ctx.handle, lib().ks_padded_fft_create(ctx.handle, sp, x.cols, rect, mx, al, C.byref(h)))
+        owner = _FeatureMapHandle(ctx, h.value)
+        n_out = PaddedFFT.next_positive_power_of_two(x.cols) // 2
+        super().__init__(x, [h.value], [n_out], [owner])
+
+
+class RandomSignNode(Transformer):
+    """``in :* signs`` (K/nodes/stats/RandomSignNode.scala:11-16).  On a device batch the product is lazy and folds into the
+    PaddedFFT map that follows."""
+
+    def __init__(self, signs: np.ndarray, ctx: Optional[Context] = None):
+        self.signs = np.ascontiguousarray(signs, dtype=np.float64)
+        self.ctx = ctx
+
+    @classmethod
+    def create(cls, size: int, rng: Optional[np.random.Generator] = None, ctx: Optional[Context] = None) -> "RandomSignNode":
+        """Companion factory (:19-23): 2 * Binomial(1, 0.5) - 1 per element."""
+        rng = rng or np.random.default_rng()
+        return cls(2.0 * rng.integers(0, 2, size).astype(np.float64) - 1.0, ctx)
+
+    def apply(self, data):
+        single = isinstance(data, np.ndarray) and data.ndim == 1
+        ds = _as_dataset(self.ctx, data)
+        if not isinstance(ds, DeviceMatrix):
+            ds = ds.materialize()
+        if ds.cols != self.signs.shape[0]:
+            raise ValueError("signs and input have different lengths")
+        out = _SignedInput(ds, self.signs)
+        return out.to_numpy()[0] if single else out
+
+
+class PaddedFFT(Transformer):
+    """Pads to the next power of two P and returns the real part of the first P / 2 FFT bins
+    (K/nodes/stats/PaddedFFT.scala:13-21) -- on the device a fixed cosine-matrix product on the tensor cores."""
+
+    def __init__(self, ctx: Optional[Context] = None):
+        self.ctx = ctx
+
+    @staticmethod
+    def next_positive_power_of_two(i: int) -> int:
+        return 1 << max(0, (int(i) - 1).bit_length())
+
+    def apply(self, data):
+        single = isinstance(data, np.ndarray) and data.ndim == 1
+        if isinstance(data, _SignedInput):
+            out = _FFTFeatures(data.x, data.signs)
+        else:
+            ds = _as_dataset(self.ctx, data)
+            if not isinstance(ds, DeviceMatrix):
+                ds = ds.materialize()
+            out = _FFTFeatures(ds, None)
+        return out.to_numpy()[0] if single else out
+
+
+class LinearRectifier(Transformer):
+    """``max(maxVal, x - alpha)`` (K/nodes/stats/LinearRectifier.scala:12-17); after PaddedFFT it becomes the epilogue of the
+    FFT GEMM."""
+
+    def __init__(self, max_val: float = 0.0, alpha: float = 0.0, ctx: Optional[Context] = None):
+        self.max_val, self.alpha, self.ctx = float(max_val), float(alpha), ctx
+
+    def apply(self, data):
+        single = isinstance(data, np.ndarray) and data.ndim == 1
+        if isinstance(data, _FFTFeatures) and data.rectifier is None:
+            return _FFTFeatures(data.x_in, data.signs, (self.max_val, self.alpha))
+        ds = _as_dataset(self.ctx, data)
+        if not isinstance(ds, DeviceMatrix):
+            ds = ds.materialize()
+        h = C.c_int64(0)
+        check(ds.ctx.handle, lib().ks_matrix_map(ds.ctx.handle, ds.handle, 1, None, self.max_val, self.alpha, C.byref(h)))
+        out = DeviceMatrix(ds.ctx, h.value, ds.rows, ds.cols)
+        return out.to_numpy()[0] if single else out
+
+
 class VectorCombiner(Transformer):
     """Concatenates the outputs of gathered branches (VectorCombiner.scala:11-14)."""
 
@@ -127,9 +242,24 @@ class MaxClassifier(Transformer):
 
 
 # ------------------------------------------------------------------------------------------
+class _ModelHandle:
+    """Owns one model handle of the library (and with it the pinned host mirror the arrays below point into)."""
+
+    def __init__(self, ctx: Context, handle: int):
+        self.ctx, self.handle = ctx, handle
+
+    def __del__(self):
+        try:
+            if self.handle and self.ctx.handle:
+                lib().ks_model_destroy(self.ctx.handle, self.handle)
+        except Exception:
+            pass
+
+
 class _HostView:
-    """Array-interface holder for a block of the model's pinned host mirror; numpy keeps it (and through it the mapper that
-    owns the memory) alive as the array's base."""
+    """Array-interface holder for a block of the model's pinned host mirror; numpy keeps it (and through it the model handle
+    that owns the memory) alive as the array's base.  It references the handle object, not the mapper: no reference cycle,
+    so dropping the mapper and its arrays frees the model at once."""
 
     def __init__(self, owner, ptr: int, shape, order: str):
         self.owner = owner
@@ -144,6 +274,7 @@ class BlockLinearMapper(Transformer):
 
     def __init__(self, ctx: Context, handle: int):
         self.ctx, self.handle = ctx, handle
+        self._owner = _ModelHandle(ctx, handle)
         nb, k, bs = C.c_int32(0), C.c_int64(0), C.c_int32(0)
         check(ctx.handle, lib().ks_model_num_blocks(ctx.handle, handle, C.byref(nb), C.byref(k), C.byref(bs)))
         self.num_blocks, self.k, self.block_size = nb.value, k.value, bs.value
@@ -171,8 +302,7 @@ class BlockLinearMapper(Transformer):
     # The fit mirrors every finished block into pinned host memory while it is still running (ks_model_host_view); the
     # arrays below are read-only views of that mirror (no copy) and keep this mapper alive through their base object.
     def _view(self, ptr: int, shape, order: str) -> np.ndarray:
-        holder = _HostView(self, ptr, shape, order)
-        return np.asarray(holder)
+        return np.asarray(_HostView(self._owner, ptr, shape, order))
 
     def _block(self, j: int):
         rows = C.c_int64(0)
@@ -235,14 +365,6 @@ class BlockLinearMapper(Transformer):
         out = C.c_double(0)
         check(self.ctx.handle, lib().ks_model_cost(self.ctx.handle, self.handle, f, x, rfs, n, lb.handle, lam, C.byref(out)))
         return out.value
-
-    def __del__(self):
-        try:
-            if self.handle and self.ctx.handle:
-                lib().ks_model_destroy(self.ctx.handle, self.handle)
-        except Exception:
-            pass
-
 
 class LinearMapper(BlockLinearMapper):
     """LinearMapper(x, bOpt, featureScaler): the single-block special case (LinearMapper.scala:18-63)."""

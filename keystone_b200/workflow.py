@@ -117,7 +117,22 @@ class _Gather(Transformer):
     def __init__(self, branches: Sequence[Pipeline]):
         self.branches = list(branches)
 
+    @staticmethod
+    def _context_of(pipe: "Pipeline"):
+        for s in pipe.stages:
+            ctx = getattr(s, "ctx", None)
+            if ctx is not None:
+                return ctx
+        return None
+
     def apply(self, data):
+        # a host batch is uploaded ONCE and every branch sees the same device matrix (gathered lazy feature maps must
+        # share their input; the reference's branches all read the same RDD, Pipeline.scala:119-154)
+        import numpy as np
+        if isinstance(data, np.ndarray) and data.ndim == 2:
+            ctx = next((c for c in (self._context_of(b) for b in self.branches) if c is not None), None)
+            if ctx is not None:
+                data = ctx.matrix(data)
         return [b.apply(data) for b in self.branches]
 
 

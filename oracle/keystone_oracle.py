@@ -113,6 +113,38 @@ def cosine_random_features_params(n_in: int, n_out: int, gamma: float, rng: np.r
 
 
 # --------------------------------------------------------------------------------------
+# MNIST random-FFT featurizer: K/nodes/stats/RandomSignNode.scala:11-24,
+# PaddedFFT.scala:13-21, LinearRectifier.scala:12-17, K/pipelines/images/mnist/MnistRandomFFT.scala:40-44
+# --------------------------------------------------------------------------------------
+def random_sign_node(x: np.ndarray, signs: np.ndarray) -> np.ndarray:
+    """``in :* signs`` (RandomSignNode.scala:15)."""
+    return np.asarray(x, dtype=F64) * np.asarray(signs, dtype=F64)
+
+
+def next_positive_power_of_two(i: int) -> int:
+    """PaddedFFT.scala:20: ``1 << (32 - numberOfLeadingZeros(i - 1))``."""
+    return 1 << max(0, (int(i) - 1).bit_length())
+
+
+def padded_fft(x: np.ndarray) -> np.ndarray:
+    """Zero-pad to the next power of two P, Fourier transform, real part of bins [0, P/2) (PaddedFFT.scala:14-18)."""
+    x = np.asarray(x, dtype=F64)
+    p = next_positive_power_of_two(x.shape[-1])
+    return np.fft.fft(x, n=p, axis=-1)[..., : p // 2].real
+
+
+def linear_rectifier(x: np.ndarray, max_val: float = 0.0, alpha: float = 0.0) -> np.ndarray:
+    """``max(maxVal, x - alpha)`` elementwise (LinearRectifier.scala:14-16)."""
+    return np.maximum(max_val, np.asarray(x, dtype=F64) - alpha)
+
+
+def mnist_random_fft_features(x: np.ndarray, signs_list: Sequence[np.ndarray]) -> np.ndarray:
+    """gather(RandomSignNode andThen PaddedFFT andThen LinearRectifier(0.0)) andThen VectorCombiner
+    (MnistRandomFFT.scala:40-44)."""
+    return np.concatenate([linear_rectifier(padded_fft(random_sign_node(x, s)), 0.0) for s in signs_list], axis=-1)
+
+
+# --------------------------------------------------------------------------------------
 # label helpers (K/nodes/util/ClassLabelIndicators.scala:15-29, MaxClassifier.scala:9-11)
 # --------------------------------------------------------------------------------------
 def class_label_indicators(labels: np.ndarray, num_classes: int) -> np.ndarray:

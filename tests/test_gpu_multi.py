@@ -55,7 +55,7 @@ def test_two_rank_fit_matches_oracle(pipeline, precision):
     id_holder = mgr.dict(); ret = mgr.dict()
     id_holder["id"] = ks.Context.new_nccl_id()
     mp.spawn(_worker, args=(2, id_holder, ret, pipeline, precision), nprocs=2, join=True)
-    assert ret["rel"] < (5e-5 if precision == "default" else 1.5e-3), ret["rel"]
+    assert ret["rel"] < (1e-4 if precision == "default" else 1.5e-3), ret["rel"]
     assert ret["cost_rel"] < 1e-4 and ret["b_err"] < 1e-6   # computeCost applies the model in the context's (parity) mode
     assert np.array_equal(ret["W0"], ret["W1"])      # redundant solves are bit-identical across ranks
 
@@ -95,7 +95,7 @@ def test_two_rank_class_sharded_bwls_matches_oracle():
     B = np.loadtxt(os.path.join(ROOT, "tests", "golden", "bMat.csv"), delimiter=",")
     xs, fb = ko.bwls_fit(A, B, 4, 10, 0.1, 0.3)
     Wr = np.concatenate(xs, 0)
-    assert np.linalg.norm(ret["W0"] - Wr) / np.linalg.norm(Wr) < 5e-5
-    assert np.abs(ret["b0"] - fb).max() < 5e-5
+    assert np.linalg.norm(ret["W0"] - Wr) / np.linalg.norm(Wr) < 1e-4
+    assert np.abs(ret["b0"] - fb).max() < 1e-4
     assert np.array_equal(ret["W0"], ret["W1"]) and np.array_equal(ret["b0"], ret["b1"])
     assert ret["rejected0"] and ret["rejected1"]

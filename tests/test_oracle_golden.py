@@ -283,3 +283,32 @@ def test_block_ls_pinned_by_bwls_with_zero_mixture_weight(golden_dir, bs, iters)
     xs_s, _, _ = ko.block_ls_fit(As, Bs, bs, iters, lam * n)
     for xw, x in zip(xs_w, xs_s):
         assert np.abs(xw - x).max() < 1e-10
+
+
+# ---- MNIST random-FFT featurizer nodes -------------------------------------------------------------------------------
+def test_padded_fft_known_answers():
+    """T/nodes/stats/PaddedFFTSuite.scala:13-36: length-100 unit impulses -> 64 real bins, agreement with R's Re(fft(.))."""
+    ones = np.zeros(100); ones[0] = 1.0
+    twos = np.zeros(100); twos[2] = 1.0
+    out = ko.padded_fft(np.stack([twos, ones]))
+    assert out.shape == (2, 64)
+    assert abs(out[0, 0] - 1.0) < 1e-8 and abs(out[0, 16]) < 1e-8 and abs(out[0, 32] + 1.0) < 1e-8 and abs(out[0, 48]) < 1e-8
+    assert np.abs(out[1] - 1.0).max() < 1e-8
+    assert ko.next_positive_power_of_two(784) == 1024 and ko.next_positive_power_of_two(1024) == 1024
+
+
+def test_random_sign_node_and_linear_rectifier():
+    """T/nodes/stats/RandomSignNodeSuite.scala:11-18 and LinearRectifierSuite.scala:13-27."""
+    assert np.array_equal(ko.random_sign_node(np.array([1.0, 2.0, 3.0]), np.array([1.0, -1.0, 1.0])), np.array([1.0, -2.0, 3.0]))
+    x = np.random.default_rng(0).standard_normal((128, 16))
+    assert (x < 0).any() and (ko.linear_rectifier(x) >= 0).all()
+    assert np.array_equal(ko.linear_rectifier(np.array([-1.0, 0.5, 3.0]), 0.25, 1.0), np.array([0.25, 0.25, 2.0]))
+
+
+def test_fft_featurizer_is_a_cosine_matrix_product():
+    """The identity the device path uses: Re(FFT(pad(x .* s)))[f] = sum_n x[n] s[n] cos(2 pi f n / P)."""
+    rng = np.random.default_rng(1)
+    x = rng.random((5, 784)); s = 2.0 * rng.integers(0, 2, 784) - 1.0
+    P = 1024
+    M = s[None, :] * np.cos(2 * np.pi * np.outer(np.arange(P // 2), np.arange(784)) / P)
+    assert np.abs(ko.padded_fft(ko.random_sign_node(x, s)) - x @ M.T).max() < 1e-9

@@ -2,6 +2,7 @@
 workload (GPU box).  Every configuration gets 1 warm-up + 3 timed fits; the list runs twice so drift shows up as a
 difference between the passes.  With KS_TIMELINE set, the last fit of every configuration dumps its span timeline."""
 import json
+import os
 import sys
 import time
 
@@ -12,6 +13,7 @@ import keystone_b200 as ks
 
 
 def main():
+    tl_base = os.environ.pop("KS_TIMELINE", None)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
     configs = [c.split(":") for c in sys.argv[2:]] or [["1", "f16"], ["0", "f16"], ["1", "f16x2"], ["1", "tf32"]]
     rng = np.random.default_rng(0)
@@ -31,11 +33,14 @@ def main():
                 est = ks.BlockLeastSquaresEstimator(n_out, 1, 1.0, precision=prec)
                 est.fit(feats, y)
                 ts = []
-                for _ in range(3):
+                for i in range(3):
+                    if tl_base and i == 2:
+                        os.environ["KS_TIMELINE"] = f"{tl_base}_p{pipe}_{prec}"
                     t0 = time.perf_counter()
                     m = est.fit(feats, y)
                     _ = m.xs[-1][0, 0]          # the model is on the host when fit returns
                     ts.append(1e3 * (time.perf_counter() - t0))
+                os.environ.pop("KS_TIMELINE", None)
                 st = ctx.last_fit_stats()
                 print(json.dumps({"probe": "pipe_ab", "pass": rep, "pipeline": pipe, "precision": prec, "opts": cfg[2:],
                                   "ms": [round(t, 1) for t in ts], "device_ms": round(st["total_ms"], 1),
