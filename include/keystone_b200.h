@@ -163,6 +163,11 @@ KS_API int32_t ks_model_get_intercept(int64_t ctx, int64_t model, double* b_out,
  * stay valid until ks_model_destroy.  Any argument may be NULL.  (A JNI caller hands them to SetDoubleArrayRegion.) */
 KS_API int32_t ks_model_host_view(int64_t ctx, int64_t model, int32_t j, const double** W_ptr, const double** mean_ptr,
                                   const double** intercept_ptr);
+/* Fitted model <-> flat little-endian file ("KSB2MDL1", int32 block_size, int32 n_blocks, int64 k, int32 has_mean,
+ * int32 has_intercept, int64 rows[n_blocks], per block W (rows x k fp64 column-major) [+ rows means], k intercepts): replaces
+ * the Java-serialised FittedPipeline for the BlockLinearMapper stage (K/workflow/FittedPipeline.scala:18-22). */
+KS_API int32_t ks_model_save(int64_t ctx, int64_t model, const char* path);
+KS_API int32_t ks_model_load(int64_t ctx, const char* path, int64_t* out_model);
 /* BlockLinearMapper.apply(RDD) :40-73 -> new (N x k) matrix of predictions. */
 KS_API int32_t ks_model_apply(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
                        int64_t* out_predictions);
@@ -180,6 +185,21 @@ KS_API int32_t ks_model_confusion_matrix(int64_t ctx, int64_t model, int64_t fea
 KS_API int32_t ks_model_cost(int64_t ctx, int64_t model, int64_t features, int64_t x_in, const int64_t* rfs, int32_t n_rfs,
                       int64_t labels, double lambda, double* out_cost);
 KS_API int32_t ks_model_destroy(int64_t ctx, int64_t model);
+
+/* ---- on-disk formats at the edges of the path (host code; need no context) -----------------
+ * Headerless CSV of doubles (K/loaders/CsvDataLoader.scala:28-30): ks_csv_dims counts rows and the fields of the first row;
+ * ks_csv_read_* parse into a caller-owned row-major buffer (pinned memory makes the following upload asynchronous), split by
+ * lines over the host threads.  MNIST CSVs carry the 1-based label in column 0 (K/pipelines/images/mnist/MnistRandomFFT.scala:34-36). */
+KS_API const char* ks_io_last_error(void);
+KS_API int32_t ks_csv_dims(const char* path, int64_t* n_rows, int64_t* n_cols);
+KS_API int32_t ks_csv_read_f64(const char* path, double* out, int64_t n_rows, int64_t n_cols, int64_t ld);
+KS_API int32_t ks_csv_read_f32(const char* path, float* out, int64_t n_rows, int64_t n_cols, int64_t ld);
+/* TIMIT sparse label file, lines "row label", both 1-based (K/loaders/TimitFeaturesDataLoader.scala:22-42):
+ * labels_out[row - 1] = label - 1; rows the file does not mention keep -1. */
+KS_API int32_t ks_timit_labels_read(const char* path, int32_t* labels_out, int64_t n_rows);
+/* CIFAR-10 binary records, 1 label byte + 3072 image bytes (K/loaders/CifarLoader.scala:30-45).  With both output pointers NULL
+ * only *n_out (the record count) is set. */
+KS_API int32_t ks_cifar_read(const char* path, uint8_t* images_out, int32_t* labels_out, int64_t max_records, int64_t* n_out);
 
 /* ---- instrumentation ----------------------------------------------------------------------
  * JSON with per-phase device milliseconds of the last fit (featurize, gram, allreduce, solve, update),

@@ -12,6 +12,7 @@ from .nodes import (  # noqa: F401
     BlockWeightedLeastSquaresEstimator,
     ClassLabelIndicatorsFromIntLabels,
     CosineRandomFeatures,
+    LeastSquaresEstimator,
     LinearMapEstimator,
     LinearMapper,
     LinearRectifier,
@@ -20,6 +21,14 @@ from .nodes import (  # noqa: F401
     RandomSignNode,
     VectorCombiner,
     VectorSplitter,
+)
+from .loaders import (  # noqa: F401
+    CifarLoader,
+    CsvDataLoader,
+    LabeledData,
+    MnistCsvLoader,
+    TimitFeaturesDataLoader,
+    TimitLabelsLoader,
 )
 from .evaluation import (  # noqa: F401
     BinaryClassificationMetrics,

@@ -96,6 +96,14 @@ def _declare(L: C.CDLL) -> None:
     sig("ks_model_cost", i64, i64, i64, i64, p_i64, i32, i64, f64, p_f64)
     sig("ks_model_confusion_matrix", i64, i64, i64, i64, p_i64, i32, i64, C.c_void_p)
     sig("ks_model_destroy", i64, i64)
+    sig("ks_model_save", i64, i64, C.c_char_p)
+    sig("ks_model_load", i64, C.c_char_p, p_i64)
+    sig("ks_io_last_error", restype=C.c_char_p)
+    sig("ks_csv_dims", C.c_char_p, p_i64, p_i64)
+    sig("ks_csv_read_f64", C.c_char_p, C.c_void_p, i64, i64, i64)
+    sig("ks_csv_read_f32", C.c_char_p, C.c_void_p, i64, i64, i64)
+    sig("ks_timit_labels_read", C.c_char_p, C.c_void_p, i64)
+    sig("ks_cifar_read", C.c_char_p, C.c_void_p, C.c_void_p, i64, p_i64)
     sig("ks_last_fit_stats_json", i64, C.c_char_p, i64)
     sig("ks_debug_gram", i64, i64, i64, C.c_void_p, i64, C.c_void_p, i64)
     sig("ks_debug_time_gram", i64, i64, i64, i32, p_f64)

@@ -273,6 +273,13 @@ void Ctx::allreduce_f64(double* p, size_t n, bool prep) {
   if (world <= 1 || n == 0) return;
   KS_NCCL(nccl_api().AllReduce(p, p, n, ncclFloat64, ncclSum, prep ? comm2 : comm, prep ? st2 : st));
 }
+int* Ctx::next_tile_counter(cudaStream_t s) {
+  constexpr int kCounters = 256;
+  if (!tile_counters.p) tile_counters.alloc(sizeof(int) * kCounters);
+  int* p = tile_counters.as<int>() + (tile_counter_next++ % kCounters);
+  KS_CUDA(cudaMemsetAsync(p, 0, sizeof(int), s));
+  return p;
+}
 void Ctx::allreduce_on(void* p, size_t n, bool f64, ncclComm_t cm, cudaStream_t s) {
   if (world <= 1 || n == 0) return;
   KS_NCCL(nccl_api().AllReduce(p, p, n, f64 ? ncclFloat64 : ncclFloat32, ncclSum, cm, s));
@@ -560,6 +567,7 @@ void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* s
   // the projection kernel is persistent (one CTA per SM for its whole duration); on the look-ahead stream leave a few SMs
   // free so that the critical chain's small kernels (NCCL all-reduce, triangular solves) can always be scheduled
   k.num_sms = (st == c.st2) ? std::max(1, c.num_sms - c.reserve_sms) : c.num_sms;
+  if (c.dyn_tiles) k.p.tile_counter = c.next_tile_counter(st);
   KS_CUDA(launch_kmajor(k, st));
   c.launches += 1;
 }
@@ -1429,6 +1437,7 @@ KS_API int32_t ks_ctx_destroy(int64_t ctx) {
   if (c->comm) nccl_api().CommDestroy(c->comm);
   c->solver_work.release();
   c->dev_info.release();
+  c->tile_counters.release();
   cudaStreamDestroy(c->st);
   if (c->st2) cudaStreamDestroy(c->st2);
   if (c->st3) cudaStreamDestroy(c->st3);
@@ -1469,6 +1478,7 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     else if (n == "custom_solve") c.custom_solve = value != 0;
     else if (n == "reserve_sms" && value >= 0 && value < 148) c.reserve_sms = static_cast<int>(value);
     else if (n == "pipeline" && value >= 0 && value <= 2) c.pipeline = static_cast<int>(value);
+    else if (n == "dyn_tiles") c.dyn_tiles = value != 0;
     else if (n == "solve_lanes" && value >= 1 && value <= 16) c.solve_lanes = static_cast<int>(value);
     else if (n == "host_mirror") c.host_mirror = value != 0;
     else if (n == "timing") c.timing = value != 0;
@@ -1797,21 +1807,104 @@ KS_API int32_t ks_model_get_block(int64_t ctx, int64_t model, int32_t j, double*
     KS_CUDA(cudaStreamSynchronize(c.st));
   });
 }
+static void ensure_host_mirror(Ctx& c, Model& m) {
+  if (m.host_valid) return;
+  model_alloc_host(m);
+  for (int q = 0; q < static_cast<int>(m.brows.size()); ++q) model_block_to_host(m, q, c.st);
+  model_intercept_to_host(m, c.st);
+  KS_CUDA(cudaStreamSynchronize(c.st));
+}
 KS_API int32_t ks_model_host_view(int64_t ctx, int64_t model, int32_t j, const double** W_ptr, const double** mean_ptr,
                                   const double** intercept_ptr) {
   return guard(ctx, [&](Ctx& c) {
     Model& m = c.model(model);
     if (j < 0 || j >= static_cast<int>(m.brows.size())) throw KsError{KS_ERR_INVALID, "block index out of range"};
-    if (!m.host_valid) {  // models that were not fitted with the mirror on (or came from the host): mirror now
-      model_alloc_host(m);
-      for (int q = 0; q < static_cast<int>(m.brows.size()); ++q) model_block_to_host(m, q, c.st);
-      model_intercept_to_host(m, c.st);
-      KS_CUDA(cudaStreamSynchronize(c.st));
-    }
+    ensure_host_mirror(c, m);  // models that were not fitted with the mirror on (or came from the host): mirror now
     const uint8_t* h = static_cast<const uint8_t*>(m.host.p);
     if (W_ptr) *W_ptr = reinterpret_cast<const double*>(h + m.host_w_off[j]);
     if (mean_ptr) *mean_ptr = m.has_mean ? reinterpret_cast<const double*>(h + m.host_mean_off[j]) : nullptr;
     if (intercept_ptr) *intercept_ptr = m.has_intercept ? reinterpret_cast<const double*>(h + m.host_b_off) : nullptr;
+  });
+}
+// Flat model file (little endian): "KSB2MDL1", int32 block_size, int32 n_blocks, int64 k, int32 has_mean, int32 has_intercept,
+// int64 rows[n_blocks], then per block W (rows x k fp64, column-major) [+ rows means], then k intercepts.  Replaces the
+// Java-serialised FittedPipeline of the reference (K/workflow/FittedPipeline.scala:18-22) for the BlockLinearMapper stage.
+KS_API int32_t ks_model_save(int64_t ctx, int64_t model, const char* path) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!path) throw KsError{KS_ERR_INVALID, "null path"};
+    Model& m = c.model(model);
+    ensure_host_mirror(c, m);
+    FILE* f = fopen(path, "wb");
+    if (!f) throw KsError{KS_ERR_INVALID, std::string("cannot open ") + path + " for writing"};
+    const int32_t hdr[2] = {m.block_size, static_cast<int32_t>(m.brows.size())};
+    const int64_t k = m.k;
+    const int32_t flags[2] = {m.has_mean ? 1 : 0, m.has_intercept ? 1 : 0};
+    bool ok = fwrite("KSB2MDL1", 1, 8, f) == 8 && fwrite(hdr, sizeof(hdr), 1, f) == 1 && fwrite(&k, sizeof(k), 1, f) == 1 &&
+              fwrite(flags, sizeof(flags), 1, f) == 1 && fwrite(m.brows.data(), sizeof(int64_t), m.brows.size(), f) == m.brows.size();
+    const uint8_t* h = static_cast<const uint8_t*>(m.host.p);
+    for (size_t j = 0; ok && j < m.brows.size(); ++j) {
+      const size_t nw = static_cast<size_t>(m.brows[j]) * m.k;
+      ok = fwrite(h + m.host_w_off[j], sizeof(double), nw, f) == nw;
+      if (ok && m.has_mean) ok = fwrite(h + m.host_mean_off[j], sizeof(double), m.brows[j], f) == static_cast<size_t>(m.brows[j]);
+    }
+    if (ok && m.has_intercept) ok = fwrite(h + m.host_b_off, sizeof(double), m.k, f) == static_cast<size_t>(m.k);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) throw KsError{KS_ERR_INVALID, std::string("short write to ") + path};
+  });
+}
+KS_API int32_t ks_model_load(int64_t ctx, const char* path, int64_t* out_model) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!path || !out_model) throw KsError{KS_ERR_INVALID, "null argument"};
+    FILE* f = fopen(path, "rb");
+    if (!f) throw KsError{KS_ERR_INVALID, std::string("cannot open ") + path};
+    struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+    char magic[8];
+    int32_t hdr[2], flags[2];
+    int64_t k = 0;
+    if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "KSB2MDL1", 8) != 0) throw KsError{KS_ERR_INVALID, "not a keystone_b200 model file"};
+    if (fread(hdr, sizeof(hdr), 1, f) != 1 || fread(&k, sizeof(k), 1, f) != 1 || fread(flags, sizeof(flags), 1, f) != 1 ||
+        hdr[0] <= 0 || hdr[1] <= 0 || hdr[1] > (1 << 20) || k <= 0)
+      throw KsError{KS_ERR_INVALID, "corrupt model header"};
+    auto m = std::make_unique<Model>();
+    m->block_size = hdr[0];
+    m->k = k;
+    m->has_mean = flags[0] != 0;
+    m->has_intercept = flags[1] != 0;
+    m->brows.resize(hdr[1]);
+    if (fread(m->brows.data(), sizeof(int64_t), m->brows.size(), f) != m->brows.size()) throw KsError{KS_ERR_INVALID, "truncated model file"};
+    for (auto r : m->brows)
+      if (r <= 0 || r > m->block_size) throw KsError{KS_ERR_INVALID, "corrupt model header (block rows)"};
+    for (size_t j = 0; j < m->brows.size(); ++j) {
+      auto W = std::make_unique<DevBuf>();
+      W->alloc(sizeof(double) * static_cast<size_t>(m->brows[j]) * k);
+      m->W.push_back(std::move(W));
+      if (m->has_mean) {
+        auto mu = std::make_unique<DevBuf>();
+        mu->alloc(sizeof(double) * static_cast<size_t>(m->brows[j]));
+        m->mean.push_back(std::move(mu));
+      }
+    }
+    m->intercept.alloc(sizeof(double) * static_cast<size_t>(k));
+    model_alloc_host(*m);   // the file is read straight into the pinned mirror, then copied to the device
+    uint8_t* h = static_cast<uint8_t*>(m->host.p);
+    for (size_t j = 0; j < m->brows.size(); ++j) {
+      const size_t nw = static_cast<size_t>(m->brows[j]) * k;
+      if (fread(h + m->host_w_off[j], sizeof(double), nw, f) != nw) throw KsError{KS_ERR_INVALID, "truncated model file"};
+      KS_CUDA(cudaMemcpyAsync(m->W[j]->p, h + m->host_w_off[j], sizeof(double) * nw, cudaMemcpyHostToDevice, c.st));
+      if (m->has_mean) {
+        if (fread(h + m->host_mean_off[j], sizeof(double), m->brows[j], f) != static_cast<size_t>(m->brows[j]))
+          throw KsError{KS_ERR_INVALID, "truncated model file"};
+        KS_CUDA(cudaMemcpyAsync(m->mean[j]->p, h + m->host_mean_off[j], sizeof(double) * m->brows[j], cudaMemcpyHostToDevice, c.st));
+      }
+    }
+    if (m->has_intercept) {
+      if (fread(h + m->host_b_off, sizeof(double), k, f) != static_cast<size_t>(k)) throw KsError{KS_ERR_INVALID, "truncated model file"};
+      KS_CUDA(cudaMemcpyAsync(m->intercept.p, h + m->host_b_off, sizeof(double) * k, cudaMemcpyHostToDevice, c.st));
+    } else {
+      KS_CUDA(cudaMemsetAsync(m->intercept.p, 0, sizeof(double) * k, c.st));
+    }
+    KS_CUDA(cudaStreamSynchronize(c.st));
+    *out_model = c.add(std::move(m));
   });
 }
 KS_API int32_t ks_model_get_intercept(int64_t ctx, int64_t model, double* b_out, int32_t* has_intercept) {

@@ -216,6 +216,10 @@ struct Ctx {
   void allreduce_f32(float* p, size_t n, bool prep = false);
   void allreduce_f64(double* p, size_t n, bool prep = false);
   void allreduce_on(void* p, size_t n, bool f64, ncclComm_t cm, cudaStream_t s);
+  DevBuf tile_counters;  // ring of zero-initialised tile counters for the persistent projection kernel (one per launch in flight)
+  int tile_counter_next = 0;
+  int dyn_tiles = 1;     // the projection kernel draws its tiles from a counter (0: static striding)
+  int* next_tile_counter(cudaStream_t s);
   std::vector<cudaEvent_t> fit_events;  // events of the fit in flight (returned to event_pool when it ends, also on error)
   void allreduce_max_u32(unsigned* p, size_t n);
   void ensure_solver();

@@ -37,6 +37,7 @@ struct KmParams {
   float* colsum;      // EPI_COS: if non-null, colsum[n] += sum over valid rows of the stored values (fp32 atomics)
   float acc_scale = 1.f;    // the accumulator is multiplied by this before the epilogue (undoes power-of-two operand scaling)
   const float* acc_scale_ptr = nullptr;  // optional device scalar multiplied into acc_scale (scale chosen on the device)
+  int* tile_counter = nullptr;  // persistent single-CTA kernel: zeroed device counter the CTAs draw their tiles from (null: static stride)
   int M, N, K;
   int flags;  // KM_FLAG_NO_ROUND: EPI_COS keeps fp32;  KM_FLAG_REDUCE: add into the output instead of overwriting it
 };

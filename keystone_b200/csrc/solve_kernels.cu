@@ -33,30 +33,49 @@ __device__ __forceinline__ void dmma(double (&d)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
-// acc[g] (8 rows x 8 columns per n-group g) += A[8 x K] * Bm[K x 8 NG] over K = [k0, k1) (multiples of 4 * U), read from L2.
+// acc[g] (8 rows x 8 columns per n-group g) += A[8 x K] * Bm[K x 8 NG] over K = [k0, k1) (multiples of 4 * U).
 //   A(m, kk)  = TRANS ? Aptr[kk + m * lda] : Aptr[m + kk * lda]     m = lane / 4, kk = lane % 4 (+ 4 per step)
 //   Bm(kk, c) = Bptr[kk + c * ldb]                                   kk = lane % 4, c = lane / 4 (+ 8 per n-group)
 // Rows kk >= krow_limit of A / Bm and A rows m >= mrow_limit read as zero (ragged edges).
+// A (the factor) streams from L2 and is prefetched one 64-row chunk ahead (its latency hides behind the 16 NG DMMAs of the
+// current chunk); Bm (rows this CTA solved earlier) is read through L1, where the eight warps of the CTA share it.
 template <int NG, bool TRANS>
 __device__ __forceinline__ void bulk_dmma(double (&acc)[NG][2], const double* __restrict__ Aptr, size_t lda, int mrow_limit,
                                           const double* Bptr, size_t ldb, const bool (&col_ok)[NG], int k0, int k1, int krow_limit,
                                           int lane) {
   const int m = lane >> 2, kq = lane & 3;
   const bool m_ok = m < mrow_limit;
-  for (int kb = k0; kb < k1; kb += 4 * U) {
-    double a[U], b[U][NG];
+  if (k0 >= k1) return;
+  double a[U], an[U];
+  auto load_a = [&](double (&dst)[U], int kb) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int kk = kb + 4 * u + kq;
-      const bool ok = kk < krow_limit;
-      a[u] = (ok && m_ok) ? __ldg(TRANS ? Aptr + kk + static_cast<size_t>(m) * lda : Aptr + m + static_cast<size_t>(kk) * lda) : 0.0;
-#pragma unroll
-      for (int g = 0; g < NG; ++g) b[u][g] = (ok && col_ok[g]) ? __ldcg(Bptr + kk + static_cast<size_t>(8 * g + m) * ldb) : 0.0;
+      dst[u] = (kk < krow_limit && m_ok) ? __ldg(TRANS ? Aptr + kk + static_cast<size_t>(m) * lda : Aptr + m + static_cast<size_t>(kk) * lda) : 0.0;
     }
+  };
+  load_a(a, k0);
+  for (int kb = k0; kb < k1; kb += 4 * U) {
+    const bool more = kb + 4 * U < k1;
+    if (more) load_a(an, kb + 4 * U);
 #pragma unroll
-    for (int u = 0; u < U; ++u)
+    for (int h = 0; h < 2; ++h) {   // two half-chunks: 8 steps of B operands in registers at a time
+      double b[U / 2][NG];
 #pragma unroll
-      for (int g = 0; g < NG; ++g) dmma(acc[g], a[u], b[u][g]);
+      for (int u = 0; u < U / 2; ++u) {
+        const int kk = kb + 4 * (h * (U / 2) + u) + kq;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) b[u][g] = (kk < krow_limit && col_ok[g]) ? Bptr[kk + static_cast<size_t>(8 * g + m) * ldb] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U / 2; ++u)
+#pragma unroll
+        for (int g = 0; g < NG; ++g) dmma(acc[g], a[h * (U / 2) + u], b[u][g]);
+    }
+    if (more) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) a[u] = an[u];
+    }
   }
 }
 }  // namespace
@@ -64,7 +83,7 @@ __device__ __forceinline__ void bulk_dmma(double (&acc)[NG][2], const double* __
 // 8 warps: warp w owns rows 8 w .. 8 w + 8 of the current 64-row tile.  Shared memory: the 64 x NC tile right-hand side only
 // (10 KB at NC = 16), registers ~130 x 256 threads: a CTA fits beside a Gram CTA (209 KB shared, 14 K registers) on one SM.
 template <int NC>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __maxnreg__(168)
 chol_solve_kernel(const double* __restrict__ L, const double* __restrict__ Dinv, int n, double* B, int k) {
   constexpr int NG = NC / 8;
   constexpr int VP = NC + 4;                 // pitch of sV: conflict-free B-fragment reads (k * VP + c distinct mod 16)
@@ -97,7 +116,7 @@ chol_solve_kernel(const double* __restrict__ L, const double* __restrict__ Dinv,
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int row = r0 + m, col = c0 + 8 * g + 2 * cq + e;
-          const double bv = (row < n && col < k) ? __ldcg(B + row + static_cast<size_t>(col) * ld) : 0.0;
+          const double bv = (row < n && col < k) ? B[row + static_cast<size_t>(col) * ld] : 0.0;
           sV[(8 * rg + m) * VP + 8 * g + 2 * cq + e] = bv - acc[g][e];
         }
       __syncthreads();
@@ -123,7 +142,7 @@ chol_solve_kernel(const double* __restrict__ L, const double* __restrict__ Dinv,
           const int row = r0 + m, col = c0 + 8 * g + 2 * cq + e;
           if (row < n && col < k) B[row + static_cast<size_t>(col) * ld] = y[g][e];
         }
-      __syncthreads();  // the solved rows are visible to every warp of the CTA (they are read back through L2) before the next tile
+      __syncthreads();  // the solved rows are visible to every warp of the CTA before the next tile reads them back
     }
   }
 }

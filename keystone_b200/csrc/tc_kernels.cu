@@ -396,7 +396,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* ring_bar = tempty_bar + 2;       // [8] tile-id ring: the producer publishes, MMA issuer and epilogue warps consume
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ring_bar + 8);
+  int* tile_ring = reinterpret_cast<int*>(tmem_slot + 2);  // [8]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -421,6 +423,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_init(&tfull_bar[a], 1);
         mbar_init(&tempty_bar[a], 8);  // one arrive per epilogue warp
       }
+      for (int r = 0; r < 8; ++r) mbar_init(&ring_bar[r], 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -432,10 +435,20 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Tile schedule.  With p.tile_counter the CTAs draw tiles from a global counter: a CTA that got its SM late (this kernel is
+  // persistent and shares the GPU with the factor / solve chains' kernels) simply takes fewer tiles instead of stretching the
+  // whole launch by its late start.  Without a counter the tiles are strided statically.  Either way the producer publishes
+  // every tile id (then -1) in an 8-slot ring; it never runs more than ~3 tiles ahead of the epilogue, so slots are free.
   if (warp == 0) {
     if (elect_one()) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      uint32_t it = 0, tl = 0;
+      int next = p.tile_counter ? atomicAdd(p.tile_counter, 1) : static_cast<int>(blockIdx.x);
+      for (;; ++tl) {
+        const int t = next < total_tiles ? next : -1;
+        tile_ring[tl & 7] = t;
+        mbar_arrive(&ring_bar[tl & 7]);
+        if (t < 0) break;
+        next = p.tile_counter ? atomicAdd(p.tile_counter, 1) : t + static_cast<int>(gridDim.x);  // latency hides under this tile
         const int m0 = (t / n_tiles) * Cfg::BM;
         const int n0 = (t % n_tiles) * BN;
         for (int ks = 0; ks < ksteps; ++ks, ++it) {
@@ -453,7 +466,9 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (elect_one()) {
       constexpr uint32_t idesc = F16 ? make_idesc_f16(Cfg::BM, BN, 0, 0) : make_idesc_tf32(Cfg::BM, BN, 0, 0);
       uint32_t it = 0, tl = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      for (;; ++tl) {
+        mbar_wait(&ring_bar[tl & 7], (tl >> 3) & 1);
+        if (tile_ring[tl & 7] < 0) break;
         const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
         mbar_wait(&tempty_bar[a], aph ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
@@ -488,7 +503,10 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint8_t* buf = staging + ew * 4096;
     const float ascale = p.acc_scale_ptr ? __ldg(p.acc_scale_ptr) * p.acc_scale : p.acc_scale;
     uint32_t tl = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+    for (;; ++tl) {
+      mbar_wait(&ring_bar[tl & 7], (tl >> 3) & 1);
+      const int t = tile_ring[tl & 7];
+      if (t < 0) break;
       const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
       const int m0 = (t / n_tiles) * Cfg::BM;
       const int n0 = (t % n_tiles) * BN + half * 128;

@@ -330,6 +330,16 @@ class BlockLinearMapper(Transformer):
         check(self.ctx.handle, lib().ks_model_host_view(self.ctx.handle, self.handle, 0, None, None, C.byref(bp)))
         return self._view(bp.value, (self.k,), "C") if bp.value else None
 
+    # ---- persistence (replaces the Java-serialised FittedPipeline, K/workflow/FittedPipeline.scala:18-22) ----
+    def save(self, path: str) -> None:
+        check(self.ctx.handle, lib().ks_model_save(self.ctx.handle, self.handle, path.encode()))
+
+    @classmethod
+    def load(cls, ctx: Context, path: str) -> "BlockLinearMapper":
+        h = C.c_int64(0)
+        check(ctx.handle, lib().ks_model_load(ctx.handle, path.encode(), C.byref(h)))
+        return cls(ctx, h.value)
+
     # ---- apply ----
     def apply(self, data):
         single = isinstance(data, np.ndarray) and data.ndim == 1
@@ -449,6 +459,62 @@ class LinearMapEstimator(LabelEstimator):
         check(ctx.handle, lib().ks_linear_map_fit(ctx.handle, ds.handle, lb.handle, 0 if self.lam is None else 1,
                                                    0.0 if self.lam is None else float(self.lam), C.byref(h)))
         return LinearMapper(ctx, h.value)
+
+
+class LeastSquaresEstimator(LabelEstimator, WeightedNode):
+    """The reference's cost-model-driven solver choice (K/nodes/learning/LeastSquaresEstimator.scala:17-87): the four
+    options' ``CostModel.cost`` formulas -- dense L-BFGS (K/nodes/learning/LBFGS.scala:175-191), sparse L-BFGS (:264-280),
+    ``BlockLeastSquaresEstimator(1000, 3, lambda)`` (BlockLinearMapper.scala:268-282) and ``LinearMapEstimator(Some(lambda))``
+    (LinearMapper.scala:100-115) -- with the reference's empirical weights; ``optimize`` returns the cheapest.
+
+    On this engine the two direct solvers run on the GPU.  The L-BFGS options are not part of the hot path: when
+    the cost model prefers one of them, ``fit`` runs the GPU block solver instead and records both in ``selected`` / ``used``."""
+
+    def __init__(self, lam: float = 0.0, num_machines: Optional[int] = None, cpu_weight: float = 3.8e-4, mem_weight: float = 2.9e-1,
+                 network_weight: float = 1.32, ctx: Optional[Context] = None):
+        self.lam, self.num_machines, self.ctx = lam, num_machines, ctx
+        self.cpu_weight, self.mem_weight, self.network_weight = cpu_weight, mem_weight, network_weight
+        self.weight = 20 + 1          # default = DenseLBFGSwithL2(numIterations = 20): weight numIterations + 1 (LBFGS.scala)
+        self.selected: Optional[str] = None
+        self.used: Optional[str] = None
+
+    @staticmethod
+    def _lbfgs_cost(n, d, k, sparsity, m, cw, mw, nw, sparse: bool, num_iterations: int = 20, sparse_overhead: float = 8.0):
+        dens = sparsity if sparse else 1.0
+        flops = float(n) * dens * d * k / m
+        bytes_scanned = float(n) * d * dens / m
+        network = 2.0 * d * k * math.log(m) / math.log(2.0)
+        return num_iterations * ((sparse_overhead if sparse else 1.0) * max(cw * flops, mw * bytes_scanned) + nw * network)
+
+    def costs(self, n: int, d: int, k: int, sparsity: float, num_machines: int) -> dict:
+        cw, mw, nw = self.cpu_weight, self.mem_weight, self.network_weight
+        block = BlockLeastSquaresEstimator(1000, 3, self.lam)
+        exact_flops = float(n) * d * (d + k) / num_machines
+        exact_bytes = float(n) * d / num_machines + float(d) * d
+        return {
+            "dense_lbfgs": self._lbfgs_cost(n, d, k, sparsity, num_machines, cw, mw, nw, False),
+            "sparse_lbfgs": self._lbfgs_cost(n, d, k, sparsity, num_machines, cw, mw, nw, True),
+            "block": block.cost(n, d, k, sparsity, num_machines, cw, mw, nw),
+            "exact": max(cw * exact_flops, mw * exact_bytes) + nw * float(d) * (d + k),
+        }
+
+    def optimize(self, n: int, d: int, k: int, sparsity: float = 1.0, num_machines: Optional[int] = None) -> str:
+        """``options.minBy(cost)`` (:83); ties resolve in the reference's option order."""
+        m = num_machines or self.num_machines or 1
+        c = self.costs(n, d, k, sparsity, m)
+        self.selected = min(("dense_lbfgs", "sparse_lbfgs", "block", "exact"), key=lambda name: c[name])
+        return self.selected
+
+    def fit(self, data, labels) -> BlockLinearMapper:
+        ds = _as_dataset(self.ctx, data)
+        lb = _as_dataset(ds.ctx, labels)
+        n_total = ds.rows * max(1, ds.ctx.world_size)
+        choice = self.optimize(n_total, ds.cols, lb.cols, 1.0, self.num_machines or ds.ctx.world_size)
+        if choice == "exact":
+            self.used = "exact"
+            return LinearMapEstimator(self.lam, ds.ctx).fit(ds, lb)
+        self.used = "block"
+        return BlockLeastSquaresEstimator(1000, 3, self.lam, ctx=ds.ctx).fit(ds, lb)
 
 
 class StandardScalerModel(Transformer):

@@ -160,3 +160,20 @@ def test_multiclass_metrics_host_formulas_match_the_reference_suite():
                          (m.avgAccuracy, o["avg_accuracy"]), (m.avgError, o["avg_error"])]:
         assert abs(mine - theirs) < 1e-12
     assert abs(m.macroFScore(2.0) - ko.multiclass_metrics(cm, beta=2.0)["macro_fscore"]) < 1e-12
+
+
+def test_least_squares_estimator_cost_model_selection():
+    """T/nodes/learning/LeastSquaresEstimatorSuite.scala:11-102: with the reference's weights and 16 machines the cost model picks
+    the exact solver for (n=1e6, d=1000, k=1000), the block solver for (n=1e6, d=10000, k=1000) and sparse L-BFGS for
+    (n=1e6, d=10000, k=2, sparsity 0.01)."""
+    import keystone_b200 as ks
+    est = ks.LeastSquaresEstimator(num_machines=16)
+    assert est.optimize(1_000_000, 1000, 1000, 1.0) == "exact"
+    assert est.optimize(1_000_000, 10000, 1000, 1.0) == "block"
+    assert est.optimize(1_000_000, 10000, 2, 0.01) == "sparse_lbfgs"
+    c = est.costs(1_000_000, 10000, 1000, 1.0, 16)
+    # BlockLinearMapper.scala:268-282 with blockSize 1000, 3 iterations
+    flops = 1e6 * 10000 * (1000 + 1000) / 16
+    bytes_scanned = 1e6 * 10000 / 16 + 10000.0 * 1000
+    network = 2.0 * 10000 * (1000 + 1000) * 4.0
+    assert abs(c["block"] - 3 * (max(3.8e-4 * flops, 2.9e-1 * bytes_scanned) + 1.32 * network)) < 1e-6 * c["block"]

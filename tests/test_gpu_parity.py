@@ -552,3 +552,29 @@ def test_mnist_random_fft_pipeline_matches_oracle(ctx):
     mfast = ks.BlockLeastSquaresEstimator(bs, 1, lam, precision="f16").fit(feats, y)
     assert ctx.last_fit_stats()["mma"] == "tf32x1"
     assert np.linalg.norm(np.concatenate(mfast.xs, 0) - Wr) / np.linalg.norm(Wr) < W_TOL_FAST
+
+
+def test_model_save_load_round_trip(ctx, tmp_path):
+    """Fitted model -> flat file -> model (replaces the Java-serialised FittedPipeline, K/workflow/FittedPipeline.scala:18-22):
+    bit-identical arrays and identical predictions; a BWLS model (no feature scalers) survives too."""
+    rng = np.random.default_rng(8)
+    F = rng.standard_normal((500, 70)); Y = rng.standard_normal((500, 3))
+    f = ctx.matrix(F)
+    m = ks.BlockLeastSquaresEstimator(32, 1, 1.0).fit(f, ctx.matrix(Y))
+    p = str(tmp_path / "model.ksb")
+    m.save(p)
+    m2 = ks.BlockLinearMapper.load(ctx, p)
+    assert m2.num_blocks == 3 and m2.k == 3 and m2.block_size == 32
+    assert all(np.array_equal(a, b) for a, b in zip(m.xs, m2.xs))
+    assert all(np.array_equal(a, b) for a, b in zip(m.feature_means, m2.feature_means))
+    assert np.array_equal(m.b_opt, m2.b_opt)
+    assert np.array_equal(m(f).to_numpy(), m2(f).to_numpy())
+    cls = rng.integers(0, 3, 500)
+    mw = ks.BlockWeightedLeastSquaresEstimator(32, 1, 0.1, 0.3).fit(f, ctx.labels_from_classes(cls, 3))
+    mw.save(p)
+    mw2 = ks.BlockLinearMapper.load(ctx, p)
+    assert mw2.feature_means is None and np.array_equal(mw.b_opt, mw2.b_opt)
+    assert all(np.array_equal(a, b) for a, b in zip(mw.xs, mw2.xs))
+    with pytest.raises(ks.KeystoneError):
+        (tmp_path / "junk").write_bytes(b"not a model")
+        ks.BlockLinearMapper.load(ctx, str(tmp_path / "junk"))

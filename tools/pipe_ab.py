@@ -27,15 +27,17 @@ def main():
         for rep in range(2):
             for cfg in configs:
                 pipe, prec = int(cfg[0]), cfg[1]
+                opts = {"custom_solve": 1, "dyn_tiles": 1, "gram_chunk_rows": 0}     # defaults, so that configs do not leak
+                opts.update({name: int(val) for name, val in (o.split("=") for o in cfg[2:])})
                 ctx.set_option("pipeline", pipe)
-                for name, val in (o.split("=") for o in cfg[2:]):
-                    ctx.set_option(name, int(val))
+                for name, val in opts.items():
+                    ctx.set_option(name, val)
                 est = ks.BlockLeastSquaresEstimator(n_out, 1, 1.0, precision=prec)
                 est.fit(feats, y)
                 ts = []
                 for i in range(3):
                     if tl_base and i == 2:
-                        os.environ["KS_TIMELINE"] = f"{tl_base}_p{pipe}_{prec}"
+                        os.environ["KS_TIMELINE"] = f"{tl_base}_p{pipe}_{prec}" + "".join("_" + o.replace("=", "") for o in cfg[2:])
                     t0 = time.perf_counter()
                     m = est.fit(feats, y)
                     _ = m.xs[-1][0, 0]          # the model is on the host when fit returns
