@@ -83,7 +83,8 @@ KS_API int32_t ks_ctx_synchronize(int64_t ctx);
  * right-hand-side columns over the ranks], "reserve_sms" [8], "timing" [1], "pipeline" [1: all tensor-core kernels of a fit on
  * one stream, solve / factor chains beside it; 0: the two-stream arrangement of round 1], "host_mirror" [1: fits copy each
  * finished model block into pinned host memory while they run]; "custom_solve" [0: cusolverDnDpotrs; 1: the library's
- * own multi-right-hand-side triangular solve kernel]. */
+ * own DMMA multi-right-hand-side triangular solve kernel], "dyn_tiles" [1: the projection kernel draws its tiles from a
+ * counter], "solve_lanes" [4: concurrent per-class solves of the weighted solver]. */
 KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value);
 
 /* ---- row-sharded matrices (this rank's rows) ---------------------------------------------
@@ -93,6 +94,11 @@ KS_API int32_t ks_matrix_from_host_f64(int64_t ctx, const double* rowmajor, int6
                                 int64_t* out_m);
 KS_API int32_t ks_matrix_from_host_f32(int64_t ctx, const float* rowmajor, int64_t n_rows, int64_t n_cols, int64_t ld,
                                 int64_t* out_m);
+/* A zero matrix filled by row ranges afterwards: how an executor uploads its RDD partitions one at a time
+ * (mapPartitionsWithIndex + MatrixUtils.rowsToMatrix per partition, K/utils/MatrixUtils.scala:48-93). */
+KS_API int32_t ks_matrix_create(int64_t ctx, int64_t n_rows, int64_t n_cols, int64_t* out_m);
+KS_API int32_t ks_matrix_write_rows_f64(int64_t ctx, int64_t m, int64_t row0, const double* rowmajor, int64_t n_rows, int64_t ld);
+KS_API int32_t ks_matrix_write_rows_f32(int64_t ctx, int64_t m, int64_t row0, const float* rowmajor, int64_t n_rows, int64_t ld);
 /* iid N(mean, stddev) generated on the device (benchmarks; counter-based, reproducible per (seed,row,col)). */
 KS_API int32_t ks_matrix_synthetic_normal(int64_t ctx, int64_t n_rows, int64_t n_cols, uint64_t seed, int64_t global_row_offset,
                                    double mean, double stddev, int64_t* out_m);

@@ -70,6 +70,9 @@ def _declare(L: C.CDLL) -> None:
     sig("ks_ctx_launch_count", i64, p_i64)
     sig("ks_matrix_from_host_f64", i64, C.c_void_p, i64, i64, i64, p_i64)
     sig("ks_matrix_from_host_f32", i64, C.c_void_p, i64, i64, i64, p_i64)
+    sig("ks_matrix_create", i64, i64, i64, p_i64)
+    sig("ks_matrix_write_rows_f64", i64, i64, i64, C.c_void_p, i64, i64)
+    sig("ks_matrix_write_rows_f32", i64, i64, i64, C.c_void_p, i64, i64)
     sig("ks_matrix_synthetic_normal", i64, i64, i64, u64, i64, f64, f64, p_i64)
     sig("ks_labels_from_classes", i64, C.c_void_p, i64, i32, p_i64)
     sig("ks_matrix_shape", i64, i64, p_i64, p_i64)

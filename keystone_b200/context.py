@@ -110,6 +110,23 @@ class Context:
         check(self.handle, fn(self.handle, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1], a.shape[1], C.byref(h)))
         return DeviceMatrix(self, h.value, a.shape[0], a.shape[1])
 
+    def matrix_from_partitions(self, parts: Sequence[np.ndarray]) -> "DeviceMatrix":
+        """One device matrix from several host row chunks (an executor's RDD partitions), uploaded chunk by chunk."""
+        parts = [np.atleast_2d(np.asarray(p)) for p in parts]
+        rows, cols = sum(p.shape[0] for p in parts), parts[0].shape[1]
+        h = C.c_int64(0)
+        check(self.handle, lib().ks_matrix_create(self.handle, rows, cols, C.byref(h)))
+        out = DeviceMatrix(self, h.value, rows, cols)
+        r0 = 0
+        for p in parts:
+            if p.dtype == np.float32:
+                a, fn = np.ascontiguousarray(p), lib().ks_matrix_write_rows_f32
+            else:
+                a, fn = np.ascontiguousarray(p, dtype=np.float64), lib().ks_matrix_write_rows_f64
+            check(self.handle, fn(self.handle, h.value, r0, a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1]))
+            r0 += a.shape[0]
+        return out
+
     def synthetic_normal(self, n_rows: int, n_cols: int, seed: int, global_row_offset: int = 0, mean: float = 0.0,
                          stddev: float = 1.0) -> "DeviceMatrix":
         h = C.c_int64(0)

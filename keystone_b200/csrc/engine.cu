@@ -1131,6 +1131,12 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     for (int t = 0; t < T; ++t) {
       do_cgram(t);
       do_solve(t);
+      if (c.pipeline == 3) {  // the solve runs beside the projection (persistent kernel that leaves reserve_sms SMs free)
+        if (t + 2 < T) do_proj(t + 2);
+        do_update(t);
+        if (t + 1 < T) do_gram(t + 1);
+        continue;
+      }
       if (t + 1 < T) do_gram(t + 1);
       if (c.pipeline == 2 && t + 2 < T) do_proj(t + 2);
       do_update(t);
@@ -1373,7 +1379,7 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
       c->precision = (atoi(e) == 1 || !strcmp(e, "f16")) ? KS_PRECISION_F16 : (atoi(e) == 2 || !strcmp(e, "f16x2") || !strcmp(e, "parity")) ? KS_PRECISION_F16X2 : KS_PRECISION_TF32;
     if (const char* e = getenv("KS_CUSTOM_SOLVE")) c->custom_solve = atoi(e) != 0;
     if (const char* e = getenv("KS_RESERVE_SMS")) c->reserve_sms = std::max(0, std::min(140, atoi(e)));
-    if (const char* e = getenv("KS_PIPELINE")) c->pipeline = std::max(0, std::min(2, atoi(e)));
+    if (const char* e = getenv("KS_PIPELINE")) c->pipeline = std::max(0, std::min(3, atoi(e)));
     if (const char* e = getenv("KS_HOST_MIRROR")) c->host_mirror = atoi(e) != 0;
     KS_CUDA(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, prio_least));
     KS_CUDA(cudaStreamCreateWithPriority(&c->st3, cudaStreamNonBlocking, prio_mid));
@@ -1477,7 +1483,7 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     else if (n == "precision" && (value == KS_PRECISION_TF32 || value == KS_PRECISION_F16 || value == KS_PRECISION_F16X2)) c.precision = static_cast<int>(value);
     else if (n == "custom_solve") c.custom_solve = value != 0;
     else if (n == "reserve_sms" && value >= 0 && value < 148) c.reserve_sms = static_cast<int>(value);
-    else if (n == "pipeline" && value >= 0 && value <= 2) c.pipeline = static_cast<int>(value);
+    else if (n == "pipeline" && value >= 0 && value <= 3) c.pipeline = static_cast<int>(value);
     else if (n == "dyn_tiles") c.dyn_tiles = value != 0;
     else if (n == "solve_lanes" && value >= 1 && value <= 16) c.solve_lanes = static_cast<int>(value);
     else if (n == "host_mirror") c.host_mirror = value != 0;
@@ -1530,6 +1536,50 @@ KS_API int32_t ks_matrix_from_host_f32(int64_t ctx, const float* rowmajor, int64
     upload_rows(c, *m, rowmajor, ld, false);
     *out_m = c.add(std::move(m));
   });
+}
+// An empty (zero) matrix that is then filled by row ranges: the shape a Spark executor needs to upload the rows of its
+// partitions one partition at a time (mapPartitionsWithIndex) without first concatenating them on the JVM heap.
+KS_API int32_t ks_matrix_create(int64_t ctx, int64_t n_rows, int64_t n_cols, int64_t* out_m) {
+  return guard(ctx, [&](Ctx& c) {
+    if (n_rows < 0 || n_cols <= 0 || !out_m) throw KsError{KS_ERR_INVALID, "bad matrix arguments"};
+    auto m = new_matrix(n_rows, n_cols);
+    KS_CUDA(cudaMemsetAsync(m->d, 0, m->buf.bytes, c.st));
+    KS_CUDA(cudaStreamSynchronize(c.st));
+    *out_m = c.add(std::move(m));
+  });
+}
+static void write_rows(Ctx& c, Matrix& m, int64_t row0, const void* host, int64_t n, int64_t ld, bool is_f64) {
+  if (row0 < 0 || n < 0 || row0 + n > m.rows || ld < m.cols || (!host && n > 0)) throw KsError{KS_ERR_INVALID, "bad row range"};
+  if (n == 0) return;
+  Matrix view;  // a window onto rows [row0, row0 + n) of m (borrowed pointer: view.buf stays empty)
+  view.d = m.d + row0 * m.ld;
+  view.rows = n;
+  view.cols = m.cols;
+  view.ld = m.ld;
+  if (!is_f64) {
+    KS_CUDA(cudaMemcpy2DAsync(view.d, sizeof(float) * view.ld, host, sizeof(float) * ld, sizeof(float) * view.cols, n,
+                              cudaMemcpyHostToDevice, c.st));
+    KS_CUDA(cudaStreamSynchronize(c.st));
+    return;
+  }
+  const int64_t chunk_rows = std::max<int64_t>(1, (int64_t(256) << 20) / (8 * std::max<int64_t>(m.cols, 1)));
+  DevBuf stage;
+  stage.alloc(sizeof(double) * static_cast<size_t>(std::min(chunk_rows, n) * m.cols));
+  const double* h = static_cast<const double*>(host);
+  for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
+    const int64_t nr = std::min(chunk_rows, n - r0);
+    KS_CUDA(cudaMemcpy2DAsync(stage.p, sizeof(double) * m.cols, h + r0 * ld, sizeof(double) * ld, sizeof(double) * m.cols, nr,
+                              cudaMemcpyHostToDevice, c.st));
+    launch_f64_to_f32_rows(stage.as<double>(), m.cols, view.d + r0 * m.ld, m.ld, nr, m.cols, c.st);
+    c.launches += 1;
+    KS_CUDA(cudaStreamSynchronize(c.st));
+  }
+}
+KS_API int32_t ks_matrix_write_rows_f64(int64_t ctx, int64_t m, int64_t row0, const double* rowmajor, int64_t n_rows, int64_t ld) {
+  return guard(ctx, [&](Ctx& c) { write_rows(c, c.matrix(m), row0, rowmajor, n_rows, ld, true); });
+}
+KS_API int32_t ks_matrix_write_rows_f32(int64_t ctx, int64_t m, int64_t row0, const float* rowmajor, int64_t n_rows, int64_t ld) {
+  return guard(ctx, [&](Ctx& c) { write_rows(c, c.matrix(m), row0, rowmajor, n_rows, ld, false); });
 }
 KS_API int32_t ks_matrix_synthetic_normal(int64_t ctx, int64_t n_rows, int64_t n_cols, uint64_t seed, int64_t global_row_offset,
                                    double mean, double stddev, int64_t* out_m) {

@@ -334,7 +334,9 @@ gram2_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // =====================================================================================
 // K-major GEMM with fused epilogues (persistent, double-buffered TMEM accumulator)
 // =====================================================================================
-static constexpr int kKmThreads = 320;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-9: epilogue (2 per TMEM lane quarter)
+static constexpr int kKmThreads = 576;  // warp 0: TMA, warp 1: MMA + TMEM owner, warps 2-17: epilogue (4 per TMEM lane quarter:
+                                        // the cosine epilogue is issue-bound; with 2 warps per scheduler it ran at IPC ~0.5)
+static constexpr int kKmEpiWarps = 16;
 
 template <bool F16, int BN, int STAGES>
 struct KmCfg {
@@ -344,8 +346,8 @@ struct KmCfg {
   static constexpr int A_BYTES = BM * BK * ES;
   static constexpr int B_BYTES = BN * BK * ES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 8 * 4096;  // one 32 x 32 fp32 chunk per epilogue warp
-  static constexpr int VEC_BYTES = 8 * 256 * 4;   // per-warp bias / shift vectors
+  static constexpr int STAGING_BYTES = kKmEpiWarps * 4096;  // one 32 x 32 fp32 chunk per epilogue warp
+  static constexpr int VEC_BYTES = kKmEpiWarps * 128 * 4;   // per-warp bias / shift vectors (64 + 64 columns)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + VEC_BYTES + 1024 + 256;
 };
 
@@ -421,7 +423,7 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       for (int a = 0; a < 2; ++a) {
         mbar_init(&tfull_bar[a], 1);
-        mbar_init(&tempty_bar[a], 8);  // one arrive per epilogue warp
+        mbar_init(&tempty_bar[a], kKmEpiWarps);  // one arrive per epilogue warp
       }
       for (int r = 0; r < 8; ++r) mbar_init(&ring_bar[r], 1);
       fence_barrier_init();
@@ -494,12 +496,12 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
     }
   } else {
-    // 8 epilogue warps: TMEM lane quarter q = warp % 4 (hardware rule), column half = (warp - 2) / 4
+    // 16 epilogue warps: TMEM lane quarter q = warp % 4 (hardware rule), column quarter (64 columns) = (warp - 2) / 4
     const int ew = warp - 2;
     const int q = warp & 3;
-    const int half = ew >> 2;
-    float* v0s = vec_smem + ew * 256;  // this warp's 128 vec0 values
-    float* v1s = v0s + 128;            // and 128 vec1 values
+    const int half = ew >> 2;            // column quarter of the 256-wide tile
+    float* v0s = vec_smem + ew * 128;   // this warp's 64 vec0 values
+    float* v1s = v0s + 64;              // and 64 vec1 values
     uint8_t* buf = staging + ew * 4096;
     const float ascale = p.acc_scale_ptr ? __ldg(p.acc_scale_ptr) * p.acc_scale : p.acc_scale;
     uint32_t tl = 0;
@@ -509,34 +511,47 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       if (t < 0) break;
       const uint32_t a = tl & 1, aph = (tl >> 1) & 1;
       const int m0 = (t / n_tiles) * Cfg::BM;
-      const int n0 = (t % n_tiles) * BN + half * 128;
-      {  // stage the per-column vectors of this warp's 128 columns in shared memory (broadcast reads below)
-        const int n = n0 + lane * 4;
+      const int n0 = (t % n_tiles) * BN + half * 64;
+      {  // stage the per-column vectors of this warp's 64 columns in shared memory (broadcast reads below)
+        const int n = n0 + lane * 2;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v0s[lane * 4 + j] = (p.vec0 && n + j < p.N) ? __ldg(p.vec0 + n + j) : 0.f;
-          v1s[lane * 4 + j] = (p.vec1 && n + j < p.N) ? __ldg(p.vec1 + n + j) : 0.f;
+        for (int j = 0; j < 2; ++j) {
+          v0s[lane * 2 + j] = (p.vec0 && n + j < p.N) ? __ldg(p.vec0 + n + j) : 0.f;
+          v1s[lane * 2 + j] = (p.vec1 && n + j < p.N) ? __ldg(p.vec1 + n + j) : 0.f;
         }
       }
       __syncwarp();
       mbar_wait(&tfull_bar[a], aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < 64; c0 += 32) {
         if (n0 + c0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + half * 128 + c0, v);
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + half * 64 + c0, v);
         tmem_ld_wait();
         float o[32];
         if (EPI == EPI_COS) {
+          // cosine random feature, or (KM_FLAG_RECT) a rectified linear feature max(floor, z - alpha): PaddedFFT + LinearRectifier.
+          // The value summed into colsum must be exactly the stored one: tf32 rounding here; the fp16 slab is rounded once,
+          // by the packed conversion of the staging step, and its column sums are taken from the staged halfs.
+          if (p.flags & KM_FLAG_RECT) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float z = __uint_as_float(v[i]) * ascale;
-            // cosine random feature, or (KM_FLAG_RECT) a rectified linear feature max(floor, z - alpha): PaddedFFT + LinearRectifier
-            const float val = ((p.flags & KM_FLAG_RECT) ? fmaxf(p.rect_floor, z - v0s[c0 + i]) : cos_reduced(z + v0s[c0 + i])) - v1s[c0 + i];
-            // the value summed into colsum must be exactly the stored one: tf32 rounding here; the fp16 slab is rounded once,
-            // by the packed conversion of the staging step, and its column sums are taken from the staged halfs
-            o[i] = OUT16 ? val : ((p.flags & KM_FLAG_NO_ROUND) ? val : round_tf32(val));
+            for (int i = 0; i < 32; ++i) {
+              const float val = fmaxf(p.rect_floor, fmaf(__uint_as_float(v[i]), ascale, -v0s[c0 + i])) - v1s[c0 + i];
+              o[i] = OUT16 ? val : ((p.flags & KM_FLAG_NO_ROUND) ? val : round_tf32(val));
+            }
+          } else if (p.flags & KM_FLAG_NO_ROUND) {  // unrounded output (parity mode, materialised features): exact range reduction
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = cos_reduced(fmaf(__uint_as_float(v[i]), ascale, v0s[c0 + i])) - v1s[c0 + i];
+          } else {
+            // 10-bit slabs: cos.approx on the raw argument (its own range reduction costs ~6e-8 |z| of phase: 1e-6 at |z| = 16,
+            // three orders below the operand rounding) saves the four Cody-Waite instructions per element of this
+            // epilogue-bound kernel (profiles/README.md: 23 warp instructions per 32 elements, tensor pipe 25 % busy)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float val = __cosf(fmaf(__uint_as_float(v[i]), ascale, v0s[c0 + i])) - v1s[c0 + i];
+              o[i] = OUT16 ? val : round_tf32(val);
+            }
           }
         } else if (EPI == EPI_UPDATE) {
 #pragma unroll

@@ -27,7 +27,7 @@ def main():
         for rep in range(2):
             for cfg in configs:
                 pipe, prec = int(cfg[0]), cfg[1]
-                opts = {"custom_solve": 1, "dyn_tiles": 1, "gram_chunk_rows": 0}     # defaults, so that configs do not leak
+                opts = {"custom_solve": 0, "dyn_tiles": 1, "gram_chunk_rows": 0, "reserve_sms": 8}     # defaults, so that configs do not leak
                 opts.update({name: int(val) for name, val in (o.split("=") for o in cfg[2:])})
                 ctx.set_option("pipeline", pipe)
                 for name, val in opts.items():
