@@ -129,6 +129,22 @@ KS_API int32_t ks_padded_fft_create(int64_t ctx, const double* signs_or_null, in
  * (LinearRectifier.apply); returns a new matrix. */
 KS_API int32_t ks_matrix_map(int64_t ctx, int64_t m, int32_t op, const double* colvec_or_null, double a, double b, int64_t* out_m);
 
+/* ---- Convolver [andThen SymmetricRectifier andThen Pooler(sum) andThen ImageVectorizer] ---------------------------------
+ * The featurizer of K/pipelines/images/cifar/RandomPatchCifar.scala:59-63 (K/nodes/images/Convolver.scala:20-203,
+ * SymmetricRectifier.scala:7-32, Pooler.scala:21-69, K/utils/Stats.scala:112-123).  filters: DenseMatrix (n_filters x
+ * conv_size^2*channels) column-major, columns ordered c + x*channels + y*channels*conv_size (Convolver.packFilters), already whitened
+ * if a whitener is used; whitener_means (patch dimension) may be NULL.  Images are rows of a matrix in ImageVectorizer order
+ * (value (x, y, c) at c + x*channels + y*channels*x_dim; x_dim = image height, K/utils/images/Image.scala:140-143).
+ * ks_convolver_apply with pool_size = 0 returns the convolved images (n x resW*resH*n_filters, same vectorised order);
+ * with pool_size > 0 the rectifier and the sum pooling run in the GEMM's epilogue and only the pooled features
+ * (n x nPoolsX*nPoolsY*2*n_filters) are written. */
+KS_API int32_t ks_convolver_create(int64_t ctx, const double* filters_colmajor, int32_t n_filters, int32_t x_dim, int32_t y_dim,
+                                   int32_t channels, int32_t conv_size, const double* whitener_means_or_null, int32_t normalize_patches,
+                                   double var_constant, int64_t* out_conv);
+KS_API int32_t ks_convolver_apply(int64_t ctx, int64_t conv, int64_t images, int32_t pool_stride, int32_t pool_size, double max_val,
+                                  double alpha, int64_t* out_features);
+KS_API int32_t ks_convolver_destroy(int64_t ctx, int64_t conv);
+
 /* ---- feature source shared by fit / apply -------------------------------------------------
  * Either `features` (a materialised N x D matrix; VectorSplitter blocks are column ranges of it,
  * K/nodes/util/VectorSplitter.scala:15-25) or `x_in` + `rfs[n_rfs]` (the gather of

@@ -11,7 +11,13 @@ from .nodes import (  # noqa: F401
     BlockLinearMapper,
     BlockWeightedLeastSquaresEstimator,
     ClassLabelIndicatorsFromIntLabels,
+    Convolver,
     CosineRandomFeatures,
+    ImageVectorizer,
+    Pooler,
+    SymmetricRectifier,
+    cifar_bytes_to_matrix,
+    images_to_matrix,
     LeastSquaresEstimator,
     LinearMapEstimator,
     LinearMapper,

@@ -82,6 +82,9 @@ def _declare(L: C.CDLL) -> None:
     sig("ks_cosine_rf_create", i64, C.c_void_p, C.c_void_p, i64, i64, p_i64)
     sig("ks_cosine_rf_apply", i64, i64, i64, p_i64)
     sig("ks_cosine_rf_destroy", i64, i64)
+    sig("ks_convolver_create", i64, C.c_void_p, i32, i32, i32, i32, i32, C.c_void_p, i32, f64, p_i64)
+    sig("ks_convolver_apply", i64, i64, i64, i32, i32, f64, f64, p_i64)
+    sig("ks_convolver_destroy", i64, i64)
     sig("ks_padded_fft_create", i64, C.c_void_p, i64, i32, f64, f64, p_i64)
     sig("ks_matrix_map", i64, i64, i32, C.c_void_p, f64, f64, p_i64)
     sig("ks_blockls_fit", i64, i64, i64, p_i64, i32, i64, i32, i32, f64, i64, i32, p_i64)

@@ -427,6 +427,76 @@ void launch_w_to_operand(const double* W_colmajor, int64_t n_out, int64_t n_in, 
   w_to_operand_kernel<<<grid_for(n_out * ld, 256), 256, 0, st>>>(W_colmajor, n_out, n_in, dst, ld, round);
 }
 
+// One CTA per image (8 warps); the image sits in shared memory, one warp builds one patch row at a time: lane l owns patch
+// columns l, l + 32, ... (<= 8 per lane: patch dimension <= 256), warp-shuffle reductions for the row mean / variance.
+__global__ void __launch_bounds__(256)
+im2col_normalize_kernel(const float* __restrict__ images, int64_t ld_img, int x_dim, int y_dim, int ch, int conv, int normalize,
+                        float var_constant, const float* __restrict__ wmeans, __half* __restrict__ out, int64_t ld_out, int concat3) {
+  extern __shared__ float simg[];
+  const int64_t img = blockIdx.x;
+  const int npix = x_dim * y_dim * ch;
+  for (int i = threadIdx.x; i < npix; i += blockDim.x) simg[i] = images[img * ld_img + i];
+  __syncthreads();
+  const int rw = x_dim - conv + 1, rh = y_dim - conv + 1, pd = conv * conv * ch;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pr = warp; pr < rw * rh; pr += 8) {
+    const int x = pr % rw, y = pr / rw;
+    float v[8];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int px = lane + 32 * j;
+      v[j] = 0.f;
+      if (px < pd) {
+        const int c = px % ch, pox = (px / ch) % conv, poy = px / (ch * conv);
+        v[j] = simg[c + (x + pox) * ch + (y + poy) * ch * x_dim];
+        sum += v[j];
+      }
+    }
+    if (normalize) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      const float mean = sum / static_cast<float>(pd);
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (lane + 32 * j < pd) {
+          v[j] -= mean;
+          ss += v[j] * v[j];
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+      const float inv = rsqrtf(ss / static_cast<float>(pd - 1) + var_constant);   // sample variance (n - 1), Stats.scala:117
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= inv;
+    }
+    __half* row = out + (img * static_cast<int64_t>(rw * rh) + pr) * ld_out;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int px = lane + 32 * j;
+      if (px < pd) {
+        const float val = v[j] - (wmeans ? wmeans[px] : 0.f);
+        const __half h = __float2half_rn(val);
+        row[px] = h;
+        if (concat3) {
+          row[pd + px] = __float2half_rn(val - __half2float(h));
+          row[2 * pd + px] = h;
+        }
+      }
+    }
+    const int used = concat3 ? 3 * pd : pd;   // zero the padding columns of the row
+    for (int px = used + lane; px < ld_out; px += 32) row[px] = __float2half_rn(0.f);
+  }
+}
+void launch_im2col_normalize(const float* images, int64_t ld_img, int64_t n_images, int x_dim, int y_dim, int ch, int conv, int normalize,
+                             float var_constant, const float* whitener_means, void* out16, int64_t ld_out, int concat3, cudaStream_t st) {
+  if (n_images == 0) return;
+  const size_t smem = sizeof(float) * static_cast<size_t>(x_dim) * y_dim * ch;
+  im2col_normalize_kernel<<<static_cast<unsigned>(n_images), 256, smem, st>>>(images, ld_img, x_dim, y_dim, ch, conv, normalize,
+                                                                            var_constant, whitener_means, static_cast<__half*>(out16),
+                                                                            ld_out, concat3);
+}
+
 // PaddedFFT (K/nodes/stats/PaddedFFT.scala:13-21): Re(FFT(pad(x))) [f] = sum_n x[n] cos(2 pi f n / P); with RandomSignNode
 // (K/nodes/stats/RandomSignNode.scala:11-16) in front, x[n] carries the sign s[n]: a fixed (P/2) x n_in matrix
 __global__ void fft_real_matrix_kernel(const double* __restrict__ signs, int64_t n_in, int64_t P, float* __restrict__ dst,

@@ -1427,6 +1427,7 @@ KS_API int32_t ks_ctx_destroy(int64_t ctx) {
   c->matrices.clear();
   c->rfs.clear();
   c->models.clear();
+  c->convs.clear();
   c->tile_cache.clear();
   for (auto e : c->event_pool) cudaEventDestroy(e);
   for (auto& ln : c->lanes) {
@@ -1732,6 +1733,147 @@ KS_API int32_t ks_matrix_map(int64_t ctx, int64_t m, int32_t op, const double* c
     *out_m = c.add(std::move(out));
   });
 }
+// ---------------------------------------------------------------- Convolver / SymmetricRectifier / Pooler (CIFAR random-patch featurizer)
+KS_API int32_t ks_convolver_create(int64_t ctx, const double* filters_colmajor, int32_t n_filters, int32_t x_dim, int32_t y_dim,
+                                   int32_t channels, int32_t conv_size, const double* whitener_means_or_null, int32_t normalize_patches,
+                                   double var_constant, int64_t* out_conv) {
+  return guard(ctx, [&](Ctx& c) {
+    const int pd = conv_size * conv_size * channels;
+    if (!filters_colmajor || n_filters <= 0 || x_dim < conv_size || y_dim < conv_size || channels <= 0 || conv_size <= 0 || pd > 256 ||
+        static_cast<int64_t>(x_dim) * y_dim * channels > 12288 || !out_conv)
+      throw KsError{KS_ERR_INVALID, "bad Convolver arguments (patch dimension <= 256, image <= 12288 values)"};
+    auto cv = std::make_unique<ConvPool>();
+    cv->x_dim = x_dim; cv->y_dim = y_dim; cv->ch = channels; cv->conv = conv_size; cv->n_filters = n_filters;
+    cv->normalize = normalize_patches ? 1 : 0;
+    cv->var_constant = static_cast<float>(var_constant);
+    cv->pd = pd;
+    cv->ld1 = round_up(pd, 64);
+    cv->ld3 = round_up(3 * pd, 64);
+    // filters: DenseMatrix (n_filters x pd) column-major fp64 -> fp32 row-major [n_filters][ldf] (unrounded) -> scaled fp16 operands
+    const int64_t ldf = round_up(pd, kPadCols);
+    DevBuf stage, f32;
+    stage.alloc(sizeof(double) * static_cast<size_t>(n_filters) * pd);
+    f32.alloc(sizeof(float) * static_cast<size_t>(n_filters) * ldf);
+    KS_CUDA(cudaMemcpyAsync(stage.p, filters_colmajor, sizeof(double) * static_cast<size_t>(n_filters) * pd, cudaMemcpyHostToDevice, c.st));
+    launch_w_to_operand(stage.as<double>(), n_filters, pd, f32.as<float>(), ldf, c.st, /*round=*/false);
+    cv->wscale.alloc(sizeof(float) * 8);   // [1] max bits, [2,3] {2^e, 2^-e}
+    KS_CUDA(cudaMemsetAsync(cv->wscale.p, 0, cv->wscale.bytes, c.st));
+    launch_max_abs_f32(f32.as<float>(), ldf, n_filters, pd, cv->wscale.as<unsigned>() + 1, c.st);
+    launch_pow2_scale(cv->wscale.as<unsigned>() + 1, 4096.f, cv->wscale.as<float>() + 2, c.st);
+    cv->w16.alloc(2 * static_cast<size_t>(n_filters) * cv->ld1);
+    cv->w3.alloc(2 * static_cast<size_t>(n_filters) * cv->ld3);
+    launch_f32_to_f16_rows(f32.as<float>(), ldf, cv->w16.p, cv->ld1, n_filters, pd, c.st, cv->wscale.as<float>() + 2);
+    launch_split_concat3(f32.as<float>(), ldf, n_filters, pd, cv->wscale.as<float>() + 2, cv->w3.p, cv->ld3, 1, c.st);
+    if (whitener_means_or_null) {
+      DevBuf m64;
+      m64.alloc(sizeof(double) * pd);
+      cv->wmeans.alloc(sizeof(float) * pd);
+      KS_CUDA(cudaMemcpyAsync(m64.p, whitener_means_or_null, sizeof(double) * pd, cudaMemcpyHostToDevice, c.st));
+      launch_f64_to_f32_vec(m64.as<double>(), cv->wmeans.as<float>(), pd, c.st);
+      cv->has_means = true;
+      c.check_async("convolver_create");
+    }
+    c.launches += 6;
+    c.check_async("convolver_create");
+    const int64_t id = c.next_id++;
+    c.convs[id] = std::move(cv);
+    *out_conv = id;
+  });
+}
+KS_API int32_t ks_convolver_destroy(int64_t ctx, int64_t conv) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!c.convs.erase(conv)) throw KsError{KS_ERR_HANDLE, "unknown Convolver handle"};
+  });
+}
+// images: (n x x_dim*y_dim*channels) matrix in ImageVectorizer order (c + x*C + y*C*x_dim, K/utils/images/Image.scala:47-65).
+// pool_size == 0: Convolver.apply alone -> (n x resW*resH*n_filters), the convolved images in the same vectorised order.
+// pool_size  > 0: Convolver andThen SymmetricRectifier(max_val, alpha) andThen Pooler(stride, pool_size, identity, sum) andThen
+//                 ImageVectorizer, fused -> (n x nPoolsX*nPoolsY*2*n_filters); the convolved maps never reach HBM.
+// Operands: fp16 (context precision F16 / TF32) or split fp16 pairs concatenated along K (F16X2, the default).
+KS_API int32_t ks_convolver_apply(int64_t ctx, int64_t conv, int64_t images, int32_t pool_stride, int32_t pool_size, double max_val,
+                                  double alpha, int64_t* out_features) {
+  return guard(ctx, [&](Ctx& c) {
+    if (!out_features) throw KsError{KS_ERR_INVALID, "null output"};
+    auto it = c.convs.find(conv);
+    if (it == c.convs.end()) throw KsError{KS_ERR_HANDLE, "unknown Convolver handle"};
+    ConvPool& cv = *it->second;
+    Matrix& im = c.matrix(images);
+    if (im.cols != static_cast<int64_t>(cv.x_dim) * cv.y_dim * cv.ch) throw KsError{KS_ERR_INVALID, "image size does not match the Convolver"};
+    const int rw = cv.x_dim - cv.conv + 1, rh = cv.y_dim - cv.conv + 1, ppi = rw * rh;
+    const bool pooled = pool_size > 0;
+    int npx = 0, npy = 0;
+    std::vector<unsigned> mask(ppi, 0u);
+    if (pooled) {
+      if (pool_stride <= 0) throw KsError{KS_ERR_INVALID, "bad pool stride"};
+      const int s0 = pool_size / 2;                                   // Pooler.scala:27, :36-37
+      npx = (rw - s0 + pool_stride - 1) / pool_stride;
+      npy = (rh - s0 + pool_stride - 1) / pool_stride;
+      if (npx <= 0 || npy <= 0 || npx * npy > 16) throw KsError{KS_ERR_INVALID, "Pooler geometry unsupported (1..16 pools per image)"};
+      for (int px = 0; px < npx; ++px)
+        for (int py = 0; py < npy; ++py) {
+          const int cx = s0 + px * pool_stride, cy = s0 + py * pool_stride;
+          for (int x = cx - pool_size / 2; x < std::min(cx + pool_size / 2, rw); ++x)
+            for (int y = cy - pool_size / 2; y < std::min(cy + pool_size / 2, rh); ++y) mask[x + y * rw] |= 1u << (px + py * npx);
+        }
+    }
+    const bool x2 = c.precision == KS_PRECISION_F16X2;
+    const int64_t ldp = x2 ? cv.ld3 : cv.ld1;
+    const int kdepth = x2 ? 3 * cv.pd : cv.pd;
+    const int64_t out_cols = pooled ? static_cast<int64_t>(npx) * npy * 2 * cv.n_filters : static_cast<int64_t>(ppi) * cv.n_filters;
+    auto out = new_matrix(im.rows, out_cols);
+    KS_CUDA(cudaMemsetAsync(out->d, 0, out->buf.bytes, c.st));
+    DevBuf maskd, patches;
+    maskd.alloc(sizeof(unsigned) * ppi);
+    KS_CUDA(cudaMemcpyAsync(maskd.p, mask.data(), sizeof(unsigned) * ppi, cudaMemcpyHostToDevice, c.st));
+    // image chunks bound the patch matrix (ppi * ldp * 2 B per image) to ~4 GB
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(im.rows, (int64_t(4) << 30) / (static_cast<int64_t>(ppi) * ldp * 2)));
+    patches.alloc(2 * static_cast<size_t>(chunk) * ppi * ldp);
+    for (int64_t i0 = 0; i0 < im.rows; i0 += chunk) {
+      const int64_t ni = std::min(chunk, im.rows - i0);
+      launch_im2col_normalize(im.d + i0 * im.ld, im.ld, ni, cv.x_dim, cv.y_dim, cv.ch, cv.conv, cv.normalize, cv.var_constant,
+                              cv.has_means ? cv.wmeans.as<float>() : nullptr, patches.p, ldp, x2 ? 1 : 0, c.st);
+      KmLaunch k;
+      const int64_t m_rows = ni * ppi;
+      tmap16_or_throw(&k.tmA, patches.p, m_rows, kdepth, ldp, 64, 128, TMAP_SW128);
+      tmap16_or_throw(&k.tmB, x2 ? cv.w3.p : cv.w16.p, cv.n_filters, kdepth, ldp, 64, 256, TMAP_SW128);
+      k.f16 = 1;
+      k.pair = 0;
+      k.p.acc_scale_ptr = cv.wscale.as<float>() + 3;      // 2^-e of the filter scale
+      k.p.M = static_cast<int>(m_rows);
+      k.p.N = cv.n_filters;
+      k.p.K = kdepth;
+      k.p.vec0 = nullptr;
+      k.p.vec1 = nullptr;
+      k.p.colsum = nullptr;
+      k.num_sms = c.num_sms;
+      if (c.dyn_tiles) k.p.tile_counter = c.next_tile_counter(c.st);
+      if (pooled) {
+        k.epi = EPI_POOL;
+        k.p.flags = 0;
+        k.p.pool_mask = maskd.as<unsigned>();
+        k.p.pool_out = out->d + i0 * out->ld;
+        k.p.pool_out_ld = out->ld;
+        k.p.patches_per_image = ppi;
+        k.p.n_pools = npx * npy;
+        k.p.pool_alpha = static_cast<float>(alpha);
+        k.p.rect_floor = static_cast<float>(max_val);
+        tmap_or_throw(&k.tmOut, out->d, im.rows, std::min<int64_t>(out_cols, 32), out->ld, 32);  // unused by this epilogue
+      } else {
+        // the convolved image of image i is rows [i * ppi, (i+1) * ppi) x n_filters of the product: view the output as that matrix
+        k.epi = EPI_APPLY;
+        k.p.flags = 0;
+        if (out->ld != out_cols) throw KsError{KS_ERR_INVALID, "Convolver.apply alone needs resW*resH*n_filters to be a multiple of 32"};
+        tmap_or_throw(&k.tmOut, out->d + i0 * out->ld, m_rows, cv.n_filters, cv.n_filters, 32);
+      }
+      KS_CUDA(launch_kmajor(k, c.st));
+      c.launches += 2;
+      KS_CUDA(cudaStreamSynchronize(c.st));   // the patch buffer is reused by the next chunk
+    }
+    c.check_async("Convolver.apply");
+    *out_features = c.add(std::move(out));
+  });
+}
+
 KS_API int32_t ks_cosine_rf_apply(int64_t ctx, int64_t rf, int64_t x_in, int64_t* out_features) {
   return guard(ctx, [&](Ctx& c) {
     if (!out_features) throw KsError{KS_ERR_INVALID, "null output"};

@@ -98,6 +98,17 @@ struct CosRF {
   float rect_floor = 0.f;
 };
 
+// Convolver [+ SymmetricRectifier + sum Pooler + ImageVectorizer] (K/nodes/images/{Convolver,SymmetricRectifier,Pooler}.scala),
+// the featurizer of K/pipelines/images/cifar/RandomPatchCifar.scala:59-63
+struct ConvPool {
+  int x_dim = 0, y_dim = 0, ch = 0, conv = 0, n_filters = 0, normalize = 1;
+  float var_constant = 10.f;
+  int pd = 0;                 // patch dimension conv * conv * ch
+  int64_t ld1 = 0, ld3 = 0;   // leading dimensions (fp16 elements) of the plain and of the K-concatenated operands
+  DevBuf w16, w3, wscale, wmeans, fzero;  // filters as fp16 [n_filters][ld1] and [w_hi | w_hi | w_lo] [n_filters][ld3], times 2^e
+  bool has_means = false;
+};
+
 struct Model {  // BlockLinearMapper state (K/nodes/learning/BlockLinearMapper.scala:22-33)
   int block_size = 0;
   int64_t k = 0;
@@ -198,6 +209,7 @@ struct Ctx {
   std::unordered_map<int64_t, std::unique_ptr<Matrix>> matrices;
   std::unordered_map<int64_t, std::unique_ptr<CosRF>> rfs;
   std::unordered_map<int64_t, std::unique_ptr<Model>> models;
+  std::unordered_map<int64_t, std::unique_ptr<ConvPool>> convs;
   std::map<std::vector<int>, std::unique_ptr<DevBuf>> tile_cache;
   // phase timing of the current fit
   struct Span { int phase; cudaEvent_t a, b; int stream; };

@@ -9,7 +9,7 @@ namespace ks {
 static constexpr int kGramStageRows = 32;  // rows per TMA stage of the Gram kernel
 static constexpr int kPadCols = 32;        // every device matrix has ld % 32 == 0 (128 B rows)
 
-enum { EPI_COS = 0, EPI_UPDATE = 1, EPI_APPLY = 2 };
+enum { EPI_COS = 0, EPI_UPDATE = 1, EPI_APPLY = 2, EPI_POOL = 3 };
 
 struct GramTile {
   int m_blk;  // 128-wide block of A's columns
@@ -37,6 +37,13 @@ struct KmParams {
   float* colsum;      // EPI_COS: if non-null, colsum[n] += sum over valid rows of the stored values (fp32 atomics)
   float acc_scale = 1.f;    // the accumulator is multiplied by this before the epilogue (undoes power-of-two operand scaling)
   const float* acc_scale_ptr = nullptr;  // optional device scalar multiplied into acc_scale (scale chosen on the device)
+  // EPI_POOL (Convolver -> SymmetricRectifier -> sum Pooler -> ImageVectorizer, fused): rows are image patches (patches_per_image
+  // consecutive rows per image), columns are filters; out[img][pool * 2 N + {0, N} + filter] += max(floor, +-acc - alpha)
+  const unsigned* pool_mask = nullptr;  // [patches_per_image] bit p set: the patch position lies in pool p (pools may overlap)
+  float* pool_out = nullptr;
+  int64_t pool_out_ld = 0;
+  int patches_per_image = 0, n_pools = 0;
+  float pool_alpha = 0.f;
   int* tile_counter = nullptr;  // persistent single-CTA kernel: zeroed device counter the CTAs draw their tiles from (null: static stride)
   int M, N, K;
   int flags;  // KM_FLAG_NO_ROUND: EPI_COS keeps fp32;  KM_FLAG_REDUCE: add into the output instead of overwriting it
@@ -110,6 +117,11 @@ void launch_normal_f32(float* dst, int64_t ld, int64_t rows, int cols, uint64_t 
 void launch_w_to_operand(const double* W_colmajor, int64_t n_out, int64_t n_in, float* dst, int64_t ld, cudaStream_t st,
                          bool round = true);  // round: tf32 round-to-nearest (MMA operand); false: plain fp32
 void launch_f64_to_f32_vec(const double* src, float* dst, int64_t n, cudaStream_t st);
+// Convolver.makePatches + Stats.normalizeRows + whitener means (K/nodes/images/Convolver.scala:152-203, K/utils/Stats.scala:112-123):
+// images [n][x_dim * y_dim * ch] fp32 in ImageVectorizer order (c + x*ch + y*ch*x_dim) -> fp16 patch rows [n * resW * resH][ld],
+// row = img * resW * resH + x + y * resW, column c + pox*ch + poy*ch*conv; concat3: [hi | lo | hi] along K (split-operand mode)
+void launch_im2col_normalize(const float* images, int64_t ld_img, int64_t n_images, int x_dim, int y_dim, int ch, int conv, int normalize,
+                             float var_constant, const float* whitener_means, void* out16, int64_t ld_out, int concat3, cudaStream_t st);
 // PaddedFFT as a dense map: W[f][n] = signs[n] * cos(2 pi f n / P), f < P / 2, n < n_in (signs may be null = all ones), written
 // twice: tf32-rounded (dst) and plain fp32 (dst_full); both [P/2][ld]
 void launch_fft_real_matrix(const double* signs, int64_t n_in, int64_t P, float* dst, float* dst_full, int64_t ld, cudaStream_t st);

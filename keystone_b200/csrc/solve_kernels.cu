@@ -19,6 +19,8 @@
 //
 // L: column-major n x n (ld = n), lower triangle valid (cusolverDnDpotrf, CUBLAS_FILL_MODE_LOWER).  B: column-major n x k.
 // Dinv: ceil(n / 64) tiles of 64 x 64 doubles, column-major inside a tile, zero above the diagonal and beyond n.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 namespace ks {
@@ -190,7 +192,9 @@ cudaError_t launch_chol_solve(const double* L, const double* Dinv, int n, double
   if (n <= 0 || k <= 0) return cudaSuccess;
   // 16 right-hand sides per CTA halve the L2 traffic for L (every CTA streams the whole factor twice); with few columns (the
   // column-sharded multi-GPU solve) 8 per CTA keep more SMs busy
-  if (k > 8 * 96) chol_solve_kernel<16><<<(k + 15) / 16, 256, 0, st>>>(L, Dinv, n, B, k);
+  static const int forced_nc = getenv("KS_SOLVE_NC") ? atoi(getenv("KS_SOLVE_NC")) : 0;   // A/B override (8 or 16)
+  const bool nc16 = forced_nc ? forced_nc == 16 : k > 8 * 148;
+  if (nc16) chol_solve_kernel<16><<<(k + 15) / 16, 256, 0, st>>>(L, Dinv, n, B, k);
   else chol_solve_kernel<8><<<(k + 7) / 8, 256, 0, st>>>(L, Dinv, n, B, k);
   return cudaGetLastError();
 }

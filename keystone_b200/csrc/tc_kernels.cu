@@ -556,9 +556,66 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         } else if (EPI == EPI_UPDATE) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] - __uint_as_float(v[i]) * ascale;
-        } else {
+        } else if (EPI == EPI_APPLY) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = v0s[c0 + i] + __uint_as_float(v[i]) * ascale;
+        }
+        if (EPI == EPI_POOL) {
+          // Convolver -> SymmetricRectifier -> sum Pooler: the chunk (32 patch rows x 32 filters) is transposed through the staging
+          // buffer; lane c then owns filter column c and walks the 32 rows, adding max(floor, +-v - alpha) into the pools the row's
+          // patch position belongs to (bit mask per position; rows of a chunk may belong to two images), and flushes the pool
+          // sums of an image with fp32 atomics into out[img][pool * 2 N + {0, N} + filter] (the ImageVectorizer order).
+          const int grow = m0 + q * 32 + lane;
+          const int my_img = grow / p.patches_per_image;
+          const unsigned my_mask = grow < p.M ? __ldg(p.pool_mask + (grow - my_img * p.patches_per_image)) : 0u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]) * ascale;
+          __syncwarp();
+          stage_row_sw128(buf, lane, o);
+          __syncwarp();
+          const int f = n0 + c0 + lane;
+          constexpr int kMaxPools = 16;
+          float ap[kMaxPools], an[kMaxPools];
+#pragma unroll
+          for (int pl = 0; pl < kMaxPools; ++pl) ap[pl] = an[pl] = 0.f;
+          int cur = __shfl_sync(0xffffffffu, my_img, 0);
+          unsigned touched = 0;
+          auto flush = [&](int img) {
+            if (f < p.N && touched) {
+              float* dst = p.pool_out + static_cast<int64_t>(img) * p.pool_out_ld + f;
+#pragma unroll
+              for (int pl = 0; pl < kMaxPools; ++pl)
+                if (touched >> pl & 1) {
+                  atomicAdd(dst + static_cast<int64_t>(pl) * 2 * p.N, ap[pl]);
+                  atomicAdd(dst + static_cast<int64_t>(pl) * 2 * p.N + p.N, an[pl]);
+                  ap[pl] = an[pl] = 0.f;
+                }
+            }
+            touched = 0;
+          };
+#pragma unroll 1
+          for (int r = 0; r < 32; ++r) {
+            const int im = __shfl_sync(0xffffffffu, my_img, r);
+            const unsigned mk = __shfl_sync(0xffffffffu, my_mask, r);
+            if (im != cur) {  // warp-uniform
+              flush(cur);
+              cur = im;
+            }
+            if (mk) {
+              const float val = *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+              const float pos = fmaxf(p.rect_floor, val - p.pool_alpha), neg = fmaxf(p.rect_floor, -val - p.pool_alpha);
+#pragma unroll
+              for (int pl = 0; pl < kMaxPools; ++pl)
+                if (mk >> pl & 1) {
+                  ap[pl] += pos;
+                  an[pl] += neg;
+                }
+              touched |= mk;
+            }
+          }
+          flush(cur);
+          __syncwarp();
+          continue;  // no TMA store for this epilogue
         }
         if (EPI == EPI_COS && p.colsum != nullptr && m0 + q * 32 + lane >= p.M) {
 #pragma unroll
@@ -918,6 +975,8 @@ static cudaError_t launch_km2_t(const KmLaunch& k, cudaStream_t st) {
 }
 
 cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st) {
+  if (k.epi == EPI_POOL) return k.f16 ? launch_km_t<EPI_POOL, true, false, 256, 3>(k, st) : cudaErrorInvalidValue;
+  if (k.epi == EPI_APPLY && k.f16 && !k.pair) return launch_km_t<EPI_APPLY, true, false, 256, 3>(k, st);  // K-concatenated fp16 operands
   if (k.f16 && k.epi == EPI_UPDATE) return launch_km2_t<EPI_UPDATE, true, 4>(k, st);
   if (k.f16 && k.epi == EPI_APPLY) return launch_km2_t<EPI_APPLY, true, 4>(k, st);
   if (k.out16 && k.f16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, true, true, 256, 3>(k, st);

@@ -198,6 +198,121 @@ class LinearRectifier(Transformer):
         return out.to_numpy()[0] if single else out
 
 
+class _ConvHandle:
+    def __init__(self, ctx: Context, handle: int):
+        self.ctx, self.handle = ctx, handle
+
+    def __del__(self):
+        try:
+            if self.handle and self.ctx.handle:
+                lib().ks_convolver_destroy(self.ctx.handle, self.handle)
+        except Exception:
+            pass
+
+
+class _ConvolvedImages(Dataset):
+    """Lazy output of Convolver [-> SymmetricRectifier [-> Pooler]] on an image batch: the chain runs as ONE fused launch per image
+    chunk when it is materialised (``ImageVectorizer`` / ``to_numpy``)."""
+
+    def __init__(self, images: DeviceMatrix, conv: "Convolver", rect=None, pool=None):
+        self.ctx, self.images, self.conv, self.rect, self.pool = images.ctx, images, conv, rect, pool
+        self.rows = images.rows
+
+    def materialize(self) -> DeviceMatrix:
+        if self.rect is not None and self.pool is None:
+            raise KeystoneError(-1, "SymmetricRectifier on convolved images is fused with the Pooler that follows it: chain a Pooler")
+        stride, size = self.pool if self.pool else (0, 0)
+        max_val, alpha = self.rect if self.rect else (0.0, 0.0)
+        if self.pool and self.rect is None:
+            raise KeystoneError(-1, "Pooler after Convolver needs the SymmetricRectifier in between (the fused kernel's epilogue)")
+        h = C.c_int64(0)
+        check(self.ctx.handle, lib().ks_convolver_apply(self.ctx.handle, self.conv._h.handle, self.images.handle, stride, size,
+                                                         float(max_val), float(alpha), C.byref(h)))
+        rows, cols = C.c_int64(0), C.c_int64(0)
+        check(self.ctx.handle, lib().ks_matrix_shape(self.ctx.handle, h.value, C.byref(rows), C.byref(cols)))
+        return DeviceMatrix(self.ctx, h.value, rows.value, cols.value)
+
+    def to_numpy(self, dtype=np.float64) -> np.ndarray:
+        return self.materialize().to_numpy(dtype)
+
+
+class Convolver(Transformer):
+    """``new Convolver(filters, imgWidth, imgHeight, imgChannels, whitener, normalizePatches, varConstant)``
+    (K/nodes/images/Convolver.scala:20-47).  filters: (numFilters x convSize^2*channels), columns in packFilters order, already
+    whitened when a whitener is used; ``whitener_means`` = the whitener's means (the only part of the ZCAWhitener that apply uses,
+    :196-199).  Image batches are device matrices whose rows are images in ImageVectorizer order."""
+
+    def __init__(self, ctx: Context, filters: np.ndarray, img_width: int, img_height: int, img_channels: int,
+                 whitener_means: Optional[np.ndarray] = None, normalize_patches: bool = True, var_constant: float = 10.0):
+        filters = np.asarray(filters, dtype=np.float64)
+        self.ctx, self.n_filters = ctx, filters.shape[0]
+        self.x_dim, self.y_dim, self.ch = img_width, img_height, img_channels
+        self.conv_size = int(round(math.sqrt(filters.shape[1] / img_channels)))          # Convolver.scala:30
+        if self.conv_size * self.conv_size * img_channels != filters.shape[1]:
+            raise ValueError("filters must be square patches of the image's channel count")
+        fcol = np.asfortranarray(filters)
+        wm = None if whitener_means is None else np.ascontiguousarray(whitener_means, dtype=np.float64)
+        h = C.c_int64(0)
+        check(ctx.handle, lib().ks_convolver_create(ctx.handle, fcol.ctypes.data_as(C.c_void_p), self.n_filters, img_width, img_height,
+                                                     img_channels, self.conv_size, None if wm is None else wm.ctypes.data_as(C.c_void_p),
+                                                     1 if normalize_patches else 0, float(var_constant), C.byref(h)))
+        self._h = _ConvHandle(ctx, h.value)
+
+    def apply(self, data):
+        ds = _as_dataset(self.ctx, data)
+        if not isinstance(ds, DeviceMatrix):
+            ds = ds.materialize()
+        return _ConvolvedImages(ds, self)
+
+
+class SymmetricRectifier(Transformer):
+    """Channels [0, C) = max(maxVal, v - alpha), [C, 2C) = max(maxVal, -v - alpha) (K/nodes/images/SymmetricRectifier.scala:7-32);
+    on convolved images it becomes part of the convolution's epilogue."""
+
+    def __init__(self, max_val: float = 0.0, alpha: float = 0.0):
+        self.max_val, self.alpha = float(max_val), float(alpha)
+
+    def apply(self, data):
+        if isinstance(data, _ConvolvedImages) and data.rect is None and data.pool is None:
+            return _ConvolvedImages(data.images, data.conv, (self.max_val, self.alpha), None)
+        raise KeystoneError(-1, "SymmetricRectifier is implemented as the epilogue of a Convolver: apply it to a Convolver's output")
+
+
+class Pooler(Transformer):
+    """``new Pooler(stride, poolSize, identity, _.sum)`` (K/nodes/images/Pooler.scala:21-69; sum pooling of the pipeline,
+    RandomPatchCifar.scala:61): fused into the convolution's epilogue."""
+
+    def __init__(self, stride: int, pool_size: int):
+        self.stride, self.pool_size = int(stride), int(pool_size)
+
+    def apply(self, data):
+        if isinstance(data, _ConvolvedImages) and data.rect is not None and data.pool is None:
+            return _ConvolvedImages(data.images, data.conv, data.rect, (self.stride, self.pool_size))
+        raise KeystoneError(-1, "Pooler is implemented as the epilogue of Convolver -> SymmetricRectifier: apply it to that chain's output")
+
+
+class ImageVectorizer(Transformer):
+    """``Image.toArray`` (K/nodes/images/ImageVectorizer.scala:12-16): forces the fused chain; rows are the vectorised images."""
+
+    def apply(self, data):
+        if isinstance(data, _ConvolvedImages):
+            return data.materialize()
+        return data
+
+
+def images_to_matrix(images_xyc: np.ndarray) -> np.ndarray:
+    """(n, x, y, c) image batch -> rows in ImageVectorizer order c + x*C + y*C*xDim (what Convolver expects)."""
+    a = np.asarray(images_xyc)
+    return np.ascontiguousarray(np.transpose(a, (0, 2, 1, 3)).reshape(a.shape[0], -1), dtype=np.float32)
+
+
+def cifar_bytes_to_matrix(images_cxy: np.ndarray) -> np.ndarray:
+    """CifarLoader's records (n, 3, 32, 32) -- RowColumnMajorByteArrayVectorizedImage: value (x, y, c) at y + x*yDim + c*yDim*xDim,
+    K/utils/images/Image.scala:333-340 -- as Convolver input rows."""
+    a = np.asarray(images_cxy)                       # [n][c][x][y]
+    return images_to_matrix(np.transpose(a, (0, 2, 3, 1)))
+
+
 class VectorCombiner(Transformer):
     """Concatenates the outputs of gathered branches (VectorCombiner.scala:11-14)."""
 

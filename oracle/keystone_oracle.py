@@ -534,3 +534,109 @@ def multiclass_metrics(cm: np.ndarray, beta: float = 1.0) -> dict:
                "total_accuracy": TP / (TP + FP), "total_error": FN / (FN + TP),
                "micro_precision": TP / (TP + FP), "micro_recall": TP / (TP + FN), "micro_fscore": fscore(TP, FP, FN)}
     return out
+
+
+# --------------------------------------------------------------------------------------
+# CIFAR random-patch featurizer.  Images are arrays img[x, y, c] with the reference's
+# coordinates: x runs over image ROWS (xDim = height), y over columns (yDim = width)
+# (K/utils/images/ImageConversions.scala:10-24, K/utils/images/Image.scala:140-143).
+#   Convolver          K/nodes/images/Convolver.scala:20-203
+#   Stats.normalizeRows K/utils/Stats.scala:112-123
+#   SymmetricRectifier K/nodes/images/SymmetricRectifier.scala:7-32
+#   Pooler             K/nodes/images/Pooler.scala:21-69
+#   ImageVectorizer    K/nodes/images/ImageVectorizer.scala:12-16 (Image.toArray, Image.scala:47-65)
+# --------------------------------------------------------------------------------------
+def image_from_bgr_bytes(rgb_hwc: np.ndarray) -> np.ndarray:
+    """What ImageUtils.loadImage yields for an 8-bit RGB file: Java decodes to TYPE_3BYTE_BGR, ByteArrayVectorizedImage indexes
+    it as get(x = row, y = column, c) with c = 0 blue, 1 green, 2 red (ImageConversions.scala:10-24, Image.scala:152-176)."""
+    return np.asarray(rgb_hwc)[:, :, ::-1].astype(F64)
+
+
+def flip_image(img: np.ndarray) -> np.ndarray:
+    """ImageUtils.flipImage (K/utils/images/ImageUtils.scala:376-389): all three axes reversed."""
+    return np.asarray(img, dtype=F64)[::-1, ::-1, ::-1].copy()
+
+
+def pack_filters(filters: Sequence[np.ndarray]) -> np.ndarray:
+    """Convolver.packFilters (:104-131): row i, column c + x*C + y*C*xDim = filters[i][x, y, c]."""
+    out = []
+    for f in filters:
+        f = np.asarray(f, dtype=F64)
+        out.append(np.transpose(f, (1, 0, 2)).reshape(-1))       # y slowest, then x, then c
+    return np.stack(out, axis=0)
+
+
+def normalize_rows(mat: np.ndarray, alpha: float = 1.0) -> np.ndarray:
+    """Stats.normalizeRows (K/utils/Stats.scala:112-123): subtract the row mean, divide by sqrt(sample variance (n-1) + alpha)."""
+    mat = np.asarray(mat, dtype=F64)
+    mean = np.nan_to_num(mat.mean(axis=1))
+    var = ((mat - mean[:, None]) ** 2).sum(axis=1) / (mat.shape[1] - 1.0)
+    sd = np.sqrt(var + alpha)
+    sd = np.where(np.isnan(sd), math.sqrt(alpha), sd)
+    return (mat - mean[:, None]) / sd[:, None]
+
+
+def make_patches(img: np.ndarray, conv_size: int, normalize: bool = True, whitener_means: Optional[np.ndarray] = None,
+                 var_constant: float = 10.0) -> np.ndarray:
+    """Convolver.makePatches (:152-203): patch row py = x + y*resWidth, column px = c + pox*C + poy*C*convSize holds
+    img[x + pox, y + poy, c]; rows optionally normalised (Stats.normalizeRows with varConstant) and shifted by the whitener's means."""
+    img = np.asarray(img, dtype=F64)
+    xd, yd, ch = img.shape
+    rw, rh = xd - conv_size + 1, yd - conv_size + 1
+    pm = np.empty((rw * rh, conv_size * conv_size * ch), dtype=F64)
+    for poy in range(conv_size):
+        for pox in range(conv_size):
+            win = img[pox:pox + rw, poy:poy + rh, :]                   # [x, y, c]
+            col0 = pox * ch + poy * ch * conv_size
+            pm[:, col0:col0 + ch] = np.transpose(win, (1, 0, 2)).reshape(rw * rh, ch)   # row index x + y*rw
+    if normalize:
+        pm = normalize_rows(pm, var_constant)
+    if whitener_means is not None:
+        pm = pm - np.asarray(whitener_means, dtype=F64)
+    return pm
+
+
+def convolve(img: np.ndarray, filters: np.ndarray, conv_size: int, normalize: bool = True,
+             whitener_means: Optional[np.ndarray] = None, var_constant: float = 10.0) -> np.ndarray:
+    """Convolver.convolve (:128-149): patches * filters^T, returned as an image out[x, y, f] (RowMajorArrayVectorizedImage of the
+    column-major product: value (x, y, f) at x + y*resWidth + f*resWidth*resHeight)."""
+    img = np.asarray(img, dtype=F64)
+    rw, rh = img.shape[0] - conv_size + 1, img.shape[1] - conv_size + 1
+    res = make_patches(img, conv_size, normalize, whitener_means, var_constant) @ np.asarray(filters, dtype=F64).T
+    return np.transpose(res.reshape(rh, rw, -1), (1, 0, 2))           # row index x + y*rw -> [y][x] -> [x, y, f]
+
+
+def symmetric_rectifier(img: np.ndarray, max_val: float = 0.0, alpha: float = 0.0) -> np.ndarray:
+    """SymmetricRectifier (:7-32): channels [0, C) = max(maxVal, v - alpha), channels [C, 2C) = max(maxVal, -v - alpha)."""
+    img = np.asarray(img, dtype=F64)
+    return np.concatenate([np.maximum(max_val, img - alpha), np.maximum(max_val, -img - alpha)], axis=2)
+
+
+def pooler(img: np.ndarray, stride: int, pool_size: int, pixel_fn=None, pool_fn=np.sum) -> np.ndarray:
+    """Pooler (:21-69): pools centred at strideStart = poolSize / 2, strideStart + stride, ...; a pool covers
+    [x - poolSize/2, min(x + poolSize/2, xDim)) in each direction (integer division); out[px, py, c] = poolFn(pixelFn(values))."""
+    img = np.asarray(img, dtype=F64)
+    xd, yd, ch = img.shape
+    s0 = pool_size // 2
+    npx, npy = int(math.ceil((xd - s0) / float(stride))), int(math.ceil((yd - s0) / float(stride)))
+    out = np.zeros((npx, npy, ch), dtype=F64)
+    for x in range(s0, xd, stride):
+        for y in range(s0, yd, stride):
+            reg = img[x - pool_size // 2:min(x + pool_size // 2, xd), y - pool_size // 2:min(y + pool_size // 2, yd), :]
+            if pixel_fn is not None:
+                reg = pixel_fn(reg)
+            out[(x - s0) // stride, (y - s0) // stride, :] = pool_fn(reg.reshape(-1, ch), axis=0)
+    return out
+
+
+def image_vectorizer(img: np.ndarray) -> np.ndarray:
+    """Image.toArray (Image.scala:47-65): flat[c + x*C + y*C*xDim] = img[x, y, c]."""
+    return np.transpose(np.asarray(img, dtype=F64), (1, 0, 2)).reshape(-1)
+
+
+def random_patch_cifar_features(img: np.ndarray, filters: np.ndarray, whitener_means: Optional[np.ndarray], conv_size: int = 6,
+                                alpha: float = 0.25, pool_stride: int = 13, pool_size: int = 14) -> np.ndarray:
+    """The featurizer of K/pipelines/images/cifar/RandomPatchCifar.scala:59-63: Convolver(filters, whitener, normalizePatches = true)
+    andThen SymmetricRectifier(alpha) andThen Pooler(stride, size, identity, sum) andThen ImageVectorizer."""
+    conv = convolve(img, filters, conv_size, True, whitener_means, 10.0)
+    return image_vectorizer(pooler(symmetric_rectifier(conv, 0.0, alpha), pool_stride, pool_size))

@@ -19,7 +19,21 @@ from oracle import keystone_oracle as ko  # noqa: E402
 FIXTURES = ["aMat.csv", "bMat.csv", "aMatShuffled.csv", "bMatShuffled.csv", "aMat-1class.csv", "bMat-1class.csv"]
 
 
+def convolver_fixture():
+    """3. conv_gantrycrane.npz: the reference's convolution test image (images/gantrycrane.png, decoded to 8-bit RGB) and channel 0
+    of the expected convolution (images/convolved.gantrycrane.csv: "x,y,value" lines of a ColumnMajorArrayVectorizedImage) --
+    T/nodes/images/ConvolverSuite.scala:100-137 ("convolutions should match scipy")."""
+    from PIL import Image
+    rgb = np.array(Image.open(os.path.join(REF, "images", "gantrycrane.png")).convert("RGB"), dtype=np.uint8)
+    raw = np.loadtxt(os.path.join(REF, "images", "convolved.gantrycrane.csv"), delimiter=",")
+    xd, yd = int(raw[:, 0].max()) + 1, int(raw[:, 1].max()) + 1
+    expected = raw[:, 2].reshape(xd, yd)          # value (x, y) at y + x * yDim
+    assert np.array_equal(expected, np.rint(expected))
+    np.savez_compressed(os.path.join(HERE, "conv_gantrycrane.npz"), rgb=rgb, expected=expected.astype(np.int32))
+
+
 def main():
+    convolver_fixture()
     for f in FIXTURES:
         shutil.copyfile(os.path.join(REF, f), os.path.join(HERE, f))
     A = np.loadtxt(os.path.join(HERE, "aMat.csv"), delimiter=",")

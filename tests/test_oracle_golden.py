@@ -312,3 +312,66 @@ def test_fft_featurizer_is_a_cosine_matrix_product():
     P = 1024
     M = s[None, :] * np.cos(2 * np.pi * np.outer(np.arange(P // 2), np.arange(784)) / P)
     assert np.abs(ko.padded_fft(ko.random_sign_node(x, s)) - x @ M.T).max() < 1e-9
+
+
+# ---- CIFAR random-patch featurizer nodes ------------------------------------------------------------
+def _gantrycrane(golden_dir):
+    z = np.load(os.path.join(golden_dir, "conv_gantrycrane.npz"))
+    return ko.image_from_bgr_bytes(z["rgb"]), z["expected"].astype(np.float64)
+
+
+def test_convolver_matches_reference_golden_image(golden_dir):
+    """T/nodes/images/ConvolverSuite.scala:100-137 ("convolutions should match scipy"): 3 x 3 x 3 filters with flipFilters = true,
+    no patch normalisation; channel 0 of the result equals the reference's convolved.gantrycrane.csv EXACTLY (integers)."""
+    img, expected = _gantrycrane(golden_dir)
+    kimg, kimg2 = np.zeros((3, 3, 3)), np.zeros((3, 3, 3))
+    i = 0
+    for x in range(3):
+        for y in range(3):
+            for c in range(3):
+                kimg[x, y, 2 - c] = float(i)        # channel order reversed to match python (:108)
+                i += 1
+    kimg2[0, 0, 0] = 2.0
+    kimg2[2, 0, 1] = 1.0
+    filt = ko.pack_filters([ko.flip_image(kimg), ko.flip_image(kimg2)])
+    conv = ko.convolve(img, filt, 3, normalize=False)
+    assert conv.shape == (expected.shape[0], expected.shape[1], 2)
+    assert np.array_equal(conv[:, :, 0], expected)
+
+
+def test_convolver_small_cases_and_patch_layout():
+    """ConvolverSuite.scala:13-98: output geometry for 1 x 1 and 3 x 3 filters on the 4 x 4 / 10 x 10 ramp images, and the patch
+    column order c + pox*C + poy*C*convSize of Convolver.makePatches (:152-186)."""
+    w, h, ch = 10, 10, 3
+    img = np.zeros((w, h, ch))
+    for x in range(w):
+        for y in range(h):
+            for c in range(ch):
+                img[x, y, c] = c + x * ch + y * w * ch
+    conv1 = np.zeros(27); conv1[4] = 1.0
+    conv2 = np.zeros(27); conv2[4] = conv2[13] = conv2[22] = 0.33
+    out = ko.convolve(img, np.stack([conv1, conv2]), 3, normalize=True)
+    assert out.shape == (8, 8, 2)
+    pm = ko.make_patches(img, 3, normalize=False)
+    assert pm.shape == (64, 27)
+    assert pm[2 + 3 * 8, 1 + 2 * 3 + 1 * 9] == img[2 + 2, 3 + 1, 1]      # row x + y*resW, column c + pox*C + poy*C*convSize
+    n = ko.normalize_rows(pm, 10.0)
+    assert np.abs(n.mean(axis=1)).max() < 1e-12
+    v = ((pm - pm.mean(1, keepdims=True)) ** 2).sum(1) / 26.0
+    assert np.allclose(n, (pm - pm.mean(1, keepdims=True)) / np.sqrt(v + 10.0)[:, None])
+
+
+def test_symmetric_rectifier_pooler_vectorizer():
+    """SymmetricRectifier.scala:7-32, Pooler.scala:21-69 (CIFAR geometry: 27 x 27 -> 2 x 2 pools of 14 x 14 that overlap in
+    row / column 13), Image.toArray order (Image.scala:47-65)."""
+    rng = np.random.default_rng(0)
+    img = rng.standard_normal((27, 27, 5))
+    r = ko.symmetric_rectifier(img, 0.0, 0.25)
+    assert r.shape == (27, 27, 10) and (r >= 0).all()
+    assert np.array_equal(r[:, :, :5], np.maximum(0, img - 0.25)) and np.array_equal(r[:, :, 5:], np.maximum(0, -img - 0.25))
+    p = ko.pooler(r, 13, 14)
+    assert p.shape == (2, 2, 10)
+    assert np.allclose(p[0, 0], r[0:14, 0:14].sum((0, 1))) and np.allclose(p[1, 0], r[13:27, 0:14].sum((0, 1)))
+    assert np.allclose(p[1, 1], r[13:27, 13:27].sum((0, 1)))
+    v = ko.image_vectorizer(p)
+    assert v.shape == (40,) and v[3 + 1 * 10 + 0 * 10 * 2] == p[1, 0, 3]
