@@ -463,9 +463,10 @@ def test_bwls_larger_problem_cosine_features(ctx):
     assert np.abs(pred - ref).max() < 5e-4
 
 
-@pytest.mark.parametrize("n,k", [(4096, 1000), (300, 37), (128, 8), (5, 3), (1000, 1)])
+@pytest.mark.parametrize("n,k", [(4096, 1000), (4096, 125), (4096, 250), (4096, 500), (300, 37), (128, 8), (5, 3), (1000, 1), (777, 130)])
 def test_chol_solve_kernel(ctx, n, k):
-    """The single-kernel multi-RHS Cholesky solve (replaces cusolverDnDpotrs on the critical chain) vs numpy, and vs cuSOLVER."""
+    """The library's DMMA multi-RHS Cholesky solve (one launch; clusters of 2 / 4 / 8 CTAs per column group when there are few
+    right-hand sides, as in the column-sharded multi-GPU solve) vs numpy, and vs cuSOLVER."""
     import ctypes as C
     from keystone_b200._capi import lib, check
     rng = np.random.default_rng(n + k)
@@ -654,7 +655,7 @@ def test_cifar_loader_layout_feeds_the_convolver(ctx):
     row = ks.cifar_bytes_to_matrix(planes)
     img = np.transpose(planes[0].astype(np.float64), (1, 2, 0))              # [x, y, c]
     assert np.array_equal(row[0], ko.image_vectorizer(img).astype(np.float32))
-    filt = np.eye(108)[:4]                                                   # filter f responds to patch column f
+    filt = np.eye(108)[:32]                                                  # filter f responds to patch column f
     out = ks.Convolver(ctx, filt, 32, 32, 3, None, normalize_patches=False)(ctx.matrix(row)).to_numpy()
     ref = ko.convolve(img, filt, 6, normalize=False)
-    assert np.array_equal(np.transpose(out[0].reshape(27, 27, 4), (1, 0, 2)), ref)
+    assert np.array_equal(np.transpose(out[0].reshape(27, 27, 32), (1, 0, 2)), ref)
