@@ -82,8 +82,8 @@ KS_API int32_t ks_ctx_synchronize(int64_t ctx);
  * buffers], "proj_f16" [1: fp16 projection operands in fp16 mode], "shard_solve" [1: triangular solves sharded by
  * right-hand-side columns over the ranks], "reserve_sms" [8], "timing" [1], "pipeline" [1: all tensor-core kernels of a fit on
  * one stream, solve / factor chains beside it; 0: the two-stream arrangement of round 1], "host_mirror" [1: fits copy each
- * finished model block into pinned host memory while they run]; "custom_solve" [0: cusolverDnDpotrs; 1: the library's
- * own DMMA multi-right-hand-side triangular solve kernel], "dyn_tiles" [1: the projection kernel draws its tiles from a
+ * finished model block into pinned host memory while they run]; "custom_solve" [-1: automatic -- the library's own DMMA
+ * multi-right-hand-side triangular solve kernel when a rank solves <= 512 columns (multi-GPU), cusolverDnDpotrs otherwise; 0 / 1 force], "dyn_tiles" [1: the projection kernel draws its tiles from a
  * counter], "solve_lanes" [4: concurrent per-class solves of the weighted solver]. */
 KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value);
 

@@ -809,6 +809,9 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   const size_t es = f16 ? 2 : 4;  // bytes per slab / operand element
   const int64_t x2_chunk = 2048;  // short accumulation chains: the tensor core's fp32 accumulate truncates (~2^-25 per MMA step)
   const int NBUF = 3;
+  // which kernel performs the triangular solves of the critical chain (Ctx::custom_solve)
+  const bool custom_solve = c.custom_solve == 1 || (c.custom_solve < 0 && c.world > 1 && c.shard_solve && k >= c.world &&
+                                                    (k + c.world - 1) / c.world <= 512);
   DevBuf r_f32, r_op, cm, rhs, rsum, bop, cbias, samp, fsum, scales, sf32, r_lo, bop_lo;
   std::unique_ptr<DevBuf[]> slab_lo;
   std::unique_ptr<DevBuf[]> slab(new DevBuf[NBUF]), gbuf(new DevBuf[NBUF]), Hbuf(new DevBuf[NBUF]), ssum(new DevBuf[NBUF]);
@@ -840,7 +843,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     gbuf[i].alloc(sizeof(float) * g_elems * (x2 ? 2 : 1));  // x2: S_hi^T S_hi (upper tiles) followed by the full S_hi^T S_lo
     ssum[i].alloc(sizeof(float) * lds);
     if (!cache_factors) Hbuf[i].alloc(sizeof(double) * static_cast<size_t>(bmax) * bmax);
-    if (!cache_factors && c.custom_solve) Dbuf[i].alloc(sizeof(double) * chol_solve_dinv_doubles(bmax));
+    if (!cache_factors && custom_solve) Dbuf[i].alloc(sizeof(double) * chol_solve_dinv_doubles(bmax));
   }
   cm.alloc(sizeof(float) * c_elems);
   rhs.alloc(sizeof(double) * static_cast<size_t>(bmax) * k);
@@ -888,6 +891,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   int info_slot = 0;
   double flops = 0;
   const bool shard_solve = c.world > 1 && c.shard_solve && k >= c.world;
+
 
   // ---------------- proj(t): shift estimate (first sweep) + slab of step t, on ST
   auto do_proj = [&](int t) {
@@ -983,14 +987,14 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       factors[j] = std::make_unique<DevBuf>();
       factors[j]->alloc(sizeof(double) * static_cast<size_t>(b) * b);
       Hj = factors[j]->as<double>();
-      if (c.custom_solve) {
+      if (custom_solve) {
         dinvs[j] = std::make_unique<DevBuf>();
         dinvs[j]->alloc(sizeof(double) * chol_solve_dinv_doubles(b));
         Dj = dinvs[j]->as<double>();
       }
     } else {
       Hj = Hbuf[buf].as<double>();
-      if (c.custom_solve) Dj = Dbuf[buf].as<double>();
+      if (custom_solve) Dj = Dbuf[buf].as<double>();
     }
     KS_CUDA(cudaStreamWaitEvent(SF, ev_g[t], 0));
     c.span_begin(PH_SOLVE, SF);
@@ -1051,9 +1055,9 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     launch_build_rhs(cm.as<float>(), ldc, deltas[j]->as<double>(), rsum.as<double>(), n_total_d, lam,
                      it > 0 ? model->W[j]->as<double>() : nullptr, rhs.as<double>(), b, k, SS, f16 ? rscale + 1 : nullptr);
     c.launches += 1;
-    const double* Dj = !c.custom_solve ? nullptr : cache_factors ? dinvs[j]->as<double>() : Dbuf[buf].as<double>();
+    const double* Dj = !custom_solve ? nullptr : cache_factors ? dinvs[j]->as<double>() : Dbuf[buf].as<double>();
     auto solve_cols = [&](double* cols, int ncols) {  // (L L^T)^-1 on `ncols` right-hand sides, in place
-      if (c.custom_solve) {
+      if (custom_solve) {
         KS_CUDA(launch_chol_solve(Hj, Dj, b, cols, ncols, SS));  // one launch, runs beside the look-ahead Gram (solve_kernels.cu)
         c.launches += 1;
       } else {
@@ -1188,7 +1192,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
      << ",\"update_ms\":" << ms[PH_UPDATE] << ",\"other_ms\":" << ms[PH_OTHER] << ",\"local_flops\":" << flops
      << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"" << (x2 ? (f16 ? "f16x2" : "tf32x2") : f16 ? "f16" : "tf32x1")
      << "\",\"pipeline\":" << c.pipeline << ",\"host_mirror\":" << (model->host_valid ? 1 : 0) << ",\"solve\":\""
-     << (c.custom_solve ? "dmma-kernel" : "potrs") << (shard_solve ? "-column-sharded" : "") << "\",\"host_ms\":"
+     << (custom_solve ? "dmma-kernel" : "potrs") << (shard_solve ? "-column-sharded" : "") << "\",\"host_ms\":"
      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count() << "}";
   c.stats_json = js.str();
   return c.add(std::move(model));
@@ -1377,7 +1381,7 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
     if (const char* e = getenv("KS_PROJ_F16")) c->proj_f16 = atoi(e) != 0;
     if (const char* e = getenv("KS_PRECISION"))
       c->precision = (atoi(e) == 1 || !strcmp(e, "f16")) ? KS_PRECISION_F16 : (atoi(e) == 2 || !strcmp(e, "f16x2") || !strcmp(e, "parity")) ? KS_PRECISION_F16X2 : KS_PRECISION_TF32;
-    if (const char* e = getenv("KS_CUSTOM_SOLVE")) c->custom_solve = atoi(e) != 0;
+    if (const char* e = getenv("KS_CUSTOM_SOLVE")) c->custom_solve = std::max(-1, std::min(1, atoi(e)));
     if (const char* e = getenv("KS_RESERVE_SMS")) c->reserve_sms = std::max(0, std::min(140, atoi(e)));
     if (const char* e = getenv("KS_PIPELINE")) c->pipeline = std::max(0, std::min(3, atoi(e)));
     if (const char* e = getenv("KS_HOST_MIRROR")) c->host_mirror = atoi(e) != 0;
@@ -1482,7 +1486,7 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     else if (n == "shard_solve") c.shard_solve = value != 0;
     else if (n == "proj_f16") c.proj_f16 = value != 0;
     else if (n == "precision" && (value == KS_PRECISION_TF32 || value == KS_PRECISION_F16 || value == KS_PRECISION_F16X2)) c.precision = static_cast<int>(value);
-    else if (n == "custom_solve") c.custom_solve = value != 0;
+    else if (n == "custom_solve" && value >= -1 && value <= 1) c.custom_solve = static_cast<int>(value);
     else if (n == "reserve_sms" && value >= 0 && value < 148) c.reserve_sms = static_cast<int>(value);
     else if (n == "pipeline" && value >= 0 && value <= 3) c.pipeline = static_cast<int>(value);
     else if (n == "dyn_tiles") c.dyn_tiles = value != 0;

@@ -199,11 +199,13 @@ struct Ctx {
   int proj_f16 = 1;   // fp16 mode: the projection GEMM X W^T runs with fp16 operands too (0: tf32 operands, fp16 slab)
   int precision = KS_PRECISION_F16X2;  // what KS_PRECISION_DEFAULT resolves to: the split-operand parity mode
   int reserve_sms = 8; // SMs the persistent look-ahead kernel leaves to the critical chain
-  int custom_solve = 0; // 0 = cusolverDnDpotrs; 1 = the library's DMMA solve kernel (one launch that runs beside the look-ahead
-                        // Gram CTAs, solve_kernels.cu).  Measured in the config-3 fit (profiles/README.md, round 2): the kernel
-                        // hides completely under the Gram (11.9 ms vs 18.7 ms for potrs, which leaves 5.7 ms exposed) but slows
-                        // that Gram from 13.0 to 17.1 ms (L2 + tensor-pipe sharing): 39.5 vs 40.4 ms per block, a wash; and
-                        // its latency does not shrink with the column-sharded solve of the multi-GPU fit.  Kept as an option.
+  int custom_solve = -1; // triangular solves of the critical chain: 0 = cusolverDnDpotrs, 1 = the library's DMMA kernel
+                         // (solve_kernels.cu: one launch, co-resident with the look-ahead Gram CTAs), -1 = automatic: the DMMA
+                         // kernel when the rank solves <= 512 right-hand sides (the column-sharded multi-GPU solve, where its
+                         // CTA clusters cut the latency: 1.6 - 2.7 ms for 125 - 500 columns vs 2.6 - 3.0 ms for potrs alone and
+                         // ~10 ms for potrs next to the tensor kernels), potrs otherwise.  Measured (profiles/README.md, round 2):
+                         // N = 1, 1000 columns: the kernel hides under the Gram (11.9 vs 18.7 ms) but slows that Gram from 13.0
+                         // to 17.1 ms -- a wash; N = 2, 500 columns: 341.9 vs 352.9 ms per fit.
   int64_t sample_rows = 16384;
   int64_t next_id = 1;
   std::unordered_map<int64_t, std::unique_ptr<Matrix>> matrices;

@@ -15,6 +15,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _worker(rank, world, id_holder, ret, pipeline, precision):
     sys.path.insert(0, ROOT)
     os.environ["KS_PIPELINE"] = str(pipeline)
+    os.environ["KS_CUSTOM_SOLVE"] = "0" if pipeline == 0 else "-1"      # cuSOLVER potrs in the round-1 arrangement, automatic otherwise
     import keystone_b200 as ks
     from oracle import keystone_oracle as ko
     rng = np.random.default_rng(21)
@@ -31,6 +32,7 @@ def _worker(rank, world, id_holder, ret, pipeline, precision):
     model = ks.BlockLeastSquaresEstimator(n_out, 2, 0.5, precision=precision).fit(feats, y)
     assert ctx.last_fit_stats()["mma"] == {"f16": "f16", "tf32": "tf32x1", "default": "f16x2"}[precision]
     assert ctx.last_fit_stats()["pipeline"] == pipeline
+    assert ctx.last_fit_stats()["solve"] == ("potrs-column-sharded" if pipeline == 0 else "dmma-kernel-column-sharded")
     W = np.concatenate(model.xs, 0)
     cost = model.compute_cost(feats, y, 0.5)
     if rank == 0:
