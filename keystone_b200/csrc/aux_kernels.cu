@@ -659,7 +659,7 @@ void launch_f32_to_f16_rows(const float* src, int64_t src_ld, void* dst, int64_t
 // R16lo (optional, split-operand mode): the fp16 rounding error of the scaled value, fp16(R * scale - R16)
 __global__ void round_colsum16_kernel(const float* __restrict__ R, __half* __restrict__ R16, int64_t ld, int64_t rows, int k,
                                       double* __restrict__ sums, int64_t rows_per_block, const float* __restrict__ scale,
-                                      __half* __restrict__ R16lo) {
+                                      __half* __restrict__ R16lo, unsigned* __restrict__ overflow) {
   __shared__ double red[8][128];
   const float sc = __ldg(scale);
   const int c4 = (blockIdx.x * 32 + threadIdx.x) * 4;
@@ -677,6 +677,9 @@ __global__ void round_colsum16_kernel(const float* __restrict__ R, __half* __res
         if (c < k) {
           a[j] += in[j];
           o[j] = in[j] * sc;
+          // the residual's scale was fixed from max|R_0| with 16x headroom; a residual that grew past fp16's range (its max
+          // norm is not monotone under block coordinate descent) must not turn into inf silently
+          if (overflow && !(fabsf(o[j]) <= 65504.f)) *overflow = 1u;
         } else {
           o[j] = 0.f;
         }
@@ -709,12 +712,12 @@ __global__ void round_colsum16_kernel(const float* __restrict__ R, __half* __res
   }
 }
 void launch_round_colsum16(const float* R, void* R16, int64_t ld, int64_t rows, int k, double* sums, const float* scale,
-                           cudaStream_t st, void* R16lo) {
+                           cudaStream_t st, void* R16lo, unsigned* overflow) {
   if (rows == 0) return;
   const int64_t rpb = 1024;
   dim3 grid(static_cast<unsigned>((ld + 127) / 128), static_cast<unsigned>((rows + rpb - 1) / rpb));
   round_colsum16_kernel<<<grid, dim3(32, 8), 0, st>>>(R, static_cast<__half*>(R16), ld, rows, k, sums, rpb, scale,
-                                                      static_cast<__half*>(R16lo));
+                                                      static_cast<__half*>(R16lo), overflow);
 }
 
 // fp16 twin of pack_update_kernel: bop16[c][f] = fp16(dW[f][c] * scale[0]); Wmodel and cbias exactly as the tf32 version

@@ -808,7 +808,11 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   const bool f16 = !src.F && src.kind == 0 && (precision == KS_PRECISION_F16 || x2);
   const size_t es = f16 ? 2 : 4;  // bytes per slab / operand element
   const int64_t x2_chunk = 2048;  // short accumulation chains: the tensor core's fp32 accumulate truncates (~2^-25 per MMA step)
-  const int NBUF = 3;
+  // look-ahead of the residual-independent work (projection, G-Gram, factorisation) over the residual chain, in blocks.  With the
+  // rows sharded over GPUs the Cholesky of block t+1 (2.5 ms alone, more next to tensor kernels) sits in a dependency cycle
+  // G(t+1) -> factor(t+1) -> solve(t+1) -> update(t+1) -> ... -> G(t+1+LA): a deeper look-ahead spreads it over more blocks.
+  const int LA = (serial && c.pipeline == 1) ? (c.lookahead > 0 ? c.lookahead : (c.world > 1 ? 2 : 1)) : 1;
+  const int NBUF = LA + 2;
   // which kernel performs the triangular solves of the critical chain (Ctx::custom_solve)
   const bool custom_solve = c.custom_solve == 1 || (c.custom_solve < 0 && c.world > 1 && c.shard_solve && k >= c.world &&
                                                     (k + c.world - 1) / c.world <= 512);
@@ -1020,7 +1024,8 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     c.span_begin(PH_OTHER, SR);
     KS_CUDA(cudaMemsetAsync(cm.p, 0, sizeof(float) * c_elems, SR));
     KS_CUDA(cudaMemsetAsync(rsum.p, 0, rsum.bytes, SR));
-    if (f16) launch_round_colsum16(r_f32.as<float>(), r_op.p, kpad, n_loc, k, rsum.as<double>(), rscale, SR, x2 ? r_lo.p : nullptr);
+    if (f16) launch_round_colsum16(r_f32.as<float>(), r_op.p, kpad, n_loc, k, rsum.as<double>(), rscale, SR, x2 ? r_lo.p : nullptr,
+                                   maxbits + 6);   // scales[6]: fp16 overflow flag of the residual operand
     else launch_round_colsum(r_f32.as<float>(), r_op.as<float>(), kpad, n_loc, k, rsum.as<double>(), SR, x2 ? r_lo.as<float>() : nullptr);
     c.launches += 1;
     c.span_end(SR);
@@ -1126,15 +1131,21 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   // Enqueue order: a stream-wait on an event that has not been recorded yet counts as complete, so every wait is enqueued
   // after the corresponding record.
   if (serial) {
-    // tensor stream: proj(0) proj(1) G(0) | C(t) G(t+1) update(t) proj(t+2) | ...   (slab (t+2)%3 was last read by
-    // update(t-1), G buffer (t+1)%3 by factor(t-2): both precede in stream / event order).  The solve of step t runs beside
+    // tensor stream (look-ahead LA, LA + 2 buffers): proj(0..LA) G(0..LA-1) | C(t) G(t+LA) update(t) proj(t+LA+1) | ...
+    // (slab (t+LA+1) % (LA+2) was last read by update(t-1), G buffer (t+LA) % (LA+2) by factor(t-2): both precede in stream / event order).  The solve of step t runs beside
     // G(t+1): its CTAs fit on the SMs next to Gram CTAs (solve_kernels.cu), not next to the register-heavy projection kernel,
     // which therefore comes after the update (pipeline = 2 puts it before, for A/B runs).
-    for (int t = 0; t < std::min(T, 2); ++t) do_proj(t);
-    do_gram(0);
+    for (int t = 0; t < std::min(T, LA + 1); ++t) do_proj(t);
+    for (int t = 0; t < std::min(T, LA); ++t) do_gram(t);
     for (int t = 0; t < T; ++t) {
       do_cgram(t);
       do_solve(t);
+      if (c.pipeline == 1) {  // default: C(t), G(t+LA), update(t), proj(t+LA+1)
+        if (t + LA < T) do_gram(t + LA);
+        do_update(t);
+        if (t + LA + 1 < T) do_proj(t + LA + 1);
+        continue;
+      }
       if (c.pipeline == 3) {  // the solve runs beside the projection (persistent kernel that leaves reserve_sms SMs free)
         if (t + 2 < T) do_proj(t + 2);
         do_update(t);
@@ -1172,6 +1183,15 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   KS_CUDA(cudaEventRecord(ev1, S1));
   c.check_async("BlockLeastSquaresEstimator.fit");
   c.check_infos(info_slot);
+  if (f16) {  // collective by construction: every rank scales alike, but only some may overflow -> all-reduce the flag first
+    c.allreduce_max_u32(maxbits + 6, 1);
+    unsigned ovf = 0;
+    KS_CUDA(cudaMemcpyAsync(&ovf, maxbits + 6, sizeof(unsigned), cudaMemcpyDeviceToHost, S1));
+    KS_CUDA(cudaStreamSynchronize(S1));
+    if (ovf)
+      throw KsError{KS_ERR_INVALID, "the residual left fp16's range during the fit (it grew more than 16x over the centred labels): "
+                                    "use KS_PRECISION_TF32 for this problem"};
+  }
   float total_ms = 0;
   cudaEventElapsedTime(&total_ms, ev0, ev1);
   double ms[PH_COUNT];
@@ -1191,7 +1211,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
      << ",\"gram_ms\":" << ms[PH_GRAM] << ",\"allreduce_ms\":" << ms[PH_ALLREDUCE] << ",\"solve_ms\":" << ms[PH_SOLVE]
      << ",\"update_ms\":" << ms[PH_UPDATE] << ",\"other_ms\":" << ms[PH_OTHER] << ",\"local_flops\":" << flops
      << ",\"launches\":" << (c.launches - launches0) << ",\"mma\":\"" << (x2 ? (f16 ? "f16x2" : "tf32x2") : f16 ? "f16" : "tf32x1")
-     << "\",\"pipeline\":" << c.pipeline << ",\"host_mirror\":" << (model->host_valid ? 1 : 0) << ",\"solve\":\""
+     << "\",\"pipeline\":" << c.pipeline << ",\"lookahead\":" << LA << ",\"host_mirror\":" << (model->host_valid ? 1 : 0) << ",\"solve\":\""
      << (custom_solve ? "dmma-kernel" : "potrs") << (shard_solve ? "-column-sharded" : "") << "\",\"host_ms\":"
      << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count() << "}";
   c.stats_json = js.str();
@@ -1385,6 +1405,7 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
     if (const char* e = getenv("KS_RESERVE_SMS")) c->reserve_sms = std::max(0, std::min(140, atoi(e)));
     if (const char* e = getenv("KS_PIPELINE")) c->pipeline = std::max(0, std::min(3, atoi(e)));
     if (const char* e = getenv("KS_HOST_MIRROR")) c->host_mirror = atoi(e) != 0;
+    if (const char* e = getenv("KS_LOOKAHEAD")) c->lookahead = std::max(0, std::min(6, atoi(e)));
     KS_CUDA(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, prio_least));
     KS_CUDA(cudaStreamCreateWithPriority(&c->st3, cudaStreamNonBlocking, prio_mid));
     KS_CUDA(cudaStreamCreateWithPriority(&c->st4, cudaStreamNonBlocking, prio_mid));
@@ -1490,6 +1511,7 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     else if (n == "reserve_sms" && value >= 0 && value < 148) c.reserve_sms = static_cast<int>(value);
     else if (n == "pipeline" && value >= 0 && value <= 3) c.pipeline = static_cast<int>(value);
     else if (n == "dyn_tiles") c.dyn_tiles = value != 0;
+    else if (n == "lookahead" && value >= 0 && value <= 6) c.lookahead = static_cast<int>(value);
     else if (n == "solve_lanes" && value >= 1 && value <= 16) c.solve_lanes = static_cast<int>(value);
     else if (n == "host_mirror") c.host_mirror = value != 0;
     else if (n == "timing") c.timing = value != 0;

@@ -166,6 +166,7 @@ struct Ctx {
   ncclComm_t comm2 = nullptr;  // collectives issued on st2 (split of comm; falls back to comm)
   ncclComm_t comm3 = nullptr;  // collectives issued on st4 (pipeline 1: all-reduce of G)
   int pipeline = 1;
+  int lookahead = 0;    // blocks the projection / G-Gram / factorisation run ahead of the residual chain; 0 = 1 on one GPU, 2 on several
   int host_mirror = 1;  // fits mirror the model into pinned host memory while they run
   int shard_solve = 1;  // world > 1: every rank runs the triangular solves for its k / world right-hand sides only and the
                         // columns of dW are gathered (grouped ncclBroadcast, 32 MB at b = 4096, k = 1000) -- the solve is the

@@ -135,7 +135,7 @@ void launch_pow2_scale(const unsigned* maxbits, float target, float* scale, cuda
 void launch_f32_to_f16_rows(const float* src, int64_t src_ld, void* dst, int64_t dst_ld, int64_t rows, int64_t cols, cudaStream_t st,
                             const float* scale = nullptr);  // optional device scalar multiplied in before the conversion
 void launch_round_colsum16(const float* R, void* R16, int64_t ld, int64_t rows, int k, double* sums, const float* scale,
-                           cudaStream_t st, void* R16lo = nullptr);
+                           cudaStream_t st, void* R16lo = nullptr, unsigned* overflow = nullptr);  // *overflow = 1 if |R * scale| left fp16's range
 void launch_pack_update16(const double* dW, double* Wmodel, const double* delta, void* bop16, int ldb, float* cbias, int b, int k,
                           int kpad, const float* scale, cudaStream_t st, void* bop16_lo = nullptr);
 // split-operand mode: hi / lo fp16 planes of an fp32 matrix (+ column sums of hi + lo), and the K-concatenated projection operands

@@ -145,8 +145,48 @@ def c5():
           "solve_lanes": st["solve_lanes"], "launches": st["launches"], "finite": bool(all(np.isfinite(wj).all() for wj in m.xs))})
 
 
+def c4f():
+    """C4 WITH its featurizer (RandomPatchCifar.scala:59-66): synthetic CIFAR-shaped images -> Convolver(20000 random 6x6x3 filters,
+    whitener means, normalised patches) -> SymmetricRectifier(0.25) -> Pooler(13, 14, sum) -> D = 160000 features on the device ->
+    BlockLeastSquaresEstimator(4096, 1, lambda = 3000)."""
+    n, nf, k, bs, lam = args.c4_rows, 20000, 10, 4096, 3000.0
+    lo, hi = ks.shard_range(n, rank, world)
+    rng = np.random.default_rng([3, lo])
+    imgs = rng.integers(0, 256, (hi - lo, 3, 32, 32), dtype=np.uint8)              # CifarLoader layout
+    prm = np.random.default_rng(33)
+    filters = prm.standard_normal((nf, 108)) / 10.0
+    wmeans = prm.standard_normal(108) * 0.05
+    x = ctx.matrix(ks.cifar_bytes_to_matrix(imgs))
+    conv = ks.Convolver(ctx, filters, 32, 32, 3, wmeans, True, 10.0)
+    chain = conv.andThen(ks.SymmetricRectifier(alpha=0.25)).andThen(ks.Pooler(13, 14)).andThen(ks.ImageVectorizer())
+    chain(ctx.matrix(ks.cifar_bytes_to_matrix(imgs[:64])))                          # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    feats = chain(x)
+    barrier()
+    t_feat = time.perf_counter() - t0
+    cls = rng.integers(0, k, hi - lo).astype(np.int32)
+    y = ctx.labels_from_classes(cls, k)
+    m, dt = timed_fit(ks.BlockLeastSquaresEstimator(bs, 1, lam, precision=args.precision), feats, y, reps=1)
+    st = ctx.last_fit_stats()
+    rec = {"config": f"C4 with featurizer: N={n} CIFAR-shaped images, 20000 filters -> D=160000, k=10, lambda=3000", "gpus": world,
+           "featurize_s": t_feat, "images_per_s": n / t_feat, "featurize_precision": "split fp16 operands (context default)",
+           "fit_precision": st["mma"], "fit_s": dt, "pipeline_samples_per_s": n / (t_feat + dt), "num_blocks": st["num_blocks"],
+           "finite": bool(all(np.isfinite(w).all() for w in m.xs))}
+    if world == 1 and args.parity_rows:
+        from oracle import keystone_oracle as ko
+        ns = 32
+        sub = np.transpose(imgs[:ns].astype(np.float64), (0, 2, 3, 1))              # [n][x][y][c]
+        ref = np.stack([ko.random_patch_cifar_features(im, filters[:256], wmeans, 6, 0.25, 13, 14) for im in sub])
+        conv_s = ks.Convolver(ctx, filters[:256], 32, 32, 3, wmeans, True, 10.0)
+        got = conv_s.andThen(ks.SymmetricRectifier(alpha=0.25)).andThen(ks.Pooler(13, 14)).andThen(ks.ImageVectorizer())(
+            ctx.matrix(ks.cifar_bytes_to_matrix(imgs[:ns]))).to_numpy()
+        rec["parity"] = {"images": ns, "filters": 256, "max_rel_err_features": float(np.abs(got - ref).max() / np.abs(ref).max())}
+    emit(rec)
+
+
 for name in args.configs:
-    {"c2": c2, "c4": c4, "c5": c5}[name]()
+    {"c2": c2, "c4": c4, "c4f": c4f, "c5": c5}[name]()
 ctx.close()
 if world > 1:
     dist.destroy_process_group()
