@@ -811,7 +811,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   // look-ahead of the residual-independent work (projection, G-Gram, factorisation) over the residual chain, in blocks.  With the
   // rows sharded over GPUs the Cholesky of block t+1 (2.5 ms alone, more next to tensor kernels) sits in a dependency cycle
   // G(t+1) -> factor(t+1) -> solve(t+1) -> update(t+1) -> ... -> G(t+1+LA): a deeper look-ahead spreads it over more blocks.
-  const int LA = (serial && c.pipeline == 1) ? (c.lookahead > 0 ? c.lookahead : (c.world > 1 ? 2 : 1)) : 1;
+  const int LA = (serial && (c.pipeline == 1 || c.pipeline == 4)) ? (c.lookahead > 0 ? c.lookahead : (c.world > 1 ? 2 : 1)) : 1;
   const int NBUF = LA + 2;
   // which kernel performs the triangular solves of the critical chain (Ctx::custom_solve)
   const bool custom_solve = c.custom_solve == 1 || (c.custom_solve < 0 && c.world > 1 && c.shard_solve && k >= c.world &&
@@ -1140,9 +1140,15 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     for (int t = 0; t < T; ++t) {
       do_cgram(t);
       do_solve(t);
-      if (c.pipeline == 1) {  // default: C(t), G(t+LA), update(t), proj(t+LA+1)
+      if (c.pipeline == 1) {  // C(t), G(t+LA), update(t), proj(t+LA+1): the solve of step t runs beside G(t+LA)
         if (t + LA < T) do_gram(t + LA);
         do_update(t);
+        if (t + LA + 1 < T) do_proj(t + LA + 1);
+        continue;
+      }
+      if (c.pipeline == 4) {  // C(t), update(t), G(t+LA), proj(t+LA+1): the tensor stream waits for the solve; nothing shares the
+        do_update(t);         // GPU with it except the factor chain of the block ahead
+        if (t + LA < T) do_gram(t + LA);
         if (t + LA + 1 < T) do_proj(t + LA + 1);
         continue;
       }
@@ -1403,7 +1409,7 @@ KS_API int32_t ks_ctx_create(int32_t device_id, int32_t rank, int32_t world_size
       c->precision = (atoi(e) == 1 || !strcmp(e, "f16")) ? KS_PRECISION_F16 : (atoi(e) == 2 || !strcmp(e, "f16x2") || !strcmp(e, "parity")) ? KS_PRECISION_F16X2 : KS_PRECISION_TF32;
     if (const char* e = getenv("KS_CUSTOM_SOLVE")) c->custom_solve = std::max(-1, std::min(1, atoi(e)));
     if (const char* e = getenv("KS_RESERVE_SMS")) c->reserve_sms = std::max(0, std::min(140, atoi(e)));
-    if (const char* e = getenv("KS_PIPELINE")) c->pipeline = std::max(0, std::min(3, atoi(e)));
+    if (const char* e = getenv("KS_PIPELINE")) c->pipeline = std::max(0, std::min(4, atoi(e)));
     if (const char* e = getenv("KS_HOST_MIRROR")) c->host_mirror = atoi(e) != 0;
     if (const char* e = getenv("KS_LOOKAHEAD")) c->lookahead = std::max(0, std::min(6, atoi(e)));
     KS_CUDA(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, prio_least));
@@ -1509,7 +1515,7 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
     else if (n == "precision" && (value == KS_PRECISION_TF32 || value == KS_PRECISION_F16 || value == KS_PRECISION_F16X2)) c.precision = static_cast<int>(value);
     else if (n == "custom_solve" && value >= -1 && value <= 1) c.custom_solve = static_cast<int>(value);
     else if (n == "reserve_sms" && value >= 0 && value < 148) c.reserve_sms = static_cast<int>(value);
-    else if (n == "pipeline" && value >= 0 && value <= 3) c.pipeline = static_cast<int>(value);
+    else if (n == "pipeline" && value >= 0 && value <= 4) c.pipeline = static_cast<int>(value);
     else if (n == "dyn_tiles") c.dyn_tiles = value != 0;
     else if (n == "lookahead" && value >= 0 && value <= 6) c.lookahead = static_cast<int>(value);
     else if (n == "solve_lanes" && value >= 1 && value <= 16) c.solve_lanes = static_cast<int>(value);

@@ -14,6 +14,8 @@
 // Every epilogue goes TMEM -> registers -> 128 B-swizzled shared staging -> TMA store / TMA reduce-add, so global
 // memory only ever sees full 128 B rows (the first version stored 16 B per row per lane: 32 wavefronts per warp
 // instruction, which made the cosine epilogue 3x longer than its MMAs -- profiles/README.md).
+#include <type_traits>
+
 #include "tc_common.cuh"
 #include "kernels.h"
 
@@ -574,46 +576,51 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
           stage_row_sw128(buf, lane, o);
           __syncwarp();
           const int f = n0 + c0 + lane;
-          constexpr int kMaxPools = 16;
-          float ap[kMaxPools], an[kMaxPools];
+          // pool loops are compile-time unrolled over 4 (the CIFAR geometry: 2 x 2 pools) or 16 accumulator pairs
+          auto run = [&](auto np_tag) {
+            constexpr int NP = decltype(np_tag)::value;
+            float ap[NP], an[NP];
 #pragma unroll
-          for (int pl = 0; pl < kMaxPools; ++pl) ap[pl] = an[pl] = 0.f;
-          int cur = __shfl_sync(0xffffffffu, my_img, 0);
-          unsigned touched = 0;
-          auto flush = [&](int img) {
-            if (f < p.N && touched) {
-              float* dst = p.pool_out + static_cast<int64_t>(img) * p.pool_out_ld + f;
+            for (int pl = 0; pl < NP; ++pl) ap[pl] = an[pl] = 0.f;
+            int cur = __shfl_sync(0xffffffffu, my_img, 0);
+            unsigned touched = 0;
+            auto flush = [&](int img) {
+              if (f < p.N && touched) {
+                float* dst = p.pool_out + static_cast<int64_t>(img) * p.pool_out_ld + f;
 #pragma unroll
-              for (int pl = 0; pl < kMaxPools; ++pl)
-                if (touched >> pl & 1) {
-                  atomicAdd(dst + static_cast<int64_t>(pl) * 2 * p.N, ap[pl]);
-                  atomicAdd(dst + static_cast<int64_t>(pl) * 2 * p.N + p.N, an[pl]);
-                  ap[pl] = an[pl] = 0.f;
-                }
-            }
-            touched = 0;
-          };
+                for (int pl = 0; pl < NP; ++pl)
+                  if (touched >> pl & 1) {
+                    atomicAdd(dst + static_cast<int64_t>(pl) * 2 * p.N, ap[pl]);
+                    atomicAdd(dst + static_cast<int64_t>(pl) * 2 * p.N + p.N, an[pl]);
+                    ap[pl] = an[pl] = 0.f;
+                  }
+              }
+              touched = 0;
+            };
 #pragma unroll 1
-          for (int r = 0; r < 32; ++r) {
-            const int im = __shfl_sync(0xffffffffu, my_img, r);
-            const unsigned mk = __shfl_sync(0xffffffffu, my_mask, r);
-            if (im != cur) {  // warp-uniform
-              flush(cur);
-              cur = im;
-            }
-            if (mk) {
-              const float val = *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
-              const float pos = fmaxf(p.rect_floor, val - p.pool_alpha), neg = fmaxf(p.rect_floor, -val - p.pool_alpha);
+            for (int r = 0; r < 32; ++r) {
+              const int im = __shfl_sync(0xffffffffu, my_img, r);
+              const unsigned mk = __shfl_sync(0xffffffffu, my_mask, r);
+              if (im != cur) {  // warp-uniform
+                flush(cur);
+                cur = im;
+              }
+              if (mk) {
+                const float val = *reinterpret_cast<const float*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
+                const float pos = fmaxf(p.rect_floor, val - p.pool_alpha), neg = fmaxf(p.rect_floor, -val - p.pool_alpha);
 #pragma unroll
-              for (int pl = 0; pl < kMaxPools; ++pl)
-                if (mk >> pl & 1) {
-                  ap[pl] += pos;
-                  an[pl] += neg;
-                }
-              touched |= mk;
+                for (int pl = 0; pl < NP; ++pl)
+                  if (mk >> pl & 1) {
+                    ap[pl] += pos;
+                    an[pl] += neg;
+                  }
+                touched |= mk;
+              }
             }
-          }
-          flush(cur);
+            flush(cur);
+          };
+          if (p.n_pools <= 4) run(std::integral_constant<int, 4>{});
+          else run(std::integral_constant<int, 16>{});
           __syncwarp();
           continue;  // no TMA store for this epilogue
         }

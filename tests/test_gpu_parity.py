@@ -659,3 +659,16 @@ def test_cifar_loader_layout_feeds_the_convolver(ctx):
     out = ks.Convolver(ctx, filt, 32, 32, 3, None, normalize_patches=False)(ctx.matrix(row)).to_numpy()
     ref = ko.convolve(img, filt, 6, normalize=False)
     assert np.array_equal(np.transpose(out[0].reshape(27, 27, 32), (1, 0, 2)), ref)
+
+
+def test_least_squares_estimator_runs_the_selected_gpu_solver(ctx):
+    """K/nodes/learning/LeastSquaresEstimator.scala:63-87: the cost model picks a solver from (n, d, k, sparsity, machines) and the
+    fit runs it -- here the exact solver (LinearMapEstimator) for a small dense problem, checked against the oracle's closed form."""
+    rng = np.random.default_rng(17)
+    F = rng.standard_normal((2000, 60)); Y = rng.standard_normal((2000, 4))
+    est = ks.LeastSquaresEstimator(lam=0.5, num_machines=1, ctx=ctx)
+    model = est.fit(ctx.matrix(F), ctx.matrix(Y))
+    assert est.selected == "exact" and est.used == "exact"
+    x, ymu, mu = ko.linear_map_fit(F.astype(np.float32).astype(np.float64), Y.astype(np.float32).astype(np.float64), 0.5)
+    assert np.linalg.norm(model.xs[0] - x) / np.linalg.norm(x) < W_TOL
+    assert np.abs(model.b_opt - ymu).max() < 1e-6
