@@ -38,6 +38,23 @@ void launch_f64_to_f32_rows(const double* src, int64_t src_ld, float* dst, int64
   f64_to_f32_rows_kernel<<<grid_for(rows * dst_ld, 256), 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols);
 }
 
+// dense host-order rows -> pitched matrix rows, padding columns zeroed (the upload path stages contiguous H2D copies: a 1-D copy
+// runs at the link rate, a pitched 2-D copy of 1760-byte rows at a third of it)
+__global__ void f32_repitch_rows_kernel(const float* __restrict__ src, int64_t src_ld, float* __restrict__ dst, int64_t dst_ld,
+                                        int64_t rows, int64_t cols) {
+  const int64_t total = rows * dst_ld;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / dst_ld, c = i - r * dst_ld;
+    dst[i] = c < cols ? src[r * src_ld + c] : 0.f;
+  }
+}
+void launch_f32_repitch_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int64_t cols,
+                             cudaStream_t st) {
+  if (rows * dst_ld == 0) return;
+  f32_repitch_rows_kernel<<<grid_for(rows * dst_ld, 256), 256, 0, st>>>(src, src_ld, dst, dst_ld, rows, cols);
+}
+
 __global__ void f32_to_f64_rows_kernel(const float* __restrict__ src, int64_t src_ld, double* __restrict__ dst,
                                        int64_t dst_ld, int64_t rows, int64_t cols) {
   const int64_t total = rows * cols;

@@ -1532,26 +1532,33 @@ KS_API int32_t ks_ctx_launch_count(int64_t ctx, int64_t* out_count) {
 // ---------------------------------------------------------------- matrices
 static void upload_rows(Ctx& c, Matrix& m, const void* host, int64_t ld, bool is_f64) {
   if (m.rows == 0) return;
-  KS_CUDA(cudaMemsetAsync(m.d, 0, m.buf.bytes, c.st));
-  if (!is_f64) {
-    KS_CUDA(cudaMemcpy2DAsync(m.d, sizeof(float) * m.ld, host, sizeof(float) * ld, sizeof(float) * m.cols, m.rows,
-                              cudaMemcpyHostToDevice, c.st));
+  const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
+  if (!is_f64 && ld == m.cols && m.ld == m.cols) {  // same layout on both sides: one 1-D copy
+    KS_CUDA(cudaMemcpyAsync(m.d, host, esz * static_cast<size_t>(m.rows * m.cols), cudaMemcpyHostToDevice, c.st));
     KS_CUDA(cudaStreamSynchronize(c.st));
     return;
   }
-  // fp64 host data: stage in chunks of rows, convert on the device
-  const int64_t chunk_rows = std::max<int64_t>(1, (int64_t(256) << 20) / (8 * std::max<int64_t>(m.cols, 1)));
-  DevBuf stage;
-  stage.alloc(sizeof(double) * static_cast<size_t>(std::min(chunk_rows, m.rows) * m.cols));
-  const double* h = static_cast<const double*>(host);
-  for (int64_t r0 = 0; r0 < m.rows; r0 += chunk_rows) {
+  // Dense chunks of rows land in two alternating staging buffers by 1-D copies (2-D only when the host rows are themselves
+  // strided); a device kernel converts / re-pitches each chunk and zeroes the padding columns.  Everything is ordered on one
+  // stream, so a staging buffer is rewritten only after the kernel that read it; one synchronize at the end.
+  const int64_t chunk_rows =
+      std::min(m.rows, std::max<int64_t>(1, (int64_t(128) << 20) / static_cast<int64_t>(esz * std::max<int64_t>(m.cols, 1))));
+  DevBuf stage[2];
+  for (auto& sb : stage) sb.alloc(esz * static_cast<size_t>(chunk_rows * m.cols));
+  const char* h = static_cast<const char*>(host);
+  int which = 0;
+  for (int64_t r0 = 0; r0 < m.rows; r0 += chunk_rows, which ^= 1) {
     const int64_t nr = std::min(chunk_rows, m.rows - r0);
-    KS_CUDA(cudaMemcpy2DAsync(stage.p, sizeof(double) * m.cols, h + r0 * ld, sizeof(double) * ld, sizeof(double) * m.cols, nr,
-                              cudaMemcpyHostToDevice, c.st));
-    launch_f64_to_f32_rows(stage.as<double>(), m.cols, m.d + r0 * m.ld, m.ld, nr, m.cols, c.st);
+    const char* src = h + static_cast<size_t>(r0 * ld) * esz;
+    if (ld == m.cols)
+      KS_CUDA(cudaMemcpyAsync(stage[which].p, src, esz * static_cast<size_t>(nr * m.cols), cudaMemcpyHostToDevice, c.st));
+    else
+      KS_CUDA(cudaMemcpy2DAsync(stage[which].p, esz * m.cols, src, esz * ld, esz * m.cols, nr, cudaMemcpyHostToDevice, c.st));
+    if (is_f64) launch_f64_to_f32_rows(stage[which].as<double>(), m.cols, m.d + r0 * m.ld, m.ld, nr, m.cols, c.st);
+    else launch_f32_repitch_rows(stage[which].as<float>(), m.cols, m.d + r0 * m.ld, m.ld, nr, m.cols, c.st);
     c.launches += 1;
-    KS_CUDA(cudaStreamSynchronize(c.st));
   }
+  KS_CUDA(cudaStreamSynchronize(c.st));
 }
 
 KS_API int32_t ks_matrix_from_host_f64(int64_t ctx, const double* rowmajor, int64_t n_rows, int64_t n_cols, int64_t ld, int64_t* out_m) {
@@ -1589,24 +1596,7 @@ static void write_rows(Ctx& c, Matrix& m, int64_t row0, const void* host, int64_
   view.rows = n;
   view.cols = m.cols;
   view.ld = m.ld;
-  if (!is_f64) {
-    KS_CUDA(cudaMemcpy2DAsync(view.d, sizeof(float) * view.ld, host, sizeof(float) * ld, sizeof(float) * view.cols, n,
-                              cudaMemcpyHostToDevice, c.st));
-    KS_CUDA(cudaStreamSynchronize(c.st));
-    return;
-  }
-  const int64_t chunk_rows = std::max<int64_t>(1, (int64_t(256) << 20) / (8 * std::max<int64_t>(m.cols, 1)));
-  DevBuf stage;
-  stage.alloc(sizeof(double) * static_cast<size_t>(std::min(chunk_rows, n) * m.cols));
-  const double* h = static_cast<const double*>(host);
-  for (int64_t r0 = 0; r0 < n; r0 += chunk_rows) {
-    const int64_t nr = std::min(chunk_rows, n - r0);
-    KS_CUDA(cudaMemcpy2DAsync(stage.p, sizeof(double) * m.cols, h + r0 * ld, sizeof(double) * ld, sizeof(double) * m.cols, nr,
-                              cudaMemcpyHostToDevice, c.st));
-    launch_f64_to_f32_rows(stage.as<double>(), m.cols, view.d + r0 * m.ld, m.ld, nr, m.cols, c.st);
-    c.launches += 1;
-    KS_CUDA(cudaStreamSynchronize(c.st));
-  }
+  upload_rows(c, view, host, ld, is_f64);  // padding columns of the window are rewritten with zeros, as they already were
 }
 KS_API int32_t ks_matrix_write_rows_f64(int64_t ctx, int64_t m, int64_t row0, const double* rowmajor, int64_t n_rows, int64_t ld) {
   return guard(ctx, [&](Ctx& c) { write_rows(c, c.matrix(m), row0, rowmajor, n_rows, ld, true); });

@@ -73,6 +73,8 @@ cudaError_t launch_tri_inv_tiles(const double* L, int n, double* Dinv, cudaStrea
 size_t chol_solve_dinv_doubles(int n);
 
 // ---- element-wise / reduction helpers (aux_kernels.cu) ----
+void launch_f32_repitch_rows(const float* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int64_t cols,
+                             cudaStream_t st);
 void launch_f64_to_f32_rows(const double* src, int64_t src_ld, float* dst, int64_t dst_ld, int64_t rows, int64_t cols,
                             cudaStream_t st);
 void launch_f32_to_f64_rows(const float* src, int64_t src_ld, double* dst, int64_t dst_ld, int64_t rows, int64_t cols,

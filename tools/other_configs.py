@@ -1,5 +1,6 @@
 """The other solver configurations of BASELINE.json, timed on the GPU box with parity on a row subsample:
 
+  C1  MNIST random-FFT shape: 60000 x 784 -> 4 x PaddedFFT (D = 2048), k = 10, b = 2048, lambda = 0, with the full-size CPU oracle
   C2  N = 1M x D = 16384 materialised features (generated on the device, column mean 0.1), k = 100, b = 4096, lambda = 10, 1 GPU
   C4  N = 50K x D = 160000 direct synthetic features max(0, N(0,1)) (39 blocks of 4096 + one of 256), k = 10, lambda = 3000
   C5  BlockWeightedLeastSquares, N = 2M (or --c5-rows), d_in 440 -> D = 132 x 4096 cosine features, k = 147 class-sorted,
@@ -145,6 +146,39 @@ def c5():
           "solve_lanes": st["solve_lanes"], "launches": st["launches"], "finite": bool(all(np.isfinite(wj).all() for wj in m.xs))})
 
 
+def c1():
+    """C1 (MnistRandomFFT.scala:40-47 at its CPU-runnable size): synthetic 60000 x 784 pixel-scale rows, gather(RandomSignNode ->
+    PaddedFFT -> LinearRectifier(0)) x 4 -> D = 2048, BlockLeastSquaresEstimator(2048, 1, lambda = 0), k = 10; full-size oracle parity."""
+    n, d_in, nfft, k, bs, lam = 60_000, 784, 4, 10, 2048, 0.0
+    rng = np.random.default_rng(0)
+    X = rng.random((n, d_in), dtype=np.float32)
+    cls = rng.integers(0, k, n).astype(np.int32)
+    signs = [2.0 * rng.integers(0, 2, d_in) - 1.0 for _ in range(nfft)]
+    x = ctx.matrix(X)
+    y = ctx.labels_from_classes(cls, k)
+    branches = [ks.RandomSignNode(sg, ctx).andThen(ks.PaddedFFT(ctx)).andThen(ks.LinearRectifier(0.0, ctx=ctx)) for sg in signs]
+    feats = ks.Pipeline.gather(branches).andThen(ks.VectorCombiner())(x)
+    m, dt = timed_fit(ks.BlockLeastSquaresEstimator(bs, 1, lam, precision=args.precision), feats, y)
+    st = ctx.last_fit_stats()
+    rec = {"config": "C1 MnistRandomFFT-shaped 60000 x 784, numFFTs = 4 (D = 2048), k = 10, b = 2048, lambda = 0", "gpus": world,
+           "precision": st["mma"], "fit_s": dt, "samples_per_s": n / dt, "alg_tflops": 5.11e11 / dt / 1e12}
+    if world == 1:
+        from oracle import keystone_oracle as ko
+        t0 = time.perf_counter()
+        F = ko.mnist_random_fft_features(X.astype(np.float64), signs)
+        xs, b0, mus = ko.block_ls_fit(F, ko.class_label_indicators(cls, k), bs, 1, lam)
+        t_cpu = time.perf_counter() - t0
+        Wg, Wr = np.concatenate(m.xs, 0), np.concatenate(xs, 0)
+        pred = m.apply_argmax(feats)
+        ref = ko.block_linear_apply(F, xs, bs, b0, mus)
+        rec["cpu_oracle_s"] = t_cpu
+        rec["cpu_oracle_samples_per_s"] = n / t_cpu
+        rec["cpu_cores"] = os.cpu_count()
+        rec["parity"] = {"n_rows": n, "rel_fro_W": float(np.linalg.norm(Wg - Wr) / np.linalg.norm(Wr)),
+                         "argmax_agree": float((pred == np.argmax(ref, 1)).mean())}
+    emit(rec)
+
+
 def c4f():
     """C4 WITH its featurizer (RandomPatchCifar.scala:59-66): synthetic CIFAR-shaped images -> Convolver(20000 random 6x6x3 filters,
     whitener means, normalised patches) -> SymmetricRectifier(0.25) -> Pooler(13, 14, sum) -> D = 160000 features on the device ->
@@ -186,7 +220,7 @@ def c4f():
 
 
 for name in args.configs:
-    {"c2": c2, "c4": c4, "c4f": c4f, "c5": c5}[name]()
+    {"c1": c1, "c2": c2, "c4": c4, "c4f": c4f, "c5": c5}[name]()
 ctx.close()
 if world > 1:
     dist.destroy_process_group()
