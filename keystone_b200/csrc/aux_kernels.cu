@@ -774,31 +774,6 @@ void launch_pack_update16(const double* dW, double* Wmodel, const double* delta,
 }
 
 // ---- split-operand mode (fp16 x 2): v = hi + lo with hi = fp16(v), lo = fp16(v - hi)  (21 significant bits in two fp16)
-// slab: hi / lo planes of an fp32 matrix, plus the column sums of hi + lo (fp32 atomics; must be zeroed)
-__global__ void split_rows16_kernel(const float* __restrict__ src, int64_t ld_src, __half* __restrict__ hi, __half* __restrict__ lo,
-                                    int64_t ld_dst, int64_t rows, int cols, float* __restrict__ colsum, int64_t rows_per_block) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;  // one column per thread, coalesced along the row
-  if (c >= ld_dst) return;
-  const int64_t r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  float acc = 0.f;
-  for (int64_t r = r0; r < r1; ++r) {
-    const float v = c < cols ? src[r * ld_src + c] : 0.f;
-    const __half h = __float2half_rn(v);
-    const float hf = __half2float(h);
-    const __half l = __float2half_rn(v - hf);
-    hi[r * ld_dst + c] = h;
-    lo[r * ld_dst + c] = l;
-    acc += hf + __half2float(l);
-  }
-  if (colsum && c < cols) atomicAdd(colsum + c, acc);
-}
-void launch_split_rows16(const float* src, int64_t ld_src, void* hi, void* lo, int64_t ld_dst, int64_t rows, int cols, float* colsum,
-                         cudaStream_t st) {
-  if (rows == 0) return;
-  const int64_t rpb = 256;
-  dim3 grid(static_cast<unsigned>((ld_dst + 127) / 128), static_cast<unsigned>((rows + rpb - 1) / rpb));
-  split_rows16_kernel<<<grid, 128, 0, st>>>(src, ld_src, static_cast<__half*>(hi), static_cast<__half*>(lo), ld_dst, rows, cols, colsum, rpb);
-}
 // projection operands, concatenated along K so that ONE GEMM of depth 3 * cols accumulates hi*hi + lo*hi + hi*lo:
 //   pattern 0 (left operand X):  dst row = [ hi | lo | hi ],   pattern 1 (right operand W): dst row = [ hi | hi | lo ]
 __global__ void split_concat3_kernel(const float* __restrict__ src, int64_t ld_src, int64_t rows, int cols,

@@ -521,7 +521,7 @@ static void tmap_or_throw(CUtensorMap* m, const float* base, int64_t rows, int64
 }
 
 void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, void* slab_v, int64_t lds,
-                  int64_t row_begin, int64_t rows, bool round_out, float* colsum, cudaStream_t st, bool out16, bool x2) {
+                  int64_t row_begin, int64_t rows, bool round_out, float* colsum, cudaStream_t st, bool out16, bool x2, void* slab_lo) {
   if (rows <= 0 || cols <= 0) return;
   if (!st) st = c.st;
   float* slab = static_cast<float*>(slab_v);
@@ -551,9 +551,16 @@ void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* s
     tmap_or_throw(&k.tmA, src.xop.as<float>() + row_begin * src.X->ld, rows, src.d_in, src.X->ld, 128);
     tmap_or_throw(&k.tmB, src.Wall + c0 * src.ldw, cols, src.d_in, src.ldw, 256);
   }
-  if (out16) tmap16_or_throw(&k.tmOut, slab_v, rows, cols, lds, 32, 32, TMAP_NONE);
-  else tmap_or_throw(&k.tmOut, slab, rows, cols, lds, 32);
-  k.out16 = out16 ? 1 : 0;
+  if (slab_lo && !x2) throw KsError{KS_ERR_INVALID, "a lo plane needs the split operands"};
+  if (slab_lo) {  // the epilogue splits the unrounded value into the fp16 pair itself: no fp32 copy of the block, no second pass
+    tmap16_or_throw(&k.tmOut, slab_v, rows, cols, lds, 32, 32, TMAP_NONE);
+    tmap16_or_throw(&k.tmOut2, slab_lo, rows, cols, lds, 32, 32, TMAP_NONE);
+    k.out16 = 2;
+  } else {
+    if (out16) tmap16_or_throw(&k.tmOut, slab_v, rows, cols, lds, 32, 32, TMAP_NONE);
+    else tmap_or_throw(&k.tmOut, slab, rows, cols, lds, 32);
+    k.out16 = out16 ? 1 : 0;
+  }
   k.p.vec0 = src.ball + c0;
   k.p.vec1 = shift;
   k.p.colsum = colsum;
@@ -856,7 +863,8 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   if (x2) {
     slab_lo.reset(new DevBuf[NBUF]);
     for (int i = 0; i < NBUF; ++i) slab_lo[i].alloc(slab[i].bytes);
-    if (!src.F) sf32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));  // unrounded block before the split
+    if (!src.F && !f16)  // tf32 pairs of generated features: unrounded fp32 block before the split (fp16 pairs come out of the epilogue)
+      sf32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));
     bop_lo.alloc(bop.bytes);
   }
   cbias.alloc(sizeof(float) * kpad);
@@ -917,8 +925,10 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
         const int64_t ns = std::min<int64_t>(n_loc, c.sample_rows);
         KS_CUDA(cudaMemsetAsync(samp.p, 0, samp.bytes, ST));
         KS_CUDA(cudaMemsetAsync(ssum[buf].p, 0, ssum[buf].bytes, ST));
-        if (x2) produce_slab(c, src, c0, b, src.zeros.as<float>(), sf32.p, lds, 0, ns, /*round_out=*/false, ssum[buf].as<float>(), ST,
-                             false, true);
+        if (x2 && f16) produce_slab(c, src, c0, b, src.zeros.as<float>(), slab[buf].p, lds, 0, ns, /*round_out=*/false,
+                                    ssum[buf].as<float>(), ST, false, true, slab_lo[buf].p);
+        else if (x2) produce_slab(c, src, c0, b, src.zeros.as<float>(), sf32.p, lds, 0, ns, /*round_out=*/false, ssum[buf].as<float>(), ST,
+                                  false, true);
         else produce_slab(c, src, c0, b, src.zeros.as<float>(), slab[buf].p, lds, 0, ns, /*round_out=*/false,
                           ssum[buf].as<float>(), ST, f16);
         launch_f32_to_f64_rows(ssum[buf].as<float>(), lds, samp.as<double>(), bmax, 1, b, ST);  // 1 x b "matrix"
@@ -937,11 +947,14 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       launch_center_round(src.F->d, src.F->ld, static_cast<int>(c0), shifts[j]->as<float>(), slab[buf].as<float>(), cs, lds, n_loc, b,
                           ST, slab_lo[buf].as<float>());
       c.launches += 1;
+    } else if (x2 && f16) {  // fp16 pairs straight out of the projection's epilogue
+      produce_slab(c, src, c0, b, shifts[j]->as<float>(), slab[buf].p, lds, 0, n_loc, /*round_out=*/false, cs, ST, false, true,
+                   slab_lo[buf].p);
+      flops += 4.0 * static_cast<double>(n_loc) * src.d_in * b;  // two extra product terms of the projection
     } else if (x2) {
       produce_slab(c, src, c0, b, shifts[j]->as<float>(), sf32.p, lds, 0, n_loc, /*round_out=*/false, nullptr, ST, false, true);
-      if (f16) launch_split_rows16(sf32.as<float>(), lds, slab[buf].p, slab_lo[buf].p, lds, n_loc, b, cs, ST);
-      else launch_center_round(sf32.as<float>(), lds, 0, src.zeros.as<float>(), slab[buf].as<float>(), cs, lds, n_loc, b, ST,
-                               slab_lo[buf].as<float>());  // tf32 pairs
+      launch_center_round(sf32.as<float>(), lds, 0, src.zeros.as<float>(), slab[buf].as<float>(), cs, lds, n_loc, b, ST,
+                          slab_lo[buf].as<float>());  // tf32 pairs
       c.launches += 1;
       flops += 4.0 * static_cast<double>(n_loc) * src.d_in * b;  // two extra product terms of the projection
     } else {

@@ -279,7 +279,8 @@ void prepare_generated_operands(Ctx& c, FeatSrc& out, int precision);
 // out16: the slab is fp16 (lds in fp16 elements), generated features only
 void produce_slab(Ctx& c, FeatSrc& src, int64_t c0, int64_t cols, const float* shift, void* slab, int64_t lds,
                   int64_t row_begin, int64_t rows, bool round_out = true, float* colsum = nullptr, cudaStream_t st = nullptr,
-                  bool out16 = false, bool x2 = false);  // x2: unrounded fp32 slab from the K-concatenated split operands
+                  bool out16 = false, bool x2 = false,  // x2: unrounded slab from the K-concatenated split operands: fp32, or
+                  void* slab_lo = nullptr);             // (slab_lo given) the fp16 pair hi -> slab, lo -> slab_lo written by the epilogue
 const GramTile* gram_tiles(Ctx& c, int b, int kcols, bool with_g, bool with_c, bool pair, int* num_tiles);
 // f16: slab and R are fp16 matrices (leading dimensions in elements); G / C stay fp32
 void launch_gram_block(Ctx& c, const void* slab, int64_t lds, int64_t rows, int b, const void* R, int64_t ldr, int kcols,

@@ -51,12 +51,14 @@ struct KmParams {
 struct KmLaunch {
   CUtensorMap tmA, tmB;  // operands: box {32, 128} / {32, 256}, SWIZZLE_128B
   CUtensorMap tmOut;     // output: box {32, 32}, SWIZZLE_128B
+  CUtensorMap tmOut2;    // out16 == 2 only: the lo plane (same geometry as tmOut)
   KmParams p;
   int epi;
   int num_sms;
   int pair;  // 1: CTA-pair kernel (EPI_UPDATE / EPI_APPLY; tmB box is {32, 128}), 0: single-CTA persistent kernel
   int f16 = 0;   // 1: fp16 operands (EPI_UPDATE / EPI_APPLY on CTA pairs; boxes are {64, 128} fp16)
-  int out16 = 0; // 1: EPI_COS writes the slab as fp16 (tmOut: {32, 32} fp16 boxes, no swizzle)
+  int out16 = 0; // EPI_COS: 1 = the slab is written as fp16 (tmOut: {32, 32} fp16 boxes, no swizzle); 2 = as the fp16 pair hi + lo
+                 // of the unrounded value (tmOut, tmOut2)
 };
 
 int make_tmap_2d(CUtensorMap* out, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, bool atom32 = false);
@@ -140,9 +142,7 @@ void launch_round_colsum16(const float* R, void* R16, int64_t ld, int64_t rows, 
                            cudaStream_t st, void* R16lo = nullptr, unsigned* overflow = nullptr);  // *overflow = 1 if |R * scale| left fp16's range
 void launch_pack_update16(const double* dW, double* Wmodel, const double* delta, void* bop16, int ldb, float* cbias, int b, int k,
                           int kpad, const float* scale, cudaStream_t st, void* bop16_lo = nullptr);
-// split-operand mode: hi / lo fp16 planes of an fp32 matrix (+ column sums of hi + lo), and the K-concatenated projection operands
-void launch_split_rows16(const float* src, int64_t ld_src, void* hi, void* lo, int64_t ld_dst, int64_t rows, int cols, float* colsum,
-                         cudaStream_t st);
+// split-operand mode: the K-concatenated projection operands (the slab pair hi + lo comes out of the projection epilogue)
 void launch_split_concat3(const float* src, int64_t ld_src, int64_t rows, int cols, const float* scale, void* dst, int64_t ld_dst,
                           int pattern, cudaStream_t st);
 

@@ -385,11 +385,33 @@ __device__ __forceinline__ void stage_row_f16(uint8_t* buf, int lane, const floa
   }
 }
 
-// F16: fp16 operands (kind::f16); OUT16 (EPI_COS only): the slab is written as fp16 (tmOut: {32, 32} fp16 boxes, no swizzle).
-template <int EPI, bool F16, bool OUT16, int BN, int STAGES>
+// split flavour: v = hi + lo with hi = fp16(v), lo = fp16(v - hi); hi rows at buf, lo rows at buf + 2048 (same 64 B row layout)
+__device__ __forceinline__ void stage_row_f16x2(uint8_t* buf, int lane, const float (&o)[32]) {
+  uint4* row_hi = reinterpret_cast<uint4*>(buf + lane * 64);
+  uint4* row_lo = reinterpret_cast<uint4*>(buf + 2048 + lane * 64);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t wh[4], wl[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = o[8 * c + 2 * e], b = o[8 * c + 2 * e + 1];
+      const __half2 h = __floats2half2_rn(a, b);
+      const float2 hf = __half22float2(h);
+      const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+      wh[e] = *reinterpret_cast<const uint32_t*>(&h);
+      wl[e] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+    row_hi[c] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+    row_lo[c] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+  }
+}
+
+// F16: fp16 operands (kind::f16); OUT16 (EPI_COS only): 1 = the slab is written as fp16 (tmOut: {32, 32} fp16 boxes, no swizzle),
+// 2 = as two fp16 planes hi + lo of the unrounded value (tmOut / tmOut2), the operand pair of the split-operand Gram and update.
+template <int EPI, bool F16, int OUT16, int BN, int STAGES>
 __global__ void __launch_bounds__(kKmThreads, 1)
 gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                   const __grid_constant__ CUtensorMap tmOut, KmParams p) {
+                   const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2, KmParams p) {
   using Cfg = KmCfg<F16, BN, STAGES>;
   static_assert(BN == 256, "epilogue column split assumes BN == 256");
   extern __shared__ uint8_t smem_raw[];
@@ -631,25 +653,37 @@ gemm_kmajor_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // an fp16 chunk is 2 KB: the 4 KB staging buffer holds two, so one store may still be reading while the next chunk
         // is staged (4 chunks per tile: the halves alternate consistently from tile to tile)
         uint8_t* const sbuf = buf;
-        uint8_t* buf = OUT16 ? sbuf + ((c0 >> 5) & 1) * 2048 : sbuf;
+        uint8_t* buf = OUT16 == 1 ? sbuf + ((c0 >> 5) & 1) * 2048 : sbuf;  // the hi + lo pair fills both halves
         if (lane == 0) {  // the store that last used this staging slot has finished reading it
-          if (OUT16) bulk_wait_read1();
+          if (OUT16 == 1) bulk_wait_read1();
           else bulk_wait_read0();
         }
         __syncwarp();
-        if (OUT16) stage_row_f16(buf, lane, o);
+        if (OUT16 == 2) stage_row_f16x2(buf, lane, o);
+        else if (OUT16 == 1) stage_row_f16(buf, lane, o);
         else stage_row_sw128(buf, lane, o);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (p.flags & KM_FLAG_REDUCE) tma_reduce_add_2d(&tmOut, buf, n0 + c0, m0 + q * 32);
-          else tma_store_2d(&tmOut, buf, n0 + c0, m0 + q * 32);
+          if (OUT16 == 2) {
+            tma_store_2d(&tmOut, buf, n0 + c0, m0 + q * 32);
+            tma_store_2d(&tmOut2, buf + 2048, n0 + c0, m0 + q * 32);
+          } else if (p.flags & KM_FLAG_REDUCE) {
+            tma_reduce_add_2d(&tmOut, buf, n0 + c0, m0 + q * 32);
+          } else {
+            tma_store_2d(&tmOut, buf, n0 + c0, m0 + q * 32);
+          }
           bulk_commit();
         }
         if (EPI == EPI_COS && p.colsum != nullptr) {
           // column sums of the chunk straight from the staged copy: lane c adds column c over the 32 rows
           float cs = 0.f;
-          if (OUT16) {
+          if (OUT16 == 2) {
+#pragma unroll
+            for (int r = 0; r < 32; ++r)
+              cs += __half2float(*reinterpret_cast<const __half*>(buf + r * 64 + lane * 2)) +
+                    __half2float(*reinterpret_cast<const __half*>(buf + 2048 + r * 64 + lane * 2));
+          } else if (OUT16 == 1) {
 #pragma unroll
             for (int r = 0; r < 32; ++r) cs += __half2float(*reinterpret_cast<const __half*>(buf + r * 64 + lane * 2));
           } else {
@@ -933,7 +967,7 @@ cudaError_t launch_gram(const GramLaunch& g, cudaStream_t st) {
   return launch_gram_t<256, kGramStageRows, 4>(g, st);
 }
 
-template <int EPI, bool F16, bool OUT16, int BN, int STAGES>
+template <int EPI, bool F16, int OUT16, int BN, int STAGES>
 static cudaError_t launch_km_t(const KmLaunch& k, cudaStream_t st) {
   using Cfg = KmCfg<F16, BN, STAGES>;
   auto kern = gemm_kmajor_kernel<EPI, F16, OUT16, BN, STAGES>;
@@ -948,7 +982,7 @@ static cudaError_t launch_km_t(const KmLaunch& k, cudaStream_t st) {
   const long long total = static_cast<long long>(m_tiles) * n_tiles;
   if (total == 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>(total < k.num_sms ? total : k.num_sms);
-  kern<<<grid, kKmThreads, Cfg::SMEM_BYTES, st>>>(k.tmA, k.tmB, k.tmOut, k.p);
+  kern<<<grid, kKmThreads, Cfg::SMEM_BYTES, st>>>(k.tmA, k.tmB, k.tmOut, OUT16 == 2 ? k.tmOut2 : k.tmOut, k.p);
   return cudaGetLastError();
 }
 
@@ -982,19 +1016,20 @@ static cudaError_t launch_km2_t(const KmLaunch& k, cudaStream_t st) {
 }
 
 cudaError_t launch_kmajor(const KmLaunch& k, cudaStream_t st) {
-  if (k.epi == EPI_POOL) return k.f16 ? launch_km_t<EPI_POOL, true, false, 256, 3>(k, st) : cudaErrorInvalidValue;
-  if (k.epi == EPI_APPLY && k.f16 && !k.pair) return launch_km_t<EPI_APPLY, true, false, 256, 3>(k, st);  // K-concatenated fp16 operands
+  if (k.epi == EPI_POOL) return k.f16 ? launch_km_t<EPI_POOL, true, 0, 256, 3>(k, st) : cudaErrorInvalidValue;
+  if (k.epi == EPI_APPLY && k.f16 && !k.pair) return launch_km_t<EPI_APPLY, true, 0, 256, 3>(k, st);  // K-concatenated fp16 operands
   if (k.f16 && k.epi == EPI_UPDATE) return launch_km2_t<EPI_UPDATE, true, 4>(k, st);
   if (k.f16 && k.epi == EPI_APPLY) return launch_km2_t<EPI_APPLY, true, 4>(k, st);
-  if (k.out16 && k.f16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, true, true, 256, 3>(k, st);
-  if (k.f16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, true, false, 256, 3>(k, st);  // fp16 operands, fp32 slab (split mode)
-  if (k.out16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, false, true, 256, 3>(k, st);
+  if (k.out16 == 2 && k.epi == EPI_COS) return k.f16 ? launch_km_t<EPI_COS, true, 2, 256, 3>(k, st) : cudaErrorInvalidValue;
+  if (k.out16 && k.f16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, true, 1, 256, 3>(k, st);
+  if (k.f16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, true, 0, 256, 3>(k, st);  // fp16 operands, fp32 slab (split mode, tf32 pairs)
+  if (k.out16 && k.epi == EPI_COS) return launch_km_t<EPI_COS, false, 1, 256, 3>(k, st);
   if (k.pair && k.epi == EPI_UPDATE) return launch_km2_t<EPI_UPDATE, false, 4>(k, st);
   if (k.pair && k.epi == EPI_APPLY) return launch_km2_t<EPI_APPLY, false, 4>(k, st);
   switch (k.epi) {
-    case EPI_COS: return launch_km_t<EPI_COS, false, false, 256, 3>(k, st);
-    case EPI_UPDATE: return launch_km_t<EPI_UPDATE, false, false, 256, 3>(k, st);
-    case EPI_APPLY: return launch_km_t<EPI_APPLY, false, false, 256, 3>(k, st);
+    case EPI_COS: return launch_km_t<EPI_COS, false, 0, 256, 3>(k, st);
+    case EPI_UPDATE: return launch_km_t<EPI_UPDATE, false, 0, 256, 3>(k, st);
+    case EPI_APPLY: return launch_km_t<EPI_APPLY, false, 0, 256, 3>(k, st);
     default: return cudaErrorInvalidValue;
   }
 }

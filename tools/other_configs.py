@@ -32,6 +32,7 @@ ap.add_argument("--precision", default="f16x2")
 ap.add_argument("--c5-rows", type=int, default=2_000_000)
 ap.add_argument("--c5-blocks", type=int, default=132)
 ap.add_argument("--c4-rows", type=int, default=50_000)
+ap.add_argument("--c1-lambdas", type=float, nargs="*", default=[0.0, 1.0, 100.0])
 ap.add_argument("--parity-rows", type=int, default=8192)
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -96,12 +97,10 @@ def c4():
     n, d, k, bs, lam = args.c4_rows, 160_000, 10, 4096, 3000.0
     lo, hi = ks.shard_range(n, rank, world)
     rng = np.random.default_rng([3, lo])
-    # pooled rectified responses: max(0, N(0,1)), generated in row chunks on the host (32 GB in total at full size: per rank n / world rows)
-    parts = []
-    for r0 in range(0, hi - lo, 4096):
-        parts.append(np.maximum(rng.standard_normal((min(4096, hi - lo - r0), d), dtype=np.float32), 0))
-    f = ctx.matrix_from_partitions(parts)
-    del parts
+    # pooled rectified responses max(0, N(0,1)), generated on the device (32 GB in total at full size: n / world rows per rank)
+    g = ctx.synthetic_normal(hi - lo, d, seed=3, global_row_offset=lo)
+    f = ks.LinearRectifier(0.0, 0.0, ctx)(g)
+    del g
     cls = rng.integers(0, k, hi - lo).astype(np.int32)
     y = ctx.labels_from_classes(cls, k)
     m, dt = timed_fit(ks.BlockLeastSquaresEstimator(bs, 1, lam, precision=args.precision), f, y)
@@ -148,8 +147,20 @@ def c5():
 
 def c1():
     """C1 (MnistRandomFFT.scala:40-47 at its CPU-runnable size): synthetic 60000 x 784 pixel-scale rows, gather(RandomSignNode ->
-    PaddedFFT -> LinearRectifier(0)) x 4 -> D = 2048, BlockLeastSquaresEstimator(2048, 1, lambda = 0), k = 10; full-size oracle parity."""
-    n, d_in, nfft, k, bs, lam = 60_000, 784, 4, 10, 2048, 0.0
+    PaddedFFT -> LinearRectifier(0)) x 4 -> D = 2048, BlockLeastSquaresEstimator(2048, 1, lambda), k = 10; full-size oracle parity.
+    The pipeline's default lambda is 0: the 512 cosine bins of a 784-sample signal padded to 1024 are numerically dependent
+    (time-bandwidth product ~392), so the Gram matrix is close to singular; the device path factorises with Cholesky and reports
+    it (the reference's LU returns some solution).  Each lambda of --c1-lambdas is one record."""
+    for lam in args.c1_lambdas:
+        try:
+            c1_one(float(lam))
+        except ks.KeystoneError as e:
+            emit({"config": f"C1 MnistRandomFFT-shaped 60000 x 784, numFFTs = 4 (D = 2048), k = 10, b = 2048, lambda = {lam}", "gpus": world,
+                  "error": str(e)})
+
+
+def c1_one(lam):
+    n, d_in, nfft, k, bs = 60_000, 784, 4, 10, 2048
     rng = np.random.default_rng(0)
     X = rng.random((n, d_in), dtype=np.float32)
     cls = rng.integers(0, k, n).astype(np.int32)
@@ -160,7 +171,7 @@ def c1():
     feats = ks.Pipeline.gather(branches).andThen(ks.VectorCombiner())(x)
     m, dt = timed_fit(ks.BlockLeastSquaresEstimator(bs, 1, lam, precision=args.precision), feats, y)
     st = ctx.last_fit_stats()
-    rec = {"config": "C1 MnistRandomFFT-shaped 60000 x 784, numFFTs = 4 (D = 2048), k = 10, b = 2048, lambda = 0", "gpus": world,
+    rec = {"config": f"C1 MnistRandomFFT-shaped 60000 x 784, numFFTs = 4 (D = 2048), k = 10, b = 2048, lambda = {lam}", "gpus": world,
            "precision": st["mma"], "fit_s": dt, "samples_per_s": n / dt, "alg_tflops": 5.11e11 / dt / 1e12}
     if world == 1:
         from oracle import keystone_oracle as ko
@@ -220,7 +231,10 @@ def c4f():
 
 
 for name in args.configs:
-    {"c1": c1, "c2": c2, "c4": c4, "c4f": c4f, "c5": c5}[name]()
+    try:
+        {"c1": c1, "c2": c2, "c4": c4, "c4f": c4f, "c5": c5}[name]()
+    except ks.KeystoneError as e:          # one failing configuration must not lose the others (same error on every rank)
+        emit({"config": name, "gpus": world, "error": str(e)})
 ctx.close()
 if world > 1:
     dist.destroy_process_group()
