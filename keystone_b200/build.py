@@ -54,10 +54,12 @@ def build(force: bool = False, verbose: bool = True) -> str:
     if force or _stale(LIB, objs):
         # cudart is linked statically so the library loads (and exports its symbols) on a box without a GPU driver;
         # cuSOLVER / NCCL / the driver entry point for cuTensorMapEncodeTiled are resolved at run time.
-        cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-cudart", "static", "-ldl", "-lpthread"]
+        # linked under a temporary name and renamed: a snapshot of the tree never sees a half-written library
+        cmd = [nvcc, "-shared", "-o", LIB + ".tmp"] + objs + ["-cudart", "static", "-ldl", "-lpthread"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+        os.replace(LIB + ".tmp", LIB)
     return LIB
 
 

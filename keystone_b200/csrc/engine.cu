@@ -814,7 +814,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   const bool x2 = precision == KS_PRECISION_F16X2 && (src.F || src.proj_x2);
   const bool f16 = !src.F && src.kind == 0 && (precision == KS_PRECISION_F16 || x2);
   const size_t es = f16 ? 2 : 4;  // bytes per slab / operand element
-  const int64_t x2_chunk = 2048;  // short accumulation chains: the tensor core's fp32 accumulate truncates (~2^-25 per MMA step)
+  const int64_t x2_chunk = c.split_chunk_rows;  // short accumulation chains: the tensor core's fp32 accumulate truncates (~2^-25 per MMA step)
   // look-ahead of the residual-independent work (projection, G-Gram, factorisation) over the residual chain, in blocks.  With the
   // rows sharded over GPUs the Cholesky of block t+1 (2.5 ms alone, more next to tensor kernels) sits in a dependency cycle
   // G(t+1) -> factor(t+1) -> solve(t+1) -> update(t+1) -> ... -> G(t+1+LA): a deeper look-ahead spreads it over more blocks.
@@ -1520,6 +1520,7 @@ KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value) {
   return guard(ctx, [&](Ctx& c) {
     const std::string n = name ? name : "";
     if (n == "gram_chunk_rows" && (value == 0 || value >= kGramStageRows)) c.gram_chunk_rows = value;
+    else if (n == "split_chunk_rows" && value >= kGramStageRows && value % kGramStageRows == 0) c.split_chunk_rows = value;
     else if (n == "sample_rows" && value >= 1) c.sample_rows = value;
     else if (n == "gram_pair") c.gram_pair = value != 0;
     else if (n == "epi_multi") c.epi_multi = value != 0;
