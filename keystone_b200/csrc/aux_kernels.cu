@@ -319,11 +319,53 @@ void launch_delta_mean(const float* ssum, const float* shift, double n_total, do
   delta_mean_kernel<<<(b + 255) / 256, 256, 0, st>>>(ssum, shift, n_total, delta, mean, b);
 }
 
+// ------------------------------------------------------------------ exact Gram diagonal of a split slab
+// out[c] += sum_r (hi[r][c] + lo[r][c])^2 in fp64 (out must be zeroed).  The tensor core chops every product of an MMA step at
+// the accumulator's granularity, toward zero: entries whose products all have one sign -- the diagonal of S^T S -- lose
+// ~7.5e-8 of their value per step of the accumulation chain, zero-mean entries lose nothing (profiles/r2_trunc_probe.txt).
+// The split-operand mode therefore takes the diagonal from this reduction instead of from the tensor core.
+template <class T2>
+__device__ __forceinline__ float2 pair_to_float2(T2 v);
+template <>
+__device__ __forceinline__ float2 pair_to_float2<__half2>(__half2 v) { return __half22float2(v); }
+template <>
+__device__ __forceinline__ float2 pair_to_float2<float2>(float2 v) { return v; }
+
+template <class T2>
+__global__ void colsumsq_pair_kernel(const T2* __restrict__ hi, const T2* __restrict__ lo, int64_t ld2, int64_t rows, int cols,
+                                     double* __restrict__ out, int64_t rows_per_block) {
+  const int c2 = blockIdx.x * blockDim.x + threadIdx.x;  // column pair 2 c2, 2 c2 + 1: coalesced along the row
+  if (2 * c2 >= cols) return;
+  const int64_t r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+  for (int64_t r = r0; r < r1; ++r) {
+    const float2 h = pair_to_float2<T2>(hi[r * ld2 + c2]), l = pair_to_float2<T2>(lo[r * ld2 + c2]);
+    const double v0 = static_cast<double>(h.x) + static_cast<double>(l.x), v1 = static_cast<double>(h.y) + static_cast<double>(l.y);
+    a0 = fma(v0, v0, a0);
+    a1 = fma(v1, v1, a1);
+  }
+  atomicAdd(out + 2 * c2, a0);
+  if (2 * c2 + 1 < cols) atomicAdd(out + 2 * c2 + 1, a1);
+}
+void launch_colsumsq_pair(const void* hi, const void* lo, bool f16, int64_t ld, int64_t rows, int cols, double* out, cudaStream_t st) {
+  if (rows == 0 || cols == 0) return;
+  const int64_t rpb = 512;
+  dim3 grid(static_cast<unsigned>((cols / 2 + 1 + 127) / 128), static_cast<unsigned>((rows + rpb - 1) / rpb));
+  if (f16)
+    colsumsq_pair_kernel<__half2><<<grid, 128, 0, st>>>(static_cast<const __half2*>(hi), static_cast<const __half2*>(lo), ld / 2, rows,
+                                                         cols, out, rpb);
+  else
+    colsumsq_pair_kernel<float2><<<grid, 128, 0, st>>>(static_cast<const float2*>(hi), static_cast<const float2*>(lo), ld / 2, rows, cols,
+                                                        out, rpb);
+}
+
 // ------------------------------------------------------------------ reduced system assembly (fp64)
 // cross (optional, split-operand mode): full b x b matrix S_hi^T S_lo; the Gram of S = S_hi + S_lo is then
 // S_hi^T S_hi + cross + cross^T (the lo x lo term, ~2^-22 of the diagonal, is dropped)
 __global__ void build_system_kernel(const float* __restrict__ G, int ldg, const double* __restrict__ delta, double n_total,
-                                    double lam, double* __restrict__ H, int b, const float* __restrict__ cross) {
+                                    double lam, double* __restrict__ H, int b, const float* __restrict__ cross,
+                                    const double* __restrict__ exact_diag) {
   const int64_t total = static_cast<int64_t>(b) * b;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -331,13 +373,14 @@ __global__ void build_system_kernel(const float* __restrict__ G, int ldg, const 
     const int lo = min(r, c), hi = max(r, c);
     double g = static_cast<double>(G[static_cast<int64_t>(lo) * ldg + hi]);  // upper triangle is the computed one
     if (cross) g += static_cast<double>(cross[static_cast<int64_t>(r) * ldg + c]) + static_cast<double>(cross[static_cast<int64_t>(c) * ldg + r]);
+    if (exact_diag && r == c) g = exact_diag[r];  // launch_colsumsq_pair: the tensor core's diagonal is biased low
     H[i] = g - n_total * delta[r] * delta[c] + (r == c ? lam : 0.0);
   }
 }
 void launch_build_system(const float* G, int ldg, const double* delta, double n_total, double lam, double* H, int b,
-                         cudaStream_t st, const float* cross) {
+                         cudaStream_t st, const float* cross, const double* exact_diag) {
   if (b == 0) return;
-  build_system_kernel<<<grid_for(static_cast<int64_t>(b) * b, 256), 256, 0, st>>>(G, ldg, delta, n_total, lam, H, b, cross);
+  build_system_kernel<<<grid_for(static_cast<int64_t>(b) * b, 256), 256, 0, st>>>(G, ldg, delta, n_total, lam, H, b, cross, exact_diag);
 }
 
 __global__ void build_rhs_kernel(const float* __restrict__ C, int ldc, const double* __restrict__ delta,

@@ -827,6 +827,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   std::unique_ptr<DevBuf[]> slab_lo;
   std::unique_ptr<DevBuf[]> slab(new DevBuf[NBUF]), gbuf(new DevBuf[NBUF]), Hbuf(new DevBuf[NBUF]), ssum(new DevBuf[NBUF]);
   std::unique_ptr<DevBuf[]> Dbuf(new DevBuf[NBUF]);  // inverted diagonal tiles of the factors (operand of the library's own solve)
+  std::unique_ptr<DevBuf[]> dsq(new DevBuf[NBUF]);   // parity mode: exact diagonal of S^T S (fp64), see launch_colsumsq_pair
   r_f32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * kpad));
   r_op.alloc(f16 ? r_f32.bytes / 2 : r_f32.bytes);
   if (x2) r_lo.alloc(r_op.bytes);
@@ -863,6 +864,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
   if (x2) {
     slab_lo.reset(new DevBuf[NBUF]);
     for (int i = 0; i < NBUF; ++i) slab_lo[i].alloc(slab[i].bytes);
+    for (int i = 0; i < NBUF; ++i) dsq[i].alloc(sizeof(double) * lds);
     if (!src.F && !f16)  // tf32 pairs of generated features: unrounded fp32 block before the split (fp16 pairs come out of the epilogue)
       sf32.alloc(sizeof(float) * static_cast<size_t>(std::max<int64_t>(n_loc, 1) * lds));
     bop_lo.alloc(bop.bytes);
@@ -961,6 +963,11 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       produce_slab(c, src, c0, b, shifts[j]->as<float>(), slab[buf].p, lds, 0, n_loc, true, cs, ST, f16);
     }
     if (!src.F) flops += 2.0 * static_cast<double>(n_loc) * src.d_in * b;
+    if (x2 && it == 0) {  // the diagonal of this block's Gram matrix, exactly (the tensor core's is biased low: aux_kernels.cu)
+      KS_CUDA(cudaMemsetAsync(dsq[buf].p, 0, dsq[buf].bytes, ST));
+      launch_colsumsq_pair(slab[buf].p, slab_lo[buf].p, f16, lds, n_loc, b, dsq[buf].as<double>(), ST);
+      c.launches += 1;
+    }
     c.span_end(ST);
     KS_CUDA(cudaEventRecord(ev_slab[t], ST));
   };
@@ -990,6 +997,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
       c.span_begin(PH_ALLREDUCE, SG);
       c.allreduce_on(gbuf[buf].p, g_elems * (x2 ? 2 : 1), false, commG, SG);
       c.allreduce_on(ssum[buf].p, static_cast<size_t>(b), false, commG, SG);
+      if (x2) c.allreduce_on(dsq[buf].p, static_cast<size_t>(b), true, commG, SG);
       c.span_end(SG);
       KS_CUDA(cudaEventRecord(ev_g[t], SG));
     } else {
@@ -1017,7 +1025,7 @@ static int64_t fit_blockls(Ctx& c, FeatSrc& src, Matrix& Y, int bs, int num_iter
     c.span_begin(PH_SOLVE, SF);
     launch_delta_mean(ssum[buf].as<float>(), shifts[j]->as<float>(), n_total_d, deltas[j]->as<double>(), model->mean[j]->as<double>(), b, SF);
     launch_build_system(gbuf[buf].as<float>(), ldg, deltas[j]->as<double>(), n_total_d, lam, Hj, b, SF,
-                        x2 ? gbuf[buf].as<float>() + g_elems : nullptr);
+                        x2 ? gbuf[buf].as<float>() + g_elems : nullptr, x2 ? dsq[buf].as<double>() : nullptr);
     c.launches += 2;
     c.potrf(Hj, b, info_slot++, SF);
     if (Dj) {  // inverses of the factor's 64 x 64 diagonal tiles: the in-tile substitutions of the solve become DMMA products

@@ -195,7 +195,7 @@ struct Ctx {
   std::string stats_json;
   int64_t launches = 0;
   int64_t gram_chunk_rows = 0;  // rows of the contraction per Gram CTA (pair); 0 = chosen from the local row count (engine.cu)
-  int64_t split_chunk_rows = 2048;  // the same in the parity mode: short accumulation chains (the tensor core's fp32 accumulate truncates)
+  int64_t split_chunk_rows = 4096;  // the same in the parity mode: short accumulation chains (the tensor core chops products at the accumulator granularity)
   int gram_pair = 1;  // CTA-pair (cta_group::2) Gram kernel
   int epi_multi = 1;  // CTA-pair kernels: 8 rotating epilogue staging buffers per warp (0: one buffer, store-and-wait)
   int proj_f16 = 1;   // fp16 mode: the projection GEMM X W^T runs with fp16 operands too (0: tf32 operands, fp16 slab)

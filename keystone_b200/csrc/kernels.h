@@ -100,7 +100,10 @@ void launch_divide_by_count(const double* sums, const double* count, float* out,
 void launch_delta_mean(const float* ssum, const float* shift, double n_total, double* delta, double* mean, int b, cudaStream_t st);
 // H (fp64, column-major b x b, ld = b) = sym(G) - n * delta delta^T + lam * I
 void launch_build_system(const float* G, int ldg, const double* delta, double n_total, double lam, double* H, int b,
-                         cudaStream_t st, const float* cross = nullptr);  // cross: S_hi^T S_lo (full b x b, ld = ldg), split mode
+                         cudaStream_t st, const float* cross = nullptr,  // cross: S_hi^T S_lo (full b x b, ld = ldg), split mode
+                         const double* exact_diag = nullptr);            // split mode: the diagonal from launch_colsumsq_pair
+// out[c] (fp64, zeroed) += sum_r (hi[r][c] + lo[r][c])^2: the Gram diagonal of a split slab (fp16 or fp32 planes, ld elements)
+void launch_colsumsq_pair(const void* hi, const void* lo, bool f16, int64_t ld, int64_t rows, int cols, double* out, cudaStream_t st);
 // RHS (fp64 column-major b x k, ld = b) = C[:, :k] - n * delta * rbar^T - lam * Wold
 void launch_build_rhs(const float* C, int ldc, const double* delta, const double* rsum, double n_total, double lam,
                       const double* Wold, double* rhs, int b, int k, cudaStream_t st, const float* c_scale = nullptr);
