@@ -84,7 +84,9 @@ KS_API int32_t ks_ctx_synchronize(int64_t ctx);
  * one stream, solve / factor chains beside it; 0: the two-stream arrangement of round 1], "host_mirror" [1: fits copy each
  * finished model block into pinned host memory while they run]; "custom_solve" [-1: automatic -- the library's own DMMA
  * multi-right-hand-side triangular solve kernel when a rank solves <= 512 columns (multi-GPU), cusolverDnDpotrs otherwise; 0 / 1 force], "dyn_tiles" [1: the projection kernel draws its tiles from a
- * counter], "lookahead" [0 = automatic: blocks the residual-independent work runs ahead, 1 on one GPU, 2 on several], "solve_lanes" [4: concurrent per-class solves of the weighted solver]. */
+ * counter], "lookahead" [0 = automatic: blocks the residual-independent work runs ahead, 1 on one GPU, 2 on several], "solve_lanes" [4: concurrent per-class solves of the weighted solver],
+ * "split_chunk_rows" [4096: rows per accumulation chain of the parity mode's Gram launches; the tensor core's accumulation error grows with
+ * the chain, DESIGN.md 6]. */
 KS_API int32_t ks_ctx_set_option(int64_t ctx, const char* name, int64_t value);
 
 /* ---- row-sharded matrices (this rank's rows) ---------------------------------------------
